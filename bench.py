@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""Benchmark of the fused flow hot path (contract: see the task statement / DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload q256|r64|m128] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch: ``Flow.log_prob`` on B rows followed by ``Flow.sample`` of
+B rows (inverse direction).  Default workload (BASELINE.json configs[2], the one the north-star target and the
+1/2/4/8-GPU metric are quoted on): CouplingRQNSF(n_dim=256), B = 2^20 rows per GPU, fp32, random-init weights
+from the constructor under seed 0 with ActNorm data-initialised on the benchmark data (state T of SURVEY 8d).
+Multi-GPU: one process per GPU (torchrun), the batch is sharded, there is no data-path collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through the public
+API with pinned host buffers (H2D of x, D2H of log_prob and of the samples inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, D, rows per GPU, cpu chunk rows, cpu rows per bounded sample)
+    'q256': ('CouplingRQNSF', 256, 1 << 20, 8192, 32768),
+    'r64': ('RealNVP', 64, 1 << 20, 65536, 1 << 20),
+    'm128': ('MAF', 128, 1 << 18, 2048, 16384),
+    'mq128': ('MaskedAutoregressiveRQNSF', 128, 1 << 18, 512, 1024),
+}
+
+
+def algorithmic_bytes(D):
+    """SURVEY 8d, whole-flow kernels: log_prob reads x (4D) and writes one float; sample-from-given-z reads z and
+    writes x (8D)."""
+    return 4 * D + 4, 8 * D
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(',')]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(self.rows[0][1]),
+                'power_w_max': max(float(r[2]) for r in self.rows), 'reasons': reasons, 'samples': len(self.rows)}
+
+
+def build_flow(preset, D, device=None, init_rows=None):
+    """Random-init weights exactly as the constructor makes them under seed 0; ActNorm data-initialised by one
+    training-mode pass over `init_rows` (state T)."""
+    import torch
+    from torchflows_b200 import Flow
+    import torchflows_b200.architectures as arch
+    torch.manual_seed(0)
+    flow = Flow(getattr(arch, preset)(D))
+    if device is not None:
+        flow = flow.to(device)
+        if init_rows is not None:
+            flow.train()
+            with torch.no_grad():
+                flow.log_prob(init_rows)
+        flow.eval()
+    return flow
+
+
+def cpu_oracle_throughput(preset, D, state_dict, chunk, rows, steps, warmup, seed=1):
+    """The reference's CPU path (oracle/flow_oracle.py: the same ATen CPU ops in the same order, validated bit for
+    bit against the real reference) on all host cores: log_prob + sample over `rows` rows in chunks of `chunk`."""
+    import torch
+    from oracle.flow_oracle import OracleFlow
+    torch.set_num_threads(os.cpu_count() or 1)
+    o = OracleFlow(preset, (D,), state_dict)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(rows, D, generator=g)
+    z = torch.randn(rows, D, generator=g)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            for s in range(0, rows, chunk):
+                o.log_prob(x[s:s + chunk])
+            for s in range(0, rows, chunk):
+                o.sample_from_noise(z[s:s + chunk])
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return rows / t, t, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    preset, D, B, chunk, cpu_rows = WORKLOADS[args.workload]
+    flow = build_flow(preset, D)           # CPU module: only a weight container here
+    flow.eval()
+    sd = flow.state_dict()
+    value, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, args.steps, args.warmup)
+    sample = f'{cpu_rows} rows in chunks of {chunk} per step (log_prob + sample), state E weights'
+    line = {
+        'impl': 'reference', 'metric': 'log_prob+sample samples/s', 'value': value, 'unit': 'samples/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{preset} n_dim={D}: log_prob + sample, CPU (oracle port of the reference, torch CPU ops)',
+                   'rows_per_step': cpu_rows, 'chunk': chunk},
+        'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    preset, D, B, chunk, cpu_rows = WORKLOADS[args.workload]
+    if args.rows:
+        B = args.rows
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(B, D, device=dev, generator=g)
+    z = torch.randn(B, D, device=dev, generator=g)
+    flow = build_flow(preset, D, dev, init_rows=x[:65536])
+    by_lp, by_s = algorithmic_bytes(D)
+
+    def step():
+        lp = flow.log_prob(x)
+        xs = flow._sample_from_base(z, no_grad=True)
+        return lp, xs
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        sync_all()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+        ev[0].record(stream)
+        for i in range(args.steps):
+            lp = flow.log_prob(x)
+            ev[3 * i + 1].record(stream)
+            xs = flow._sample_from_base(z, no_grad=True)
+            ev[3 * i + 2].record(stream)
+            ev[3 * i + 3].record(stream)
+        sync_all()
+        total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+        lp_ms = [ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)]
+        s_ms = [ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]
+        sampler.stop_flag = True
+        sampler.join(timeout=3)
+        del xs
+
+        # ---- end to end through the public API: pinned host buffers in, host buffers out -----------------------
+        e2e_steps = max(2, min(args.steps, 5))
+        nchunk = 8
+        rows_c = (B + nchunk - 1) // nchunk
+        x_host = torch.empty(B, D, pin_memory=True)
+        x_host.copy_(x)
+        lp_host = torch.empty(B, pin_memory=True)
+        xs_host = torch.empty(B, D, pin_memory=True)
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def e2e_step():
+            # chunked so that the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i
+            events = []
+            for s in range(0, B, rows_c):
+                with torch.cuda.stream(copy_stream):
+                    xc = x_host[s:s + rows_c].to(dev, non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(copy_stream)
+                stream.wait_event(e)
+                lpc = flow.log_prob(xc)
+                xc.record_stream(stream)
+                lp_host[s:s + rows_c].copy_(lpc, non_blocking=True)
+            for s in range(0, B, rows_c):
+                n = min(rows_c, B - s)
+                xsc = flow.sample(n, no_grad=True)                       # draws z on the device, inverse pass
+                done = torch.cuda.Event()
+                done.record(stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done)
+                    xs_host[s:s + n].copy_(xsc, non_blocking=True)
+                    xsc.record_stream(copy_stream)
+                events.append(done)
+            stream.wait_stream(copy_stream)
+
+        e2e_step()
+        sync_all()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        t1.record(stream)
+        sync_all()
+        e2e_ms = t0.elapsed_time(t1) / e2e_steps
+
+    # max over ranks
+    times = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(times[0]), float(times[1])
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    lp_avg_ms, s_avg_ms = statistics.mean(lp_ms), statistics.mean(s_ms)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
+    achieved = by_lp * B / (lp_avg_ms * 1e-3) / 1e9
+
+    line = {
+        'metric': 'log_prob+sample samples/s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{preset} n_dim={D}, {B} rows per GPU: Flow.log_prob + Flow.sample (inverse pass)',
+                   'weights': 'random init (seed 0), ActNorm data-initialised (state T)', 'rows_per_gpu': B,
+                   'l2': f'inputs larger than L2 ({B * D * 4 >> 20} MiB per tensor)', 'precision_mode': 'default (SFU after bin search)'},
+        'log_prob_samples_per_s': world * B / (lp_avg_ms * 1e-3), 'sample_samples_per_s': world * B / (s_avg_ms * 1e-3),
+        'roofline': {'bound': 'hbm', 'kernel': 'b2f::flow_kernel (log_prob launch)', 'achieved': achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+                     'peak_source': peak_src, 'algorithmic_bytes_per_row': by_lp, 'launch_ms': lp_avg_ms,
+                     'sample_launch': {'achieved': by_s * B / (s_avg_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_row': by_s,
+                                       'launch_ms': s_avg_ms}},
+        'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': B * D * 4,
+                'd2h_bytes_per_step': B * 4 + B * D * 4, 'ms_per_step': e2e_ms},
+        'gpu_launches': 2 * args.steps,
+        'clocks': sampler.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sd = {k: v.cpu() for k, v in flow.state_dict().items()}
+        v, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, 3, 1)
+        line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'{cpu_rows} rows in chunks of {chunk} (log_prob + sample), median of 3'}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='q256', choices=sorted(WORKLOADS))
+    ap.add_argument('--rows', type=int, default=0, help='override rows per GPU')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -51,7 +51,7 @@ def build_product(force=False, verbose_ptxas=False):
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError('nvcc failed')
-    _run([NVCC, '-shared', '-o', PRODUCT_SO] + objs + ['-lcudart'])
+    _run([NVCC, '-shared', '-o', PRODUCT_SO] + objs + ['-cudart', 'static'])
     return PRODUCT_SO
 
 

@@ -1,0 +1,128 @@
+/* b2f.h -- C ABI of libb2f.so: hand-written sm_100a kernels for the coupling / masked-autoregressive
+ * bijection hot path of torchflows (v1.2.0), called from torchflows_b200's torch.autograd.Functions.
+ *
+ * The reference has no FFI boundary (it is pure Python on PyTorch eager); the entry points below are
+ * what a maintainer would bind with ctypes from the reference's own classes.
+ * Each one names the reference code it replaces, file:line relative to /root/reference/torchflows.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers to DEVICE memory (fp32, contiguous, row-major), sizes as integers, `stream` is a
+ *     cudaStream_t passed as void*; no torch types;
+ *   - the caller owns every buffer; kernels read inputs, write outputs; no allocation, no host sync;
+ *   - return 0 on success, a negative B2F_ERR_* code otherwise; b2f_last_error() gives the message of
+ *     the last failure on the calling thread;  nothing throws;
+ *   - there is no CPU path: without a CUDA device every compute entry point fails with B2F_ERR_CUDA.
+ */
+#ifndef B2F_H_
+#define B2F_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2F_OK 0
+#define B2F_ERR_INVALID (-1)     /* bad shape / null pointer / inconsistent arguments */
+#define B2F_ERR_UNSUPPORTED (-2) /* configuration outside the fused hot path */
+#define B2F_ERR_CUDA (-3)        /* CUDA runtime error (message in b2f_last_error) */
+
+/* Formula applied to each transformed element (transformers/linear/affine.py, transformers/spline/). */
+enum b2f_transformer {
+    B2F_T_SHIFT_ADD = 0,  /* Shift.forward           z = x + u0              affine.py:149-153 */
+    B2F_T_SHIFT_SUB = 1,  /* Shift.inverse           x = z - u0              affine.py:155-159 */
+    B2F_T_AFFINE_FWD = 2, /* Affine.forward / InverseAffine.inverse  z = a*x + u1, ld = +log a   affine.py:39-48 */
+    B2F_T_AFFINE_INV = 3, /* Affine.inverse / InverseAffine.forward  x = (z-u1)/a, ld = -log a   affine.py:50-59 */
+    B2F_T_RQ_FWD = 4,     /* RationalQuadratic.forward   spline/base.py:53-60, rational_quadratic.py:65-128 */
+    B2F_T_RQ_INV = 5      /* RationalQuadratic.inverse   spline/base.py:65-72, rational_quadratic.py:130-200 */
+};
+
+/* One step of a flow program = one layer of BijectiveComposition (bijections/base.py:203-232) applied
+ * in the direction the caller chose. */
+enum b2f_op_kind {
+    B2F_OP_ELEMENTWISE = 0, /* ElementwiseAffine / ActNorm with global parameters  layers_base.py:300-318, layers.py:19-69
+                               p[0] = value (D,2); tkind = AFFINE_FWD or AFFINE_INV */
+    B2F_OP_FLIP = 1,        /* ReversePermutationMatrix forward or inverse         matrix/permutation.py:19-37 */
+    B2F_OP_COUPLING = 2,    /* CouplingBijection with HalfSplit + FeedForward(n_layers=2, Tanh)
+                               layers_base.py:119-163, coupling_masks.py:78-81, transforms.py:293-307
+                               p[0]=W1 (H,Ds)  p[1]=b1 (H)  p[2]=W2 tile layout (Dt,H,PP)  p[3]=b2 (Dt*P) */
+    B2F_OP_MADE = 3,        /* MaskedAutoregressiveBijection, one-pass direction    layers_base.py:202-211, transforms.py:184-266
+                               p[0]=W1*mask (H,D)  p[1]=b1  p[2]=(W2*mask) tile layout (D,H,PP)  p[3]=b2 (D*P) */
+    B2F_OP_MADE_SEQ = 4     /* the D-step sequential direction                      layers_base.py:213-223
+                               as B2F_OP_MADE plus p[4] = int32 finalisation step of each hidden unit (H) */
+};
+
+/* W2 "tile layout": the reference's last Linear weight (Dt*P, H) (output index e*P+p, layers_base.py:143)
+ * re-laid-out as [e][j][p] with p padded to PP = b2f_padded_params(P), so that the P parameters of one
+ * element for one hidden unit are one aligned vector. */
+
+#define B2F_MAX_OPS 40
+#define B2F_FLAG_SEQ_LOGDET_EXACT 1 /* op flag: MADE_SEQ sums the true per-dimension log-dets instead of
+                                       reproducing the reference's last-iteration value */
+
+typedef struct b2f_op {
+    int32_t kind;     /* enum b2f_op_kind */
+    int32_t tkind;    /* enum b2f_transformer */
+    int32_t n_hidden; /* H */
+    int32_t n_bins;   /* RQ only (the fused program supports 8; b2f_transformer_apply supports 1..64) */
+    float boundary;   /* RQ only */
+    int32_t flags;
+    const void *p[6]; /* parameters, see enum b2f_op_kind */
+    void *g[6];       /* b2f_flow_backward only: gradient buffers with the layout of p[i] (accumulated into) */
+} b2f_op_t;
+
+/* flags of b2f_flow_apply */
+#define B2F_FLOW_LOGP_OF_INPUT 1 /* log_prob = base_log_prob(x_in) + log_det  (Flow.sample(return_log_prob=True),
+                                    flows.py:710-712) instead of base_log_prob(y) + log_det (flows.py:646-648) */
+#define B2F_FLOW_MODE_PRECISE 2  /* accurate libm-grade exp/log everywhere (default: SFU approximations after
+                                    the bin search; knots and bin indices are identical in both modes) */
+
+/* Runs `n_ops` layers over x:(B,D) in ONE kernel: y:(B,D) (nullable), log_det:(B) (nullable),
+ * log_prob:(B) (nullable; adds the DiagonalGaussian log-density with base_loc / base_log_scale:(D),
+ * both nullable = standard normal).  Replaces BijectiveComposition.forward / inverse
+ * (bijections/base.py:203-232) + Flow.forward_with_log_prob (flows.py:628-648) + DiagonalGaussian.log_prob
+ * (base_distributions/gaussian.py:46-54).  The caller lists ops in application order (for the inverse
+ * direction: reversed layers with inverse transformer kinds). */
+int b2f_flow_apply(const b2f_op_t *ops, int32_t n_ops, const float *x, float *y, float *log_det, float *log_prob,
+                   const float *base_loc, const float *base_log_scale, int64_t B, int32_t D, int32_t flags,
+                   void *stream);
+
+/* Backward of b2f_flow_apply in the density direction: given the saved input x and upstream gradients
+ * gy:(B,D) (nullable), glog_det:(B) (nullable), glog_prob:(B) (nullable), recomputes the forward per tile and
+ * produces gx:(B,D) (nullable) and accumulates parameter gradients into ops[i].g[].  Replaces autograd
+ * through the same reference code.  `workspace` holds the saved layer inputs: b2f_flow_backward_workspace()
+ * bytes. */
+int b2f_flow_backward(const b2f_op_t *ops, int32_t n_ops, const float *x, const float *gy, const float *glog_det,
+                      const float *glog_prob, const float *base_loc, const float *base_log_scale, float *gx,
+                      void *workspace, int64_t B, int32_t D, int32_t flags, void *stream);
+int64_t b2f_flow_backward_workspace(const b2f_op_t *ops, int32_t n_ops, int64_t B, int32_t D);
+
+/* Elementwise transformer given materialised parameters h (TensorTransformer.forward / inverse,
+ * transformers/base.py:24-42): x,out:(n_rows, n_event); h:(n_rows, n_event, P) with row stride
+ * h_row_stride floats (0 broadcasts one parameter set over all rows, as ElementwiseBijection.prepare_h does,
+ * layers_base.py:300-303); log_det:(n_rows) (nullable) = sum over the event; k_out:(n_rows, n_event) int32
+ * (nullable, RQ only) = the bin index used, -1 outside the spline bounds. */
+int b2f_transformer_apply(int32_t tkind, const float *x, const float *h, float *out, float *log_det,
+                          int32_t *k_out, int64_t n_rows, int32_t n_event, int64_t h_row_stride, int32_t n_bins,
+                          float boundary, int32_t flags, void *stream);
+
+/* Backward of b2f_transformer_apply: upstream gout:(n_rows,n_event) (nullable), glog_det:(n_rows) (nullable)
+ * -> gx:(n_rows,n_event), gh:(n_rows,n_event,P) (dense, row stride n_event*P). */
+int b2f_transformer_backward(int32_t tkind, const float *x, const float *h, const float *gout,
+                             const float *glog_det, float *gx, float *gh, int64_t n_rows, int32_t n_event,
+                             int64_t h_row_stride, int32_t n_bins, float boundary, int32_t flags, void *stream);
+
+/* Per-dimension batch statistics for ActNorm's data-dependent initialisation (layers.py:58-68):
+ * sum:(D) and sumsq:(D) of x:(B,D), accumulated in fp64 (must be zeroed by the caller). */
+int b2f_column_stats(const float *x, double *sum, double *sumsq, int64_t B, int32_t D, void *stream);
+
+/* Parameters per element of a transformer kind, and its padded count PP used by the W2 tile layout. */
+int32_t b2f_params_per_element(int32_t tkind, int32_t n_bins);
+int32_t b2f_padded_params(int32_t params_per_element);
+
+const char *b2f_last_error(void);
+int32_t b2f_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2F_H_ */

@@ -1,0 +1,141 @@
+"""GPU tests of the backward kernel and Flow.fit against reference autograd / the reference's fit loop."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def build(preset, event_shape, kwargs, state_dict, dev):
+    import torchflows_b200.architectures as arch
+    from torchflows_b200 import Flow
+    flow = Flow(getattr(arch, preset)(event_shape, **kwargs))
+    flow.load_state_dict(state_dict)
+    return flow.to(dev)
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('idx', range(7))
+def test_gradients_vs_reference_autograd(golden, dev, idx):
+    """P4: loss = _base_batch_loss (flows.py:199-224); every parameter gradient and dloss/dx against the
+    reference's autograd (fp32).  Bar: relative L2 per tensor 1e-3 (the reference's own fp32 gradients are 6e-4
+    from its fp64 gradients for spline knots, tests/test_c_oracle_and_hostmath.py), 1e-4 for affine flows."""
+    c = golden('grads.pt')[idx]
+    flow = build(c['preset'], c['event_shape'], c['kwargs'], c['state_dict'], dev).eval()
+    x = c['x'].to(dev).requires_grad_(True)
+    loss = flow._base_batch_loss((x, c['w'].to(dev)))
+    loss.backward()
+    assert abs(float(loss) - float(c['loss'])) <= 1e-5 * (1 + abs(float(c['loss'])))
+    tol = 2e-3 if 'RQNSF' in c['preset'] else 1e-4
+    assert rel(x.grad, c['grad_x']) < tol, ('grad_x', rel(x.grad, c['grad_x']))
+    params = dict(flow.named_parameters())
+    checked = 0
+    for k, g in c['grads'].items():
+        if g.numel() == 0:
+            continue
+        assert params[k].grad is not None, k
+        if g.norm() == 0:
+            assert params[k].grad.abs().max().item() < 1e-6, k
+        else:
+            assert rel(params[k].grad, g) < tol, (k, rel(params[k].grad, g))
+        checked += 1
+    assert checked >= 6
+
+
+def test_input_gradient_is_finite_like_reference_test(dev):
+    """test/test_autograd_bijections.py:41-54 re-pointed at this package."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import NICE, RealNVP, CouplingRQNSF, MAF, MaskedAutoregressiveRQNSF
+    for cls in (NICE, RealNVP, CouplingRQNSF, MAF, MaskedAutoregressiveRQNSF):
+        for batch_shape, event_shape in (((1,), (2,)), ((5, 2, 3), (3, 5, 2))):
+            torch.manual_seed(0)
+            flow = Flow(cls(event_shape)).to(dev)
+            x = torch.randn(*batch_shape, *event_shape, device=dev, requires_grad=True)
+            lp = flow.log_prob(x)
+            assert lp.shape == batch_shape and torch.isfinite(lp).all()
+            g = torch.autograd.grad(lp.mean(), x)[0]
+            assert g.shape == x.shape and torch.isfinite(g).all()
+
+
+@pytest.mark.parametrize('idx', range(3))
+def test_fit_loss_trajectory(golden, dev, idx):
+    """P5: the inner loop of BaseFlow.fit (flows.py:379-398), full batch, 20 AdamW steps from identical weights:
+    loss trajectory within 1e-3 relative of the reference's."""
+    c = golden('fit.pt')[idx]
+    flow = build(c['preset'], c['event_shape'], {}, c['state_dict0'], dev)
+    flow.train()
+    x = c['x'].to(dev)
+    w = torch.ones(len(x), device=dev)
+    opt = torch.optim.AdamW(flow.parameters(), lr=c['lr'])
+    losses = []
+    for _ in range(20):
+        opt.zero_grad()
+        loss = flow._base_batch_loss((x, w))
+        losses.append(float(loss))
+        loss.backward()
+        opt.step()
+    for i, (a, b) in enumerate(zip(losses, c['losses'])):
+        assert abs(a - b) <= 1e-3 * (1 + abs(b)), (i, a, b)
+    flow.eval()
+    with torch.no_grad():
+        lp = flow.log_prob(x).cpu()
+    assert (lp - c['log_prob20']).abs().max().item() <= 5e-2 * (1 + c['log_prob20'].abs().max().item())
+
+
+def test_readme_example(dev):
+    """README.md:9-31: fit RealNVP(3) to 1000 standard-normal points, then log_prob and sample(50)."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import RealNVP
+    torch.manual_seed(0)
+    n_data, n_dim = 1000, 3
+    x = torch.randn(n_data, n_dim)
+    flow = Flow(RealNVP(n_dim)).to(dev)
+    flow.fit(x, show_progress=False)
+    with torch.no_grad():
+        log_prob = flow.log_prob(x)
+        x_new = flow.sample(50)
+    assert log_prob.shape == (n_data,) and x_new.shape == (50, n_dim)
+    assert abs(float(log_prob.mean()) - (-4.26)) < 0.1       # reference: -4.263, true N(0,I): -4.265
+    assert not flow.training
+
+
+def test_fit_gaussian_statistical(dev):
+    """test/test_fit.py:81-126 (local_only in the reference), shortened: after fitting N(0, diag sigma^2) the
+    sample std is within rtol 0.1 of sigma."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import RealNVP, CouplingRQNSF
+    for cls in (RealNVP, CouplingRQNSF):
+        torch.manual_seed(0)
+        sigma = torch.tensor([0.1, 1.0, 10.0])
+        x = torch.randn(10000, 3) * sigma
+        flow = Flow(cls(3)).to(dev)
+        flow.fit(x, n_epochs=150, lr=0.05 if cls is RealNVP else 0.01)
+        with torch.no_grad():
+            s = flow.sample(100000).std(dim=0).cpu()
+        assert torch.allclose(s, sigma, rtol=0.1), (cls.__name__, s)
+
+
+def test_fit_options_smoke(dev):
+    """test/test_fit.py:132-182 shapes of the API: tiny data, validation data, early stopping, adaptive batches,
+    deepcopy before / after (test/test_deepcopy.py)."""
+    from copy import deepcopy
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import MAF, NICE
+    torch.manual_seed(0)
+    for n_train in (1, 10, 2200):
+        flow = Flow(NICE((2, 3))).to(dev)
+        deepcopy(flow)
+        flow.fit(torch.randn(n_train, 2, 3), n_epochs=2, x_val=torch.randn(7, 2, 3), early_stopping=True)
+        deepcopy(flow)
+    flow = Flow(MAF(4)).to(dev)
+    flow.fit(torch.randn(5000, 4), n_epochs=12, batch_size='adaptive', w_train=torch.rand(5000))
+    assert not flow.training

@@ -1,0 +1,149 @@
+"""ctypes binding of libb2f.so (include/b2f.h).  There is no fallback: if the library is missing or the
+tensors are not CUDA fp32 the call fails loudly."""
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libb2f.so')
+
+# enum b2f_transformer
+T_SHIFT_ADD, T_SHIFT_SUB, T_AFFINE_FWD, T_AFFINE_INV, T_RQ_FWD, T_RQ_INV = range(6)
+# enum b2f_op_kind
+OP_ELEMENTWISE, OP_FLIP, OP_COUPLING, OP_MADE, OP_MADE_SEQ = range(5)
+MAX_OPS = 40
+FLAG_SEQ_LOGDET_EXACT = 1
+FLOW_LOGP_OF_INPUT = 1
+FLOW_MODE_PRECISE = 2
+
+INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
+                T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}
+
+
+class B2FError(RuntimeError):
+    pass
+
+
+class Op(ctypes.Structure):
+    """struct b2f_op (include/b2f.h)."""
+    _fields_ = [('kind', ctypes.c_int32), ('tkind', ctypes.c_int32), ('n_hidden', ctypes.c_int32),
+                ('n_bins', ctypes.c_int32), ('boundary', ctypes.c_float), ('flags', ctypes.c_int32),
+                ('p', ctypes.c_void_p * 6), ('g', ctypes.c_void_p * 6)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2FError(f'{LIB_PATH} is missing: build it with `python build_native.py product` '
+                           '(torchflows_b200 has no CPU or PyTorch fallback for its kernels)')
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+        L.b2f_last_error.restype = ctypes.c_char_p
+        L.b2f_abi_version.restype = i32
+        L.b2f_params_per_element.argtypes = [i32, i32]
+        L.b2f_padded_params.argtypes = [i32]
+        L.b2f_flow_apply.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+        L.b2f_flow_backward.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+        L.b2f_flow_backward_workspace.argtypes = [ctypes.POINTER(Op), i32, i64, i32]
+        L.b2f_flow_backward_workspace.restype = i64
+        L.b2f_transformer_apply.argtypes = [i32, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
+        L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
+        L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B2FError(f'libb2f error {rc}: {lib().b2f_last_error().decode()}')
+
+
+def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise B2FError(f'{name} must be a CUDA tensor: torchflows_b200 runs this path only as sm_100a kernels '
+                       f'(no CPU fallback); got device {t.device}')
+    if t.dtype != torch.float32:
+        raise B2FError(f'{name} must be float32, got {t.dtype}')
+    return t.contiguous()
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def make_ops(ops: Sequence[dict]):
+    """ops: dicts with kind, tkind, n_hidden, n_bins, boundary, flags, p (list of tensors), g (list of tensors)."""
+    if len(ops) > MAX_OPS:
+        raise B2FError(f'flow program of {len(ops)} ops exceeds B2F_MAX_OPS={MAX_OPS}')
+    arr = (Op * max(len(ops), 1))()
+    for i, o in enumerate(ops):
+        a = arr[i]
+        a.kind, a.tkind = o['kind'], o.get('tkind', 0)
+        a.n_hidden, a.n_bins = o.get('n_hidden', 0), o.get('n_bins', 0)
+        a.boundary, a.flags = o.get('boundary', 0.0), o.get('flags', 0)
+        for j, t in enumerate(o.get('p', [])):
+            a.p[j] = None if t is None else t.data_ptr()
+        for j, t in enumerate(o.get('g', [])):
+            a.g[j] = None if t is None else t.data_ptr()
+    return arr
+
+
+def flow_apply(ops: Sequence[dict], x: torch.Tensor, want_y=True, want_log_det=True, want_log_prob=False,
+               base_loc=None, base_log_scale=None, flags=0):
+    """x: (B, D) CUDA fp32 contiguous.  Returns (y | None, log_det | None, log_prob | None)."""
+    x = require_cuda_f32(x, 'flow input')
+    B, D = x.shape
+    y = torch.empty_like(x) if want_y else None
+    ld = torch.empty(B, device=x.device, dtype=torch.float32) if want_log_det else None
+    lp = torch.empty(B, device=x.device, dtype=torch.float32) if want_log_prob else None
+    arr = make_ops(ops)
+    with torch.cuda.device(x.device):
+        check(lib().b2f_flow_apply(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
+                                   ptr(base_log_scale), B, D, flags, stream_ptr(x.device)))
+    return y, ld, lp
+
+
+def transformer_apply(tkind, x2: torch.Tensor, h: torch.Tensor, h_row_stride: int, n_bins=8, boundary=50.0,
+                      want_bins=False, flags=0):
+    """x2: (n_rows, E).  h: any CUDA fp32 tensor whose rows are h_row_stride floats apart."""
+    x2 = require_cuda_f32(x2, 'transformer input')
+    h = require_cuda_f32(h, 'transformer parameters')
+    n_rows, E = x2.shape
+    out = torch.empty_like(x2)
+    ld = torch.empty(n_rows, device=x2.device, dtype=torch.float32)
+    k = torch.empty((n_rows, E), device=x2.device, dtype=torch.int32) if want_bins else None
+    with torch.cuda.device(x2.device):
+        check(lib().b2f_transformer_apply(tkind, ptr(x2), ptr(h), ptr(out), ptr(ld), ptr(k), n_rows, E, h_row_stride,
+                                          n_bins, boundary, flags, stream_ptr(x2.device)))
+    return out, ld, k
+
+
+def transformer_backward(tkind, x2, h, h_row_stride, gout, gld, n_bins=8, boundary=50.0, flags=0):
+    n_rows, E = x2.shape
+    P = lib().b2f_params_per_element(tkind, n_bins)
+    gx = torch.empty_like(x2)
+    gh = torch.empty((n_rows, E, P), device=x2.device, dtype=torch.float32)
+    with torch.cuda.device(x2.device):
+        check(lib().b2f_transformer_backward(tkind, ptr(x2), ptr(h), ptr(gout), ptr(gld), ptr(gx), ptr(gh), n_rows, E,
+                                             h_row_stride, n_bins, boundary, flags, stream_ptr(x2.device)))
+    return gx, gh
+
+
+def column_stats(x2: torch.Tensor):
+    """Per-column sum and sum of squares of x2:(B, D) in fp64 (ActNorm initialisation)."""
+    B, D = x2.shape
+    s = torch.zeros(D, device=x2.device, dtype=torch.float64)
+    q = torch.zeros(D, device=x2.device, dtype=torch.float64)
+    with torch.cuda.device(x2.device):
+        check(lib().b2f_column_stats(ptr(x2), ptr(s), ptr(q), B, D, stream_ptr(x2.device)))
+    return s, q

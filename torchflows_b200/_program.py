@@ -1,0 +1,196 @@
+"""Lowering of bijection layers to libb2f flow programs and the autograd bridge.
+
+A *lowered op* describes one layer applied in one direction:
+
+    LoweredOp(kind, tkind, leafs=[module parameters], consts=[buffers], n_hidden, n_bins, boundary, flags, owner)
+
+``leafs`` are the reference-layout parameters (what ``state_dict`` holds); the kernels want the last
+Linear weight in *tile layout* ([element][hidden][param], see include/b2f.h) and MADE weights pre-multiplied
+by their masks, so ``kernel_params`` derives those once per parameter version and caches them on the layer.
+``FlowFunction`` is the single ``torch.autograd.Function`` through which every fused call goes.
+"""
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+
+
+@dataclass
+class LoweredOp:
+    kind: int
+    tkind: int = 0
+    leafs: List[torch.Tensor] = field(default_factory=list)    # differentiable inputs (reference layout)
+    consts: List[torch.Tensor] = field(default_factory=list)   # masks, finalisation steps
+    n_hidden: int = 0
+    n_bins: int = 0
+    boundary: float = 0.0
+    flags: int = 0
+    owner: Optional[torch.nn.Module] = None                    # cache holder
+
+
+def params_per_element(tkind: int, n_bins: int) -> int:
+    return {N.T_SHIFT_ADD: 1, N.T_SHIFT_SUB: 1, N.T_AFFINE_FWD: 2, N.T_AFFINE_INV: 2}.get(tkind, 3 * n_bins - 1)
+
+
+def padded(P: int) -> int:
+    return P if P <= 2 else (P + 3) // 4 * 4
+
+
+def to_tile_layout(W2: torch.Tensor, n_elem: int, P: int) -> torch.Tensor:
+    """(n_elem*P, H) with row index e*P+p  ->  (n_elem, H, PP) zero padded, contiguous."""
+    H = W2.shape[1]
+    t = W2.reshape(n_elem, P, H).transpose(1, 2)
+    PP = padded(P)
+    if PP != P:
+        t = torch.nn.functional.pad(t, (0, PP - P))
+    return t.contiguous()
+
+
+def from_tile_layout(G: torch.Tensor, n_elem: int, P: int) -> torch.Tensor:
+    """Inverse of to_tile_layout for gradients: (n_elem, H, PP) -> (n_elem*P, H)."""
+    return G[..., :P].transpose(1, 2).reshape(n_elem * P, G.shape[1])
+
+
+def kernel_params(op: LoweredOp) -> List[Optional[torch.Tensor]]:
+    """Tensors in the layout b2f_op.p[] expects (cached per parameter version on op.owner)."""
+    if op.kind == N.OP_FLIP:
+        return []
+    if op.kind == N.OP_ELEMENTWISE:
+        return [op.leafs[0].detach().reshape(-1, 2).contiguous()]
+    W1, b1, W2, b2 = op.leafs
+    key = (op.kind, op.tkind)
+    ver = tuple((t.data_ptr(), t._version) for t in op.leafs)
+    cache = getattr(op.owner, '_b2f_cache', None)
+    if cache is None:
+        cache = {}
+        if op.owner is not None:
+            object.__setattr__(op.owner, '_b2f_cache', cache)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    P = params_per_element(op.tkind, op.n_bins)
+    n_elem = W2.shape[0] // P
+    with torch.no_grad():
+        if op.kind == N.OP_COUPLING:
+            out = [W1.detach().contiguous(), b1.detach().contiguous(), to_tile_layout(W2.detach(), n_elem, P),
+                   b2.detach().contiguous()]
+        else:
+            m1, m2 = op.consts[0], op.consts[1]
+            out = [(W1.detach() * m1).contiguous(), b1.detach().contiguous(),
+                   to_tile_layout(W2.detach() * m2, n_elem, P), b2.detach().contiguous()]
+            if op.kind == N.OP_MADE_SEQ:
+                out.append(op.consts[2])
+    cache[key] = (ver, out)
+    return out
+
+
+def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None):
+    out = []
+    for i, op in enumerate(ops):
+        out.append(dict(kind=op.kind, tkind=op.tkind, n_hidden=op.n_hidden, n_bins=op.n_bins, boundary=op.boundary,
+                        flags=op.flags, p=kernel_params(op), g=(grads[i] if grads is not None else [])))
+    return out
+
+
+class _Cfg:
+    """Non-tensor arguments of FlowFunction."""
+
+    def __init__(self, ops, want_log_prob, base_loc, base_log_scale, flags):
+        self.ops, self.want_log_prob = list(ops), want_log_prob
+        self.base_loc, self.base_log_scale, self.flags = base_loc, base_log_scale, flags
+
+
+class FlowFunction(torch.autograd.Function):
+    """y, log_det, log_prob = program(x).  Forward: one b2f_flow_apply launch.  Backward: one
+    b2f_flow_backward launch that recomputes the conditioner outputs per tile (h is never materialised)."""
+
+    @staticmethod
+    def forward(ctx, x2, cfg: _Cfg, *leafs):
+        y, ld, lp = N.flow_apply(op_dicts(cfg.ops), x2, True, True, cfg.want_log_prob, cfg.base_loc,
+                                 cfg.base_log_scale, cfg.flags)
+        ctx.cfg = cfg
+        ctx.save_for_backward(x2, *leafs)
+        if lp is None:
+            lp = x2.new_empty(0)
+            ctx.mark_non_differentiable(lp)
+        return y, ld, lp
+
+    @staticmethod
+    def backward(ctx, gy, gld, glp):
+        cfg = ctx.cfg
+        x2 = ctx.saved_tensors[0]
+        ops = cfg.ops
+        if any(op.kind == N.OP_MADE_SEQ for op in ops):
+            raise NotImplementedError('backward through the sequential direction of a masked autoregressive layer '
+                                      '(IAF density / MAF sampling gradients) is not part of the fused hot path yet')
+        if cfg.flags & N.FLOW_LOGP_OF_INPUT:
+            raise NotImplementedError('backward of Flow.sample(return_log_prob=True) is not fused yet')
+        dev = x2.device
+        grads, leaf_grads = [], []
+        for op in ops:
+            kp = kernel_params(op)
+            g = [None] * len(kp)
+            if op.kind == N.OP_ELEMENTWISE:
+                if op.leafs[0].requires_grad:
+                    g[0] = torch.zeros_like(kp[0])
+            elif op.kind in (N.OP_COUPLING, N.OP_MADE):
+                if any(t.requires_grad for t in op.leafs):
+                    g = [torch.zeros_like(t) for t in kp[:4]]
+            grads.append(g)
+        B, D = x2.shape
+        arr = N.make_ops(op_dicts(ops, grads))
+        ws_bytes = N.lib().b2f_flow_backward_workspace(arr, len(ops), B, D)
+        ws = torch.empty(max(int(ws_bytes), 4) // 4, device=dev, dtype=torch.float32)
+        need_gx = ctx.needs_input_grad[0]
+        gx = torch.empty_like(x2)
+
+        def c(t):
+            return None if t is None else t.contiguous()
+        glp_ = c(glp) if (cfg.want_log_prob and glp is not None) else None
+        with torch.cuda.device(dev):
+            N.check(N.lib().b2f_flow_backward(arr, len(ops), N.ptr(x2), N.ptr(c(gy)), N.ptr(c(gld)), N.ptr(glp_),
+                                              N.ptr(cfg.base_loc), N.ptr(cfg.base_log_scale), N.ptr(gx), N.ptr(ws),
+                                              B, D, cfg.flags, N.stream_ptr(dev)))
+        for op, g in zip(ops, grads):
+            if op.kind == N.OP_ELEMENTWISE:
+                leaf_grads.append(None if g[0] is None else g[0].reshape(op.leafs[0].shape))
+            elif op.kind in (N.OP_COUPLING, N.OP_MADE):
+                if g[0] is None:
+                    leaf_grads.extend([None] * 4)
+                    continue
+                P = params_per_element(op.tkind, op.n_bins)
+                n_elem = op.leafs[2].shape[0] // P
+                gW1, gb1, gW2, gb2 = g[0], g[1], from_tile_layout(g[2], n_elem, P), g[3]
+                if op.kind == N.OP_MADE:
+                    gW1, gW2 = gW1 * op.consts[0], gW2 * op.consts[1]
+                leaf_grads.extend([gW1, gb1, gW2, gb2])
+        return (gx if need_gx else None, None, *leaf_grads)
+
+
+def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False, base_loc=None, base_log_scale=None,
+                flags=0, want_y=True):
+    """x2: (B, D).  Returns y, log_det, log_prob (None unless requested).  Programs longer than B2F_MAX_OPS are
+    chained (log-dets add, the base density is evaluated by the last launch)."""
+    x2 = N.require_cuda_f32(x2, 'input')
+    ops = list(ops)
+    if len(ops) > N.MAX_OPS:
+        if flags & N.FLOW_LOGP_OF_INPUT:
+            raise N.B2FError('program too long for LOGP_OF_INPUT')
+        y, ld_total = x2, None
+        chunks = [ops[i:i + N.MAX_OPS] for i in range(0, len(ops), N.MAX_OPS)]
+        for ci, chunk in enumerate(chunks):
+            last = ci == len(chunks) - 1
+            y, ld, lp = run_program(chunk, y, want_log_prob and last, base_loc, base_log_scale, flags)
+            ld_total = ld if ld_total is None else ld_total + ld
+        if want_log_prob:
+            lp = lp - ld + ld_total
+        return y, ld_total, (lp if want_log_prob else None)
+    leafs = [t for op in ops for t in op.leafs]
+    needs_grad = torch.is_grad_enabled() and (x2.requires_grad or any(t.requires_grad for t in leafs))
+    if needs_grad:
+        y, ld, lp = FlowFunction.apply(x2, _Cfg(ops, want_log_prob, base_loc, base_log_scale, flags), *leafs)
+        return y, ld, (lp if want_log_prob else None)
+    y, ld, lp = N.flow_apply(op_dicts(ops), x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
+    return y, ld, lp

@@ -1,0 +1,173 @@
+"""Bijection contract and sequential composition (API of torchflows/bijections/base.py:11-243).
+
+``forward(x, context=None) -> (z, log_det)`` and ``inverse(z, context=None) -> (x, log_det)`` with
+``x:(*batch, *event)``, ``log_det:(*batch)``; inputs are never mutated.  New here: ``lower(direction)`` lets a
+layer describe itself as ops of a libb2f flow program, and ``BijectiveComposition`` runs a whole stack of such
+layers as ONE kernel launch instead of the reference's per-layer Python loop (base.py:211-222)."""
+from typing import Any, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+
+from torchflows_b200 import _program as prog
+from torchflows_b200.utils import event_size, get_batch_shape
+
+
+class Bijection(nn.Module):
+    def __init__(self, event_shape: Union[torch.Size, Tuple[int, ...]],
+                 context_shape: Union[torch.Size, Tuple[int, ...]] = None, **kwargs):
+        super().__init__()
+        self.event_shape = event_shape
+        self.n_dim = event_size(event_shape)
+        self.context_shape = context_shape
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, ...]:
+        raise NotImplementedError
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, ...]:
+        raise NotImplementedError
+
+    # -- fused-path hook ---------------------------------------------------------------------------
+    def lower(self, direction: str) -> Optional[List[prog.LoweredOp]]:
+        """Ops of this layer for direction 'forward' | 'inverse', or None if it cannot join a fused program."""
+        return None
+
+    def _run_fused(self, x: torch.Tensor, direction: str):
+        ops = self.lower(direction)
+        batch_shape = get_batch_shape(x, self.event_shape)
+        y2, ld, _ = prog.run_program(ops, x.reshape(-1, self.n_dim))
+        return y2.reshape(x.shape), ld.reshape(batch_shape)
+
+    # -- chunked evaluation (base.py:58-121) --------------------------------------------------------
+    def batch_apply(self, fn: callable, batch_size: int, x: torch.Tensor, context: torch.Tensor = None, **kwargs):
+        n_batch_dims = x.dim() - len(self.event_shape)
+        xf = x.flatten(0, n_batch_dims - 1) if n_batch_dims > 1 else x
+        cf = None
+        if context is not None:
+            cf = context.flatten(0, n_batch_dims - 1) if n_batch_dims > 1 else context
+        outs: List[List[torch.Tensor]] = []
+        for i in range(0, xf.shape[0], batch_size):
+            args = (xf[i:i + batch_size],) if cf is None else (xf[i:i + batch_size], cf[i:i + batch_size])
+            for j, piece in enumerate(fn(*args, **kwargs)):
+                if len(outs) <= j:
+                    outs.append([])
+                outs[j].append(piece)
+        return tuple(torch.cat(pieces, dim=0) for pieces in outs)
+
+    def batch_forward(self, x: torch.Tensor, batch_size: int, context: torch.Tensor = None, **kwargs):
+        return self.batch_apply(self.forward, batch_size, x, context, **kwargs)
+
+    def batch_inverse(self, x: torch.Tensor, batch_size: int, context: torch.Tensor = None, **kwargs):
+        return self.batch_apply(self.inverse, batch_size, x, context, **kwargs)
+
+    def sq_norm_param(self) -> torch.Tensor:
+        """Squared norm of the trainable parameters (base.py:134-144)."""
+        return sum([torch.sum(torch.square(p)) for p in self.parameters() if p.requires_grad])
+
+    def regularization(self, *aux: Tuple[Any, ...]) -> torch.Tensor:
+        return torch.tensor(0.0)
+
+    def invert(self):
+        self.forward, self.inverse = self.inverse, self.forward
+
+
+def invert(bijection: Bijection) -> Bijection:
+    bijection.forward, bijection.inverse = bijection.inverse, bijection.forward
+    return bijection
+
+
+class BijectiveComposition(Bijection):
+    """Composition of bijections.  Consecutive lowerable layers are fused into one flow program."""
+
+    def __init__(self, layers: List[Bijection], **kwargs):
+        super().__init__(event_shape=layers[0].event_shape, context_shape=layers[0].context_shape)
+        self.layers = nn.ModuleList(layers)
+
+    def freeze_after(self, index: int):
+        for i, layer in enumerate(self.layers):
+            if i > index:
+                layer.requires_grad_(False)
+
+    def unfreeze_all_layers(self):
+        for layer in self.layers:
+            layer.requires_grad_(True)
+
+    # -- fused execution --------------------------------------------------------------------------------
+    def _segments(self, direction: str):
+        """Split the layer sequence (in application order) into maximal runs of lowerable layers.
+        A layer that needs a data-dependent initialisation first (ActNorm in training mode) starts a new run
+        so that it can look at its own input."""
+        order = list(self.layers) if direction == 'forward' else list(self.layers)[::-1]
+        segments, current = [], []
+        for layer in order:
+            ops = layer.lower(direction)
+            needs_data = direction == 'forward' and getattr(layer, 'needs_data_init', lambda: False)()
+            if ops is None or needs_data:
+                if current:
+                    segments.append(('ops', current))
+                    current = []
+                if ops is None:
+                    segments.append(('layer', layer))
+                else:
+                    segments.append(('init', layer))   # lowered after its initialisation, see _apply
+            else:
+                current.extend(ops)
+        if current:
+            segments.append(('ops', current))
+        return segments
+
+    def fused_ops(self, direction: str) -> Optional[List[prog.LoweredOp]]:
+        """The whole composition as one op list, or None if some layer cannot be lowered right now."""
+        segs = self._segments(direction)
+        if len(segs) == 1 and segs[0][0] == 'ops':
+            return segs[0][1]
+        if len(segs) == 0:
+            return []
+        return None
+
+    def lower(self, direction: str):
+        return self.fused_ops(direction)
+
+    def _apply(self, x: torch.Tensor, context, direction: str, **kwargs):
+        batch_shape = get_batch_shape(x, self.event_shape)
+        x2 = x.reshape(-1, self.n_dim)
+        log_det = None
+
+        def add(ld):
+            nonlocal log_det
+            log_det = ld if log_det is None else log_det + ld
+
+        for kind, item in self._segments(direction):
+            if kind == 'ops':
+                x2, ld, _ = prog.run_program(item, x2)
+                add(ld)
+            elif kind == 'init':
+                item.data_init(x2.reshape(*batch_shape, *self.event_shape),
+                               reduce_fn=getattr(self, '_stats_reduce_fn', None))
+                x2, ld, _ = prog.run_program(item.lower(direction), x2)
+                add(ld)
+            else:
+                fn = item.forward if direction == 'forward' else item.inverse
+                y, ld = fn(x2.reshape(*batch_shape, *self.event_shape), context=context, **kwargs)[:2]
+                x2 = y.reshape(-1, self.n_dim)
+                add(ld.reshape(-1))
+        if log_det is None:
+            log_det = torch.zeros(x2.shape[0], device=x2.device, dtype=x2.dtype)
+            x2 = x2.clone()
+        return x2.reshape(x.shape), log_det.reshape(batch_shape)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._apply(x, context, 'forward', **kwargs)
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._apply(z, context, 'inverse')
+
+    def regularization(self):
+        """Sum of the layers' regularization terms (base.py:234-243), accumulated on the parameters' device."""
+        terms = [layer.regularization() for layer in self.layers]
+        terms = [t for t in terms if isinstance(t, torch.Tensor)]
+        device = next((t.device for t in terms if t.is_cuda), torch.device('cpu'))
+        total = torch.zeros((), device=device)
+        for t in terms:
+            total = total + t.to(device)
+        return total

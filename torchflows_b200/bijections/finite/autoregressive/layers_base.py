@@ -1,0 +1,234 @@
+"""Autoregressive layer bases (API of torchflows/.../autoregressive/layers_base.py:14-318).
+
+Each class pairs a conditioner with a transformer like the reference, and adds ``lower(direction)``: the
+description of the layer as one op of a fused libb2f flow program (conditioner GEMMs + transformer + log-det
+in one kernel, ``h`` never written to HBM).  Configurations outside the fused path (non-default conditioner
+depth / nonlinearity, globally learned parameter subsets, n_bins != 8) are detected at construction time and run
+as a *composite*: conditioner as library GEMMs, transformer as the stand-alone transformer kernel."""
+from typing import Any, List, Optional, Tuple, Type, Union
+
+import torch
+import torch.nn as nn
+
+from torchflows_b200 import _native as N
+from torchflows_b200 import _program as prog
+from torchflows_b200.bijections.base import Bijection
+from torchflows_b200.bijections.finite.autoregressive.conditioning.coupling_masks import (HalfSplit, PartialCoupling,
+                                                                                           make_coupling)
+from torchflows_b200.bijections.finite.autoregressive.conditioning.transforms import (MADE, ConditionerTransform,
+                                                                                       FeedForward, Linear)
+from torchflows_b200.bijections.finite.autoregressive.transformers.base import ScalarTransformer, TensorTransformer
+from torchflows_b200.bijections.finite.autoregressive.transformers.spline.rational_quadratic import RationalQuadratic
+from torchflows_b200.utils import flatten_event, get_batch_shape, unflatten_event
+
+
+def _no_context(context_shape, what: str):
+    if context_shape is not None:
+        raise NotImplementedError(f'{what}: context-conditioned flows are not part of the B200 hot path yet '
+                                  '(SURVEY section 8f-1); construct with context_shape=None')
+
+
+def _transformer_fusable(tr) -> bool:
+    if isinstance(tr, RationalQuadratic):
+        return tr.n_bins == 8
+    return isinstance(tr, ScalarTransformer) and tr._tkind_forward >= 0
+
+
+class AutoregressiveBijection(Bijection):
+    def __init__(self, event_shape, transformer: Union[TensorTransformer, ScalarTransformer],
+                 conditioner_transform: Optional[ConditionerTransform], l2_regularization: bool = False,
+                 l2_coef: float = 0.01, **kwargs):
+        super().__init__(event_shape=event_shape, **kwargs)
+        self.conditioner_transform = conditioner_transform
+        self.transformer = transformer
+        self.l2_regularization = l2_regularization
+        self.l2_coef = l2_coef
+
+    def regularization(self, *aux: Tuple[Any, ...]):
+        """l2_coef * sum of squared trainable parameters (layers_base.py:38-48)."""
+        if self.l2_regularization and self.l2_coef > 0:
+            return self.sq_norm_param() * self.l2_coef
+        return torch.tensor(0.0)
+
+    def _tkind(self, direction: str) -> int:
+        return self.transformer._tkind_forward if direction == 'forward' else self.transformer._tkind_inverse
+
+    def _spline_args(self):
+        tr = self.transformer
+        return (tr.n_bins, tr.boundary) if isinstance(tr, RationalQuadratic) else (0, 0.0)
+
+
+class CouplingBijection(AutoregressiveBijection):
+    """x = (x_A, x_B): x_A passes through and parameterises the transformer applied to x_B."""
+
+    def __init__(self, event_shape, transformer_class: Type[TensorTransformer], context_shape=None,
+                 coupling: PartialCoupling = None, conditioner_transform_class: Type[ConditionerTransform] = FeedForward,
+                 coupling_kwargs: dict = None, conditioner_kwargs: dict = None, transformer_kwargs: dict = None,
+                 l2_regularization: bool = True, **kwargs):
+        _no_context(context_shape, type(self).__name__)
+        coupling_kwargs, conditioner_kwargs = coupling_kwargs or {}, conditioner_kwargs or {}
+        transformer_kwargs = transformer_kwargs or {}
+        if coupling is None:
+            coupling = make_coupling(event_shape, **coupling_kwargs)
+        transformer = transformer_class(event_shape=coupling.target_shape, **transformer_kwargs)
+        conditioner_transform = conditioner_transform_class(
+            input_event_shape=coupling.constant_shape, context_shape=context_shape,
+            parameter_shape=transformer.parameter_shape, **conditioner_kwargs)
+        super().__init__(event_shape=event_shape, transformer=transformer, conditioner_transform=conditioner_transform,
+                         context_shape=context_shape, l2_regularization=l2_regularization, **kwargs)
+        self.coupling = coupling
+        ct = conditioner_transform
+        self._fusable = (isinstance(coupling, HalfSplit) and type(ct) is FeedForward and ct.n_layers == 2
+                         and ct.nonlinearity is nn.Tanh and ct.is_plain and _transformer_fusable(transformer))
+
+    # -- reference API ---------------------------------------------------------------------------------------
+    def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
+        batch_shape = get_batch_shape(x, self.event_shape)
+        return flatten_event(x, self.event_shape)[..., self.coupling.source_mask.view(-1)].view(
+            *batch_shape, *self.coupling.constant_shape)
+
+    def get_transformed_part(self, x: torch.Tensor) -> torch.Tensor:
+        batch_shape = get_batch_shape(x, self.event_shape)
+        return flatten_event(x, self.event_shape)[..., self.coupling.target_mask.view(-1)].view(
+            *batch_shape, *self.coupling.target_shape)
+
+    def set_transformed_part(self, x: torch.Tensor, x_transformed: torch.Tensor):
+        batch_shape = get_batch_shape(x, self.event_shape)
+        x[..., self.coupling.target_mask] = x_transformed.reshape(*batch_shape, -1)
+
+    def partition_and_predict_parameters(self, x: torch.Tensor, context: torch.Tensor):
+        batch_shape = get_batch_shape(x, self.event_shape)
+        h = self.conditioner_transform(self.get_constant_part(x), context=context)
+        return h.view(*batch_shape, *self.transformer.parameter_shape)
+
+    # -- fused path ------------------------------------------------------------------------------------------
+    def lower(self, direction: str) -> Optional[List[prog.LoweredOp]]:
+        if not self._fusable:
+            return None
+        seq = self.conditioner_transform.sequential
+        n_bins, boundary = self._spline_args()
+        return [prog.LoweredOp(kind=N.OP_COUPLING, tkind=self._tkind(direction),
+                               leafs=[seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias],
+                               n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, owner=self)]
+
+    def _composite(self, x: torch.Tensor, context, direction: str):
+        """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""
+        batch_shape = get_batch_shape(x, self.event_shape)
+        xf = flatten_event(x, self.event_shape)
+        src, tgt = self.coupling.source_mask.view(-1).to(x.device), self.coupling.target_mask.view(-1).to(x.device)
+        h = self.conditioner_transform(xf[..., src], context=context).view(*batch_shape,
+                                                                           *self.transformer.parameter_shape)
+        fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse
+        yb, log_det = fn(xf[..., tgt].contiguous(), h)
+        out = xf.clone()
+        out[..., tgt] = yb
+        return unflatten_event(out, self.event_shape), log_det
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(x, 'forward') if self._fusable else self._composite(x, context, 'forward')
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(z, 'inverse') if self._fusable else self._composite(z, context, 'inverse')
+
+
+class MaskedAutoregressiveBijection(AutoregressiveBijection):
+    """MADE conditioner + scalar transformer.  ``forward`` is one pass; ``inverse`` is sequential over the
+    event dimensions -- the reference re-runs the full network D times (layers_base.py:213-223); here it is one
+    persistent kernel with incrementally updated hidden pre-activations (cost of one pass)."""
+
+    #: reproduce the reference's last-iteration log-det in the sequential direction
+    sequential_log_det_reference_quirk: bool = True
+
+    def __init__(self, event_shape, transformer_class: Type[ScalarTransformer], context_shape=None,
+                 transformer_kwargs: dict = None, conditioner_kwargs: dict = None, l2_regularization: bool = True,
+                 **kwargs):
+        _no_context(context_shape, type(self).__name__)
+        conditioner_kwargs, transformer_kwargs = conditioner_kwargs or {}, transformer_kwargs or {}
+        transformer = transformer_class(event_shape=event_shape, **transformer_kwargs)
+        conditioner_transform = MADE(input_event_shape=event_shape, transformed_event_shape=event_shape,
+                                     parameter_shape_per_element=transformer.parameter_shape_per_element,
+                                     context_shape=context_shape, **conditioner_kwargs)
+        super().__init__(transformer.event_shape, transformer, conditioner_transform,
+                         l2_regularization=l2_regularization, **kwargs)
+        ct = conditioner_transform
+        if not (ct.n_layers == 2 and ct.is_plain and _transformer_fusable(transformer)):
+            raise NotImplementedError('masked autoregressive layers are implemented for the default MADE depth '
+                                      '(n_layers=2), predicted parameters only, and n_bins=8 splines')
+        self.register_buffer('_fin_steps', ct.finalisation_steps(), persistent=False)
+
+    def _lower(self, one_pass: bool, transformer_direction: str):
+        seq = self.conditioner_transform.sequential
+        n_bins, boundary = self._spline_args()
+        flags = 0 if self.sequential_log_det_reference_quirk else N.FLAG_SEQ_LOGDET_EXACT
+        consts = [seq[0].mask, seq[2].mask] + ([] if one_pass else [self._fin_steps])
+        return [prog.LoweredOp(kind=N.OP_MADE if one_pass else N.OP_MADE_SEQ, tkind=self._tkind(transformer_direction),
+                               leafs=[seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias], consts=consts,
+                               n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, flags=flags, owner=self)]
+
+    def lower(self, direction: str):
+        return self._lower(True, 'forward') if direction == 'forward' else self._lower(False, 'inverse')
+
+    def apply_conditioner_transformer(self, inputs, context, forward: bool = True):
+        h = self.conditioner_transform(inputs, context)
+        return self.transformer.forward(inputs, h) if forward else self.transformer.inverse(inputs, h)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(x, 'forward')
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(z, 'inverse')
+
+
+class InverseMaskedAutoregressiveBijection(MaskedAutoregressiveBijection):
+    """forward = sequential direction (with transformer.inverse), inverse = one pass (layers_base.py:226-234)."""
+
+    def lower(self, direction: str):
+        return self._lower(False, 'inverse') if direction == 'forward' else self._lower(True, 'forward')
+
+
+class ElementwiseBijection(AutoregressiveBijection):
+    """Per-element transformer with globally learned parameters ``value`` (layers_base.py:237-318).  The
+    reference materialises ``value`` repeated over the batch (:300-303); the kernels broadcast it."""
+
+    def __init__(self, event_shape, transformer_class: Type[ScalarTransformer], context_shape=None,
+                 transformer_kwargs: dict = None, fill_value: Union[float, torch.Tensor] = None,
+                 conditioner_transform_class: Type[ConditionerTransform] = Linear, conditioner_kwargs: dict = None,
+                 **kwargs):
+        _no_context(context_shape, type(self).__name__)
+        transformer = transformer_class(event_shape=event_shape, **(transformer_kwargs or {}))
+        if fill_value is None:
+            value = torch.randn(*transformer.parameter_shape)
+        elif isinstance(fill_value, torch.Tensor):
+            if fill_value.shape != transformer.parameter_shape:
+                raise ValueError('Shape of fill_value must match the transformer parameter shape')
+            value = fill_value
+        else:
+            value = torch.full(size=tuple(transformer.parameter_shape), fill_value=float(fill_value))
+        super().__init__(event_shape=event_shape, context_shape=None, transformer=transformer,
+                         conditioner_transform=None, **kwargs)
+        self.register_parameter('value', nn.Parameter(value))
+        self.use_global_parameters = True
+
+    def prepare_h(self, context: torch.Tensor, batch_shape):
+        """Parameters broadcast over the batch as a stride-0 view (no copy)."""
+        return self.value.expand(*batch_shape, *self.value.shape)
+
+    def lower(self, direction: str):
+        tk = self._tkind(direction)
+        if tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
+            return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
+        return None
+
+    def _apply(self, x, direction):
+        if self.lower(direction) is not None:
+            return self._run_fused(x, direction)
+        batch_shape = get_batch_shape(x, self.event_shape)
+        h = self.prepare_h(None, batch_shape).contiguous()
+        fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse
+        return fn(x, h)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._apply(x, 'forward')
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._apply(z, 'inverse')

@@ -1,0 +1,37 @@
+// Shared host-side helpers of libb2f.so: error reporting, launch checks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "b2f.h"
+
+namespace b2f {
+
+char* last_error_buffer();   // thread-local, defined in b2f_api.cu
+
+inline int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(last_error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2F_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return B2F_OK;
+}
+
+inline int params_per_element(int tkind, int n_bins) {
+    switch (tkind) {
+        case B2F_T_SHIFT_ADD: case B2F_T_SHIFT_SUB: return 1;
+        case B2F_T_AFFINE_FWD: case B2F_T_AFFINE_INV: return 2;
+        case B2F_T_RQ_FWD: case B2F_T_RQ_INV: return 3 * n_bins - 1;
+        default: return -1;
+    }
+}
+inline int padded_params(int P) { return P <= 2 ? P : (P + 3) / 4 * 4; }
+
+}  // namespace b2f

@@ -1,0 +1,390 @@
+// Backward of the fused flow program (kernel K6): one launch per call, no materialised h.
+//
+// Replaces torch autograd through the ~470-op graph the reference builds for one log_prob call
+// (/root/reference/torchflows/flows.py:199-224 -> bijections/base.py:203-224 -> layers_base.py:145-153,
+//  202-211, 300-318 -> transforms.py:293-307 -> transformers/...).  The math of the transformer backward is
+// SURVEY.md Appendix D (csrc/b2f_math.cuh: rq_backward_fwd, affine_*_backward).
+//
+// Per CTA (tile of TM samples, both the activation tile xt and the gradient tile gt live in shared memory):
+//   phase A  recompute the forward pass layer by layer; the tile as it enters each conditioner layer is written
+//            to the caller's workspace (B*D floats per such layer) because spline layers cannot be un-done
+//            exactly; elementwise layers are un-done in place during phase B instead;
+//   phase B  walk the layers in reverse.  For a conditioner layer: reload its input tile, recompute the hidden
+//            activations and, per (sample, target element), the P transformer parameters in registers; run the
+//            transformer backward -> dL/dx_target and dL/dh[P]; push dL/dh through the last Linear
+//            (dL/dhid via shared-memory atomics, dL/dW2 and dL/db2 by a per-warp [P x 32]x[32 x H] product
+//            staged in shared memory), then tanh', the first Linear (dL/dW1, dL/db1) and dL/dx_source.
+// Parameter gradients are accumulated into global fp32 buffers with red.global.add (one atomic per weight
+// per tile); the caller zero-fills them.  Deterministic within a tile, atomic order across tiles.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "b2f_flow_device.cuh"
+
+namespace b2f {
+
+struct BwdOp {
+    DevOp f;
+    float *g0, *g1, *g2, *g3;
+    long long ws_off;   // float offset of this op's saved input in the workspace (-1: none)
+};
+
+struct BwdArgs {
+    BwdOp ops[B2F_MAX_OPS];
+    int n_ops, D, TM, logTM, XS, HS, WPG, G, flags;
+    long long B;
+    const float* x;
+    const float* gy;
+    const float* gld;
+    const float* glp;
+    const float* base_loc;
+    const float* base_log_scale;
+    float* gx;
+    float* ws;
+};
+
+struct BTile {
+    Tile t;
+    float* gt;    // [TM][XS] gradient w.r.t. the current activations
+    float* dhid;  // [TM][HS] gradient w.r.t. hidden activations, then pre-activations
+    float* GL;    // [TM]     dL/dlog_det of each sample (constant through the layers)
+    float* dhs;   // [NW][32][PPmax] per-warp staging of dL/dh for the weight-gradient product
+    int rows;
+};
+
+template <int TK, int MODE, int P, int PP>
+__device__ __forceinline__ void transformer_backward_element(float v, const float (&acc)[PP], float boundary, float GZ,
+                                                             float GL, float& dv, float (&dh)[PP]) {
+#pragma unroll
+    for (int p = 0; p < PP; ++p) dh[p] = 0.0f;
+    if constexpr (TK == B2F_T_SHIFT_ADD) { dv = GZ; dh[0] = GZ; }
+    else if constexpr (TK == B2F_T_SHIFT_SUB) { dv = GZ; dh[0] = -GZ; }
+    else if constexpr (TK == B2F_T_AFFINE_FWD) affine_fwd_backward<MODE>(v, acc[0], GZ, GL, dv, dh[0], dh[1]);
+    else if constexpr (TK == B2F_T_AFFINE_INV) affine_inv_backward<MODE>(v, acc[0], acc[1], GZ, GL, dv, dh[0], dh[1]);
+    else if constexpr (TK == B2F_T_RQ_FWD) {
+        auto h = [&](int i) { return acc[i]; };
+        auto g = [&](int i, float val) { dh[i] = val; };
+        rq_backward_fwd<8, MODE>(v, h, 8, boundary, GZ, GL, dv, g);
+    } else {
+        dv = 0.0f;   // RQ_INV backward is rejected on the host
+    }
+}
+
+// conditioner-layer backward for every target element
+template <int TK, int MODE>
+__device__ __forceinline__ void transform_pass_backward(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
+    constexpr int P = TInfo<TK>::P, PP = TInfo<TK>::PP;
+    const Tile& t = b.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % t.G, slot = warp / t.G;
+    const int m = g * 32 + lane, H = op.f.H;
+    const float* hid_m = t.hid + m * t.HS;
+    const float* hid_g = t.hid + (g * 32) * t.HS;
+    float* dhs = b.dhs + warp * 32 * PP;
+    const float GLm = b.GL[m];
+    const bool want_w = op.g2 != nullptr;
+    for (int e = slot; e < n_tgt; e += t.WPG) {
+        const float* w2e = op.f.p2 + (size_t)e * H * PP;
+        float acc[PP], dh[PP];
+        element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)e * P, hid_m, H);
+        const int c = t.col(t0 + e);
+        float dv;
+        transformer_backward_element<TK, MODE, P, PP>(t.xt[m * t.XS + c], acc, op.f.boundary, b.gt[m * t.XS + c], GLm,
+                                                      dv, dh);
+        b.gt[m * t.XS + c] = dv;
+        // dL/dhid[m][j] += sum_p dh[p] * W2[e][j][p]
+        for (int j = 0; j < H; ++j) {
+            float s = 0.0f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) s = fmaf(dh[p], __ldg(w2e + j * PP + p), s);
+            atomicAdd(b.dhid + m * t.HS + j, s);
+        }
+        if (want_w) {
+            // dL/dW2[e][j][p] += sum_m dh[m][p] * hid[m][j];  dL/db2[e][p] += sum_m dh[m][p]   (m over this warp)
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < PP; ++p) dhs[lane * PP + p] = dh[p];
+            __syncwarp();
+            for (int idx = lane; idx < H * PP; idx += 32) {
+                const int j = idx / PP, p = idx - j * PP;
+                if (p < P) {
+                    float s = 0.0f;
+                    for (int mm = 0; mm < 32; ++mm) s = fmaf(dhs[mm * PP + p], hid_g[mm * t.HS + j], s);
+                    atomicAdd(op.g2 + ((size_t)e * H + j) * PP + p, s);
+                }
+            }
+            if (lane < P) {
+                float s = 0.0f;
+                for (int mm = 0; mm < 32; ++mm) s += dhs[mm * PP + lane];
+                atomicAdd(op.g3 + (size_t)e * P + lane, s);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void run_transform_backward(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
+    switch (op.f.tkind) {
+        case B2F_T_SHIFT_ADD: transform_pass_backward<B2F_T_SHIFT_ADD, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_SHIFT_SUB: transform_pass_backward<B2F_T_SHIFT_SUB, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_AFFINE_FWD: transform_pass_backward<B2F_T_AFFINE_FWD, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_AFFINE_INV: transform_pass_backward<B2F_T_AFFINE_INV, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_RQ_FWD: transform_pass_backward<B2F_T_RQ_FWD, MODE>(b, op, t0, n_tgt); break;
+        default: break;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void run_transform_forward(const Tile& t, const DevOp& op, int t0, int n_tgt) {
+    switch (op.tkind) {
+        case B2F_T_SHIFT_ADD: transform_pass<B2F_T_SHIFT_ADD, MODE>(t, op, t0, n_tgt); break;
+        case B2F_T_SHIFT_SUB: transform_pass<B2F_T_SHIFT_SUB, MODE>(t, op, t0, n_tgt); break;
+        case B2F_T_AFFINE_FWD: transform_pass<B2F_T_AFFINE_FWD, MODE>(t, op, t0, n_tgt); break;
+        case B2F_T_AFFINE_INV: transform_pass<B2F_T_AFFINE_INV, MODE>(t, op, t0, n_tgt); break;
+        case B2F_T_RQ_FWD: transform_pass<B2F_T_RQ_FWD, MODE>(t, op, t0, n_tgt); break;
+        default: break;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constant__ BwdArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    BTile b;
+    Tile& t = b.t;
+    t.D = A.D; t.TM = A.TM; t.logTM = A.logTM; t.XS = A.XS; t.HS = A.HS; t.WPG = A.WPG; t.G = A.G; t.flip = 0;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
+    const int D = A.D, TM = A.TM, XS = A.XS, HS = A.HS;
+    t.xt = smem;
+    b.gt = t.xt + TM * XS;
+    t.hid = b.gt + TM * XS;
+    b.dhid = t.hid + TM * HS;
+    t.act = nullptr;
+    t.ldp = b.dhid + TM * HS;              // [WPG][TM] (written by the forward recompute, unused)
+    b.GL = t.ldp + A.WPG * TM;             // [TM]
+    float* ea = b.GL + TM;                 // [3*D]
+    b.dhs = ea + 3 * D;                    // [NW][32][24]
+    const long long row0 = (long long)blockIdx.x * TM;
+    const int rows = (int)min((long long)TM, A.B - row0);
+    b.rows = rows;
+
+    for (int m = warp; m < TM; m += NW) {
+        float* dst = t.xt + m * XS;
+        for (int j = lane; j < D; j += 32) dst[j] = (m < rows) ? __ldg(A.x + (row0 + m) * D + j) : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- phase A: forward recompute, saving the input of every conditioner layer ---------------------
+    for (int oi = 0; oi < A.n_ops; ++oi) {
+        const BwdOp& op = A.ops[oi];
+        if (op.f.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
+        if (op.f.kind == B2F_OP_ELEMENTWISE) {
+            elementwise_stage(ea, op.f, D);
+            __syncthreads();
+            elementwise_apply(t, ea, op.f.tkind == B2F_T_AFFINE_FWD);
+            __syncthreads();
+            continue;
+        }
+        float* save = A.ws + op.ws_off + row0 * D;
+        for (int m = warp; m < rows; m += NW)
+            for (int j = lane; j < D; j += 32) save[(size_t)m * D + j] = t.xt[m * XS + j];   // physical layout
+        const bool coupling = op.f.kind == B2F_OP_COUPLING;
+        const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0;
+        hidden_layer<true>(t, op.f, n_src);
+        __syncthreads();
+        run_transform_forward<MODE>(t, op.f, t0, D - t0);
+        __syncthreads();
+    }
+
+    // ---- gradient seed: dL/dz = gy + glp * d base_logp / dz ;  dL/dlog_det = gld + glp ------------------
+    for (int m = warp; m < TM; m += NW) {
+        const bool live = m < rows;
+        const float glp = (live && A.glp) ? __ldg(A.glp + row0 + m) : 0.0f;
+        for (int j = lane; j < D; j += 32) {
+            const int c = t.col(j);
+            float gseed = (live && A.gy) ? __ldg(A.gy + (row0 + m) * D + j) : 0.0f;
+            if (A.glp) {
+                const float loc = A.base_loc ? __ldg(A.base_loc + j) : 0.0f;
+                const float lsc = A.base_log_scale ? __ldg(A.base_log_scale + j) : 0.0f;
+                const float is = expf(-lsc);
+                gseed -= glp * (t.xt[m * XS + c] - loc) * is * is;     // d/dz of -(0.5*((z-loc)/scale)^2 + ...)
+            }
+            b.gt[m * XS + c] = gseed;
+        }
+        if (lane == 0) b.GL[m] = live ? ((A.gld ? __ldg(A.gld + row0 + m) : 0.0f) + glp) : 0.0f;
+    }
+    __syncthreads();
+
+    // ---- phase B: reverse walk ---------------------------------------------------------------------------
+    for (int oi = A.n_ops - 1; oi >= 0; --oi) {
+        const BwdOp& op = A.ops[oi];
+        if (op.f.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
+        if (op.f.kind == B2F_OP_ELEMENTWISE) {
+            elementwise_stage(ea, op.f, D);
+            __syncthreads();
+            const bool fwd = op.f.tkind == B2F_T_AFFINE_FWD;
+            // thread per column: un-do the layer in place, propagate the gradient, reduce the parameter gradient
+            for (int j = tid; j < D; j += NT) {
+                const int c = t.col(j);
+                const float a = ea[j], bta = ea[D + j], ia = 1.0f / a;
+                float du0 = 0.0f, du1 = 0.0f;
+                for (int m = 0; m < TM; ++m) {
+                    const float zo = t.xt[m * XS + c], gz = b.gt[m * XS + c], GLm = b.GL[m];
+                    if (fwd) {                     // z = a*x + b, ld += log a
+                        const float xi = (zo - bta) * ia;
+                        du0 += gz * xi + GLm * ia;
+                        du1 += gz;
+                        t.xt[m * XS + c] = xi;
+                        b.gt[m * XS + c] = gz * a;
+                    } else {                       // z = (x - b)/a, ld -= log a
+                        du0 += -gz * zo * ia - GLm * ia;
+                        du1 += -gz * ia;
+                        t.xt[m * XS + c] = fmaf(a, zo, bta);
+                        b.gt[m * XS + c] = gz * ia;
+                    }
+                }
+                if (op.g0) {
+                    atomicAdd(op.g0 + 2 * j, du0 * (a - kAffineM) * 0.5f);
+                    atomicAdd(op.g0 + 2 * j + 1, du1);
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        // conditioner layer: reload its input, recompute hidden activations
+        const float* saved = A.ws + op.ws_off + row0 * D;
+        for (int m = warp; m < TM; m += NW)
+            for (int j = lane; j < D; j += 32) t.xt[m * XS + j] = (m < rows) ? saved[(size_t)m * D + j] : 0.0f;
+        for (int i = tid; i < TM * HS; i += NT) b.dhid[i] = 0.0f;
+        __syncthreads();
+        const bool coupling = op.f.kind == B2F_OP_COUPLING;
+        const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0, H = op.f.H;
+        hidden_layer<true>(t, op.f, n_src);
+        __syncthreads();
+        run_transform_backward<MODE>(b, op, t0, D - t0);
+        __syncthreads();
+        // tanh': dpre = dhid * (1 - hid^2)
+        for (int idx = tid; idx < (H << t.logTM); idx += NT) {
+            const int m = idx & (TM - 1), j = idx >> t.logTM;
+            const float a = t.hid[m * HS + j];
+            b.dhid[m * HS + j] *= (1.0f - a * a);
+        }
+        __syncthreads();
+        if (op.g0) {
+            // dL/dW1[j][k] = sum_m dpre[m][j] * x_src[m][k];  dL/db1[j] = sum_m dpre[m][j]
+            for (int idx = tid; idx < H * n_src; idx += NT) {
+                const int j = idx / n_src, k = idx - j * n_src;
+                const int c = t.col(k);
+                float s = 0.0f;
+                for (int m = 0; m < TM; ++m) s = fmaf(b.dhid[m * HS + j], t.xt[m * XS + c], s);
+                atomicAdd(op.g0 + idx, s);
+            }
+            for (int j = tid; j < H; j += NT) {
+                float s = 0.0f;
+                for (int m = 0; m < TM; ++m) s += b.dhid[m * HS + j];
+                atomicAdd(op.g1 + j, s);
+            }
+        }
+        // dL/dx_src[m][k] += sum_j dpre[m][j] * W1[j][k]
+        for (int idx = tid; idx < (n_src << t.logTM); idx += NT) {
+            const int m = idx & (TM - 1), k = idx >> t.logTM;
+            float s = 0.0f;
+            for (int j = 0; j < H; ++j) s = fmaf(b.dhid[m * HS + j], __ldg(op.f.p0 + (size_t)j * n_src + k), s);
+            b.gt[m * XS + t.col(k)] += s;
+        }
+        __syncthreads();
+    }
+
+    if (A.gx) {
+        for (int m = warp; m < rows; m += NW)
+            for (int j = lane; j < D; j += 32) A.gx[(row0 + m) * D + j] = b.gt[m * XS + t.col(j)];
+    }
+}
+
+static int ilog2b(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+}  // namespace b2f
+
+using namespace b2f;
+
+extern "C" int64_t b2f_flow_backward_workspace(const b2f_op_t* ops, int32_t n_ops, int64_t B, int32_t D) {
+    int64_t n = 0;
+    for (int i = 0; i < n_ops; ++i)
+        if (ops[i].kind == B2F_OP_COUPLING || ops[i].kind == B2F_OP_MADE) ++n;
+    return n * B * (int64_t)D * (int64_t)sizeof(float);
+}
+
+extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float* x, const float* gy,
+                                 const float* glog_det, const float* glog_prob, const float* base_loc,
+                                 const float* base_log_scale, float* gx, void* workspace, int64_t B, int32_t D,
+                                 int32_t flags, void* stream) {
+    if (!ops || n_ops < 0 || !x || D <= 0 || B < 0) return fail(B2F_ERR_INVALID, "b2f_flow_backward: bad arguments");
+    if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: %d ops > B2F_MAX_OPS", n_ops);
+    if (B == 0) return B2F_OK;
+    BwdArgs A;
+    memset(&A, 0, sizeof(A));
+    int Hmax = 1;
+    long long off = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const b2f_op_t& o = ops[i];
+        BwdOp& d = A.ops[i];
+        d.f.kind = o.kind; d.f.tkind = o.tkind; d.f.H = o.n_hidden; d.f.flags = o.flags; d.f.boundary = o.boundary;
+        d.f.p0 = (const float*)o.p[0]; d.f.p1 = (const float*)o.p[1]; d.f.p2 = (const float*)o.p[2];
+        d.f.p3 = (const float*)o.p[3]; d.f.p4 = nullptr;
+        d.g0 = (float*)o.g[0]; d.g1 = (float*)o.g[1]; d.g2 = (float*)o.g[2]; d.g3 = (float*)o.g[3];
+        d.ws_off = -1;
+        switch (o.kind) {
+            case B2F_OP_FLIP: break;
+            case B2F_OP_ELEMENTWISE:
+                if (!o.p[0]) return fail(B2F_ERR_INVALID, "op %d: elementwise layer without parameters", i);
+                if (o.tkind != B2F_T_AFFINE_FWD && o.tkind != B2F_T_AFFINE_INV)
+                    return fail(B2F_ERR_UNSUPPORTED, "op %d: elementwise transformer kind %d", i, o.tkind);
+                break;
+            case B2F_OP_COUPLING: case B2F_OP_MADE: {
+                if (!o.p[0] || !o.p[1] || !o.p[2] || !o.p[3] || o.n_hidden <= 0)
+                    return fail(B2F_ERR_INVALID, "op %d: conditioner parameters missing", i);
+                if (o.tkind == B2F_T_RQ_INV)
+                    return fail(B2F_ERR_UNSUPPORTED, "op %d: backward of the inverse-direction spline is not fused", i);
+                if (o.tkind == B2F_T_RQ_FWD && o.n_bins != 8)
+                    return fail(B2F_ERR_UNSUPPORTED, "op %d: fused RQ spline needs n_bins == 8", i);
+                const bool any_g = o.g[0] || o.g[1] || o.g[2] || o.g[3];
+                if (any_g && !(o.g[0] && o.g[1] && o.g[2] && o.g[3]))
+                    return fail(B2F_ERR_INVALID, "op %d: give all four gradient buffers or none", i);
+                if (!workspace) return fail(B2F_ERR_INVALID, "b2f_flow_backward: workspace missing");
+                d.ws_off = off;
+                off += B * (long long)D;
+                Hmax = std::max(Hmax, o.n_hidden);
+                break;
+            }
+            case B2F_OP_MADE_SEQ:
+                return fail(B2F_ERR_UNSUPPORTED, "op %d: backward through the sequential direction is not fused", i);
+            default: return fail(B2F_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
+        }
+    }
+    A.n_ops = n_ops; A.D = D; A.B = B; A.flags = flags;
+    A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
+    A.gx = gx; A.ws = (float*)workspace;
+    A.XS = D | 1; A.HS = Hmax | 1;
+    int TM = 64, NT = 256;
+    if (const char* e = getenv("B2F_BWD_TM")) TM = atoi(e);
+    if (const char* e = getenv("B2F_BWD_NT")) NT = atoi(e);
+    auto smem_bytes = [&](int tm, int nt) {
+        const int wpg = (nt / 32) / (tm / 32);
+        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + 2 * (size_t)tm * A.HS + (size_t)wpg * tm + tm + 3 * D +
+                                        (size_t)(nt / 32) * 32 * 24 + 4);
+    };
+    while (TM > 32 && smem_bytes(TM, NT) > 200 * 1024) TM >>= 1;
+    if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 256 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
+        return fail(B2F_ERR_INVALID, "b2f_flow_backward: bad tile shape TM=%d NT=%d", TM, NT);
+    const size_t smem = smem_bytes(TM, NT);
+    if (smem > 227 * 1024) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: D=%d H=%d does not fit shared memory", D, Hmax);
+    A.TM = TM; A.logTM = ilog2b(TM); A.G = TM / 32; A.WPG = (NT / 32) / A.G;
+    const long long grid = (B + TM - 1) / TM;
+    if (grid > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: batch too large for one launch");
+    auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_backward_kernel<0> : flow_backward_kernel<1>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+    return check_launch("b2f_flow_backward");
+}

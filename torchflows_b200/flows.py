@@ -1,0 +1,316 @@
+"""Distribution API: ``Flow(bijection).log_prob / sample / fit`` (API of torchflows/flows.py:18-455,606-713).
+
+What changes underneath: ``log_prob`` and ``sample`` of a lowerable bijection are ONE kernel launch each
+(layers + log-det + base density, csrc/b2f_flow.cu); ``fit`` trains through the hand-written backward kernel
+and, when ``torch.distributed`` is initialised, runs data-parallel: every rank takes its slice of each
+minibatch and gradients are all-reduced over NCCL (NVLink/NVSwitch) in one flat bucket per step."""
+import time
+import warnings
+from copy import deepcopy
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from tqdm import tqdm
+
+from torchflows_b200 import _native as N
+from torchflows_b200 import _program as prog
+from torchflows_b200.base_distributions.gaussian import DiagonalGaussian
+from torchflows_b200.bijections.base import Bijection
+from torchflows_b200.utils import event_size, flatten_event, get_batch_shape, unflatten_event
+
+
+def _dist_info() -> Tuple[int, int]:
+    """(rank, world_size) of the default process group, (0, 1) when not distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of an n-row batch owned by `rank`; sizes differ by at most one row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_gradients(parameters, world: int) -> None:
+    """Mean of the gradients over all ranks: one flat bucket, one all-reduce (NCCL on GPU)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in parameters if p.grad is not None]
+    if not grads or world == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world)
+    offset = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[offset:offset + n].view_as(g))
+        offset += n
+
+
+def _allreduce_stats(s, q, n):
+    import torch.distributed as dist
+    packed = torch.cat([s, q, n.reshape(1)])
+    dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+    d = s.numel()
+    return packed[:d], packed[d:2 * d], packed[2 * d]
+
+
+class BaseFlow(nn.Module):
+    def __init__(self, event_shape, base_distribution: Union[torch.distributions.Distribution, str] = 'standard_normal'):
+        super().__init__()
+        self.event_shape = event_shape
+        self.event_size = event_size(event_shape)
+        if isinstance(base_distribution, str) and base_distribution == 'standard_normal':
+            self.base = DiagonalGaussian(loc=torch.zeros(self.event_size), scale=torch.ones(self.event_size))
+        elif isinstance(base_distribution, torch.distributions.Distribution):
+            self.base = base_distribution
+        else:
+            raise ValueError(f'Invalid base distribution: {base_distribution}')
+        self.register_buffer('device_buffer', torch.empty(size=()))
+        self._optimizer = None
+
+    def get_device(self):
+        return self.device_buffer.device
+
+    def base_log_prob(self, z: torch.Tensor):
+        return self.base.log_prob(flatten_event(z, self.event_shape))
+
+    def base_sample(self, sample_shape: Union[torch.Size, Tuple[int, ...]]):
+        return unflatten_event(self.base.sample(sample_shape), self.event_shape)
+
+    def regularization(self, *args, **kwargs):
+        return self.bijection.regularization(*args, **kwargs)
+
+    def _fusable_base(self) -> bool:
+        b = self.base
+        return type(b) is DiagonalGaussian and not any(p.requires_grad for p in b.parameters())
+
+    # ---------------------------------------------------------------------------------------------------
+    def _base_batch_loss(self, batch, reduction: callable = torch.mean, use_regularization: bool = True):
+        """-reduction(w * log_prob(x)) / event_size + regularization   (flows.py:199-224)."""
+        x, weights = batch[:2]
+        context = batch[2] if len(batch) == 3 else None
+        log_prob = self.log_prob(x.to(self.get_device()), context=context)
+        loss = -reduction(log_prob * weights.to(self.get_device())) / self.event_size
+        if use_regularization:
+            loss = loss + self.regularization()
+        return loss
+
+    def fit(self, x_train: torch.Tensor, n_epochs: int = 500, lr: float = 0.05, batch_size: Union[int, str] = 1024,
+            shuffle: bool = True, show_progress: bool = False, w_train: torch.Tensor = None,
+            context_train: torch.Tensor = None, x_val: torch.Tensor = None, w_val: torch.Tensor = None,
+            context_val: torch.Tensor = None, keep_best_weights: bool = True, early_stopping: bool = False,
+            early_stopping_threshold: int = 50, max_batch_size_mb: int = None,
+            time_limit_seconds: Union[float, int] = None, reset_optimizer: bool = True):
+        """Maximum-likelihood fit with the reference's semantics (flows.py:226-455): AdamW, minibatches in a fresh
+        random order every epoch, best-weights snapshot, divergence rollback, optional validation / early stopping /
+        adaptive batch size / time limit.  The data are moved to the flow's device once and batches are index
+        slices there (the reference collates every batch on the host through a DataLoader)."""
+        t0 = time.time()
+        self.train()
+        params = list(self.parameters())
+        if len(params) == 0:
+            return
+        if not any(p.requires_grad for p in params):
+            self.eval()
+            return
+        if context_train is not None or context_val is not None:
+            raise NotImplementedError('context-conditioned training is not part of the B200 hot path yet')
+        device = self.get_device()
+        rank, world = _dist_info()
+        n_train = len(x_train)
+
+        adaptive = isinstance(batch_size, str) and batch_size == 'adaptive'
+        if batch_size is None:
+            batch_size = n_train
+        elif adaptive:
+            max_batch_size = min(4096, n_train // 10)
+            if max_batch_size_mb is not None:
+                max_batch_size = max(1, min(max_batch_size, int(max_batch_size_mb / (self.event_size / 2 ** 20))))
+            batch_size = max(32, min(1024, n_train // 100))
+
+        x_dev = x_train.to(device=device, dtype=torch.float32)
+        w_dev = (torch.ones(n_train) if w_train is None else w_train).to(device=device, dtype=torch.float32)
+        if len(w_dev) != n_train:
+            raise ValueError(f'Expected same number of training data and training weights, '
+                             f'but found {n_train} and {len(w_dev)}')
+        if x_val is not None:
+            xv_dev = x_val.to(device=device, dtype=torch.float32)
+            wv_dev = (torch.ones(len(x_val)) if w_val is None else w_val).to(device=device, dtype=torch.float32)
+            if len(wv_dev) != len(xv_dev):
+                raise ValueError(f'Expected same number of validation data and validation weights, '
+                                 f'but found {len(xv_dev)} and {len(wv_dev)}')
+
+        if self._optimizer is None or reset_optimizer:
+            self._optimizer = torch.optim.AdamW(self.parameters(), lr=lr)
+        trainable = [p for p in self.parameters() if p.requires_grad]
+        if world > 1:
+            self.bijection._stats_reduce_fn = _allreduce_stats     # ActNorm initialises from global statistics
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(int(torch.initial_seed()) & 0x7fffffff)    # identical batch order on every rank
+
+        val_loss = None
+        best_val_loss = best_train_loss = float('inf')
+        best_val_epoch = best_train_epoch = 0
+        best_weights = deepcopy(self.state_dict())
+        diverged = False
+
+        for epoch in (pbar := tqdm(range(n_epochs), desc='Fitting NF', disable=not show_progress)):
+            if time_limit_seconds is not None and time.time() - t0 >= time_limit_seconds:
+                print('Training time limit exceeded')
+                break
+            if adaptive and epoch % 10 == 9 and batch_size < max_batch_size:
+                batch_size = min(batch_size * 2, max_batch_size)      # doubled every 10 epochs (flows.py:346-352)
+
+            order = torch.randperm(n_train, generator=gen).to(device) if shuffle else None
+            total, n_batches = 0.0, 0
+            for start in range(0, n_train, batch_size):
+                stop = min(start + batch_size, n_train)
+                lo, hi = shard_bounds(stop - start, rank, world)
+                idx = slice(start + lo, start + hi) if order is None else order[start + lo:start + hi]
+                xb, wb = x_dev[idx], w_dev[idx]
+                self._optimizer.zero_grad()
+                if world == 1:
+                    loss = self._base_batch_loss((xb, wb), reduction=torch.mean, use_regularization=True)
+                else:
+                    # local sum / global count, so that the mean over ranks of the gradients is the gradient of the
+                    # global-batch mean; the regularisation term is identical on every rank
+                    lp = self.log_prob(xb)
+                    loss = -(lp * wb).sum() * (world / (stop - start)) / self.event_size + self.regularization()
+                loss_value = loss.detach()
+                if world > 1:
+                    import torch.distributed as dist
+                    loss_value = loss_value.clone()
+                    dist.all_reduce(loss_value, op=dist.ReduceOp.SUM)
+                    loss_value /= world
+                if not torch.isfinite(loss_value):
+                    self.load_state_dict(best_weights)       # roll back (flows.py:387-393)
+                    warnings.warn('Flow training diverged. Reverting to previous weights.')
+                    diverged = True
+                    break
+                total += float(loss_value)
+                n_batches += 1
+                loss.backward()
+                if world > 1:
+                    allreduce_gradients(trainable, world)
+                self._optimizer.step()
+                if show_progress:
+                    msg = f'Training loss (batch): {float(loss_value):.4f} [{best_train_loss:.4f} @ {best_train_epoch}]'
+                    if val_loss is not None:
+                        msg += f' , Validation loss (batch): {val_loss:.4f} [{best_val_loss:.4f} @ {best_val_epoch}]'
+                    pbar.set_postfix_str(msg)
+            if diverged:
+                break
+
+            mean_loss = total / max(n_batches, 1)
+            if mean_loss < best_train_loss:
+                best_train_loss, best_train_epoch = mean_loss, epoch
+            if x_val is not None:
+                with torch.no_grad():
+                    acc = 0.0
+                    for start in range(0, len(xv_dev), batch_size):
+                        sl = slice(start, start + batch_size)
+                        acc += float(self._base_batch_loss((xv_dev[sl], wv_dev[sl]), reduction=torch.sum,
+                                                           use_regularization=False))
+                val_loss = acc / len(xv_dev)
+                if val_loss < best_val_loss:
+                    best_val_loss, best_val_epoch = val_loss, epoch
+            if keep_best_weights:
+                improved = best_val_epoch == epoch if x_val is not None else best_train_epoch == epoch
+                if improved:
+                    best_weights = deepcopy(self.state_dict())
+            if early_stopping:
+                ref_epoch = best_val_epoch if x_val is not None else best_train_epoch
+                if epoch - ref_epoch > early_stopping_threshold:
+                    break
+
+        if keep_best_weights:
+            self.load_state_dict(best_weights)
+        self.eval()
+
+    def variational_fit(self, *args, **kwargs):
+        raise NotImplementedError('variational_fit (gradients through the sampling direction) is listed as the next '
+                                  'step after the maximum-likelihood hot path (SURVEY section 8f-2)')
+
+    def fit_kl_p_to_q(self, *args, **kwargs):
+        raise NotImplementedError('fit_kl_p_to_q is outside the B200 hot path of this round (SURVEY section 8f-2)')
+
+
+class Flow(BaseFlow):
+    """A bijection applied to a base distribution."""
+
+    def __init__(self, bijection: Bijection, **kwargs):
+        super().__init__(event_shape=bijection.event_shape, **kwargs)
+        self.register_module('bijection', bijection)
+
+    @property
+    def context_shape(self):
+        return self.bijection.context_shape
+
+    def forward_with_log_prob(self, x: torch.Tensor, context: torch.Tensor = None):
+        """z = bijection.forward(x); log_prob = base.log_prob(z) + log_det   (flows.py:628-648)."""
+        if context is not None:
+            if self.context_shape is None:
+                raise ValueError('Context shape must be set.')
+            assert get_batch_shape(x, self.event_shape) == get_batch_shape(context, self.context_shape)
+            context = context.to(self.get_device())
+        x = x.to(self.get_device())
+        ops = self.bijection.lower('forward') if context is None else None
+        if ops is not None and self._fusable_base():
+            batch_shape = get_batch_shape(x, self.event_shape)
+            z2, _, lp = prog.run_program(ops, x.reshape(-1, self.event_size), want_log_prob=True,
+                                         base_loc=self.base.loc, base_log_scale=self.base.log_scale)
+            return z2.reshape(x.shape), lp.reshape(batch_shape)
+        z, log_det = self.bijection.forward(x, context=context)[:2]
+        return z, self.base_log_prob(z) + log_det
+
+    def log_prob(self, x: torch.Tensor, context: torch.Tensor = None) -> torch.Tensor:
+        if context is None and not (torch.is_grad_enabled() and (x.requires_grad or any(
+                p.requires_grad for p in self.parameters()))):
+            # inference: skip writing z back to HBM altogether
+            x = x.to(self.get_device())
+            ops = self.bijection.lower('forward')
+            if ops is not None and self._fusable_base() and len(ops) <= N.MAX_OPS:
+                batch_shape = get_batch_shape(x, self.event_shape)
+                _, _, lp = prog.run_program(ops, x.reshape(-1, self.event_size), want_log_prob=True,
+                                            base_loc=self.base.loc, base_log_scale=self.base.log_scale, want_y=False)
+                return lp.reshape(batch_shape)
+        return self.forward_with_log_prob(x, context)[1]
+
+    def sample(self, sample_shape: Union[int, torch.Size, Tuple[int, ...]], context: torch.Tensor = None,
+               no_grad: bool = False, return_log_prob: bool = False):
+        """x = bijection.inverse(z), z ~ base.  With ``return_log_prob`` the second output is
+        ``base.log_prob(z) + log_det_inverse`` exactly as in the reference (flows.py:710-712)."""
+        if isinstance(sample_shape, int):
+            sample_shape = (sample_shape,)
+        if context is not None:
+            raise NotImplementedError('context-conditioned sampling is not part of the B200 hot path yet')
+        z = self.base_sample(sample_shape=sample_shape)
+        return self._sample_from_base(z, no_grad, return_log_prob)
+
+    def _sample_from_base(self, z: torch.Tensor, no_grad: bool = False, return_log_prob: bool = False):
+        """The deterministic part of ``sample``: push base draws ``z`` through the inverse bijection."""
+        z = z.to(self.get_device())
+        batch_shape = get_batch_shape(z, self.event_shape)
+        grad_needed = (not no_grad) and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not grad_needed:
+            ops = self.bijection.lower('inverse')
+            if ops is not None and self._fusable_base() and len(ops) <= N.MAX_OPS:
+                with torch.no_grad():
+                    x2, _, lp = prog.run_program(ops, z.detach().reshape(-1, self.event_size),
+                                                 want_log_prob=return_log_prob, base_loc=self.base.loc,
+                                                 base_log_scale=self.base.log_scale, flags=N.FLOW_LOGP_OF_INPUT)
+                x = x2.reshape(z.shape)
+                return (x, lp.reshape(batch_shape)) if return_log_prob else x
+        if no_grad:
+            with torch.no_grad():
+                x, log_det = self.bijection.inverse(z.detach())[:2]
+        else:
+            x, log_det = self.bijection.inverse(z)[:2]
+        if return_log_prob:
+            return x, self.base_log_prob(z) + log_det
+        return x
