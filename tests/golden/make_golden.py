@@ -174,14 +174,23 @@ def fit_cases():
     """Loss trajectories of BaseFlow.fit's inner loop (flows.py:379-398) with full-batch, unshuffled
     steps so that they are comparable step by step (check P5)."""
     cases = []
-    for n, (preset, event_shape, n_data, lr) in enumerate((('RealNVP', (3,), 1000, 0.05),
-                                                           ('CouplingRQNSF', (4,), 512, 0.01),
-                                                           ('MAF', (4,), 512, 0.05))):
+    for n, (preset, event_shape, n_data, lr, data_init) in enumerate((('RealNVP', (3,), 1000, 0.05, False),
+                                                                      ('CouplingRQNSF', (4,), 512, 0.01, False),
+                                                                      ('MAF', (4,), 512, 0.05, False),
+                                                                      ('RealNVP', (3,), 1000, 0.05, True))):
         torch.manual_seed(0)
         x = torch.randn(n_data, *event_shape)
         flow = Flow(getattr(ref_arch, preset)(event_shape))
         sd0 = {k: v.clone() for k, v in flow.state_dict().items()}
         flow.train()
+        if not data_init:
+            # Keep the constructor's ActNorm parameters.  With a fresh data-dependent init the mean of every
+            # normalised activation is exactly zero, so several gradients are pure rounding noise (~1e-9) and Adam's
+            # first step (lr * g / (|g| + eps)) turns that noise into O(lr) parameter changes: the trajectory is then
+            # not reproducible even between two runs of the reference on different thread counts.
+            for layer in flow.bijection.layers:
+                if hasattr(layer, 'first_training_batch_pass'):
+                    layer.first_training_batch_pass = False
         opt = torch.optim.AdamW(flow.parameters(), lr=lr)
         w = torch.ones(n_data)
         losses = []
@@ -195,6 +204,7 @@ def fit_cases():
         with torch.no_grad():
             lp = flow.log_prob(x)
         cases.append(dict(preset=preset, event_shape=event_shape, lr=lr, x=x, state_dict0=sd0, losses=losses,
+                          data_init=data_init,
                           state_dict20={k: v.clone() for k, v in flow.state_dict().items()}, log_prob20=lp))
     return cases
 

@@ -34,7 +34,7 @@ def test_gradients_vs_reference_autograd(golden, dev, idx):
     x = c['x'].to(dev).requires_grad_(True)
     loss = flow._base_batch_loss((x, c['w'].to(dev)))
     loss.backward()
-    assert abs(float(loss) - float(c['loss'])) <= 1e-5 * (1 + abs(float(c['loss'])))
+    assert abs(float(loss.detach()) - float(c['loss'])) <= 1e-5 * (1 + abs(float(c['loss'])))
     tol = 2e-3 if 'RQNSF' in c['preset'] else 1e-4
     assert rel(x.grad, c['grad_x']) < tol, ('grad_x', rel(x.grad, c['grad_x']))
     params = dict(flow.named_parameters())
@@ -66,13 +66,20 @@ def test_input_gradient_is_finite_like_reference_test(dev):
             assert g.shape == x.shape and torch.isfinite(g).all()
 
 
-@pytest.mark.parametrize('idx', range(3))
+@pytest.mark.parametrize('idx', range(4))
 def test_fit_loss_trajectory(golden, dev, idx):
-    """P5: the inner loop of BaseFlow.fit (flows.py:379-398), full batch, 20 AdamW steps from identical weights:
-    loss trajectory within 1e-3 relative of the reference's."""
+    """P5: the inner loop of BaseFlow.fit (flows.py:379-398), full batch, 20 AdamW steps from identical weights.
+    Cases 0-2 keep the constructor's ActNorm parameters: loss trajectory within 1e-3 relative of the reference's.
+    Case 3 lets ActNorm data-initialise on the first step; several gradients are then rounding noise that Adam's
+    normalisation amplifies (see tests/golden/make_golden.py), so only the first loss is compared tightly and the
+    rest of the trajectory loosely."""
     c = golden('fit.pt')[idx]
     flow = build(c['preset'], c['event_shape'], {}, c['state_dict0'], dev)
     flow.train()
+    if not c['data_init']:
+        for layer in flow.bijection.layers:
+            if hasattr(layer, 'first_training_batch_pass'):
+                layer.first_training_batch_pass = False
     x = c['x'].to(dev)
     w = torch.ones(len(x), device=dev)
     opt = torch.optim.AdamW(flow.parameters(), lr=c['lr'])
@@ -80,15 +87,17 @@ def test_fit_loss_trajectory(golden, dev, idx):
     for _ in range(20):
         opt.zero_grad()
         loss = flow._base_batch_loss((x, w))
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
         loss.backward()
         opt.step()
     for i, (a, b) in enumerate(zip(losses, c['losses'])):
-        assert abs(a - b) <= 1e-3 * (1 + abs(b)), (i, a, b)
-    flow.eval()
-    with torch.no_grad():
-        lp = flow.log_prob(x).cpu()
-    assert (lp - c['log_prob20']).abs().max().item() <= 5e-2 * (1 + c['log_prob20'].abs().max().item())
+        tol = 1e-3 if (not c['data_init'] or i == 0) else 3e-2
+        assert abs(a - b) <= tol * (1 + abs(b)), (i, a, b)
+    if not c['data_init']:
+        flow.eval()
+        with torch.no_grad():
+            lp = flow.log_prob(x).cpu()
+        assert (lp - c['log_prob20']).abs().max().item() <= 2e-2 * (1 + c['log_prob20'].abs().max().item())
 
 
 def test_readme_example(dev):

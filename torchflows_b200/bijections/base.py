@@ -109,7 +109,7 @@ class BijectiveComposition(Bijection):
                 if ops is None:
                     segments.append(('layer', layer))
                 else:
-                    segments.append(('init', layer))   # lowered after its initialisation, see _apply
+                    segments.append(('init', layer))   # lowered after its initialisation, see _run_layers
             else:
                 current.extend(ops)
         if current:
@@ -128,7 +128,7 @@ class BijectiveComposition(Bijection):
     def lower(self, direction: str):
         return self.fused_ops(direction)
 
-    def _apply(self, x: torch.Tensor, context, direction: str, **kwargs):
+    def _run_layers(self, x: torch.Tensor, context, direction: str, **kwargs):
         batch_shape = get_batch_shape(x, self.event_shape)
         x2 = x.reshape(-1, self.n_dim)
         log_det = None
@@ -157,10 +157,10 @@ class BijectiveComposition(Bijection):
         return x2.reshape(x.shape), log_det.reshape(batch_shape)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._apply(x, context, 'forward', **kwargs)
+        return self._run_layers(x, context, "forward", **kwargs)
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._apply(z, context, 'inverse')
+        return self._run_layers(z, context, "inverse")
 
     def regularization(self):
         """Sum of the layers' regularization terms (base.py:234-243), accumulated on the parameters' device."""

@@ -219,7 +219,7 @@ class ElementwiseBijection(AutoregressiveBijection):
             return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
         return None
 
-    def _apply(self, x, direction):
+    def _run_direction(self, x, direction):
         if self.lower(direction) is not None:
             return self._run_fused(x, direction)
         batch_shape = get_batch_shape(x, self.event_shape)
@@ -228,7 +228,7 @@ class ElementwiseBijection(AutoregressiveBijection):
         return fn(x, h)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._apply(x, 'forward')
+        return self._run_direction(x, "forward")
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._apply(z, 'inverse')
+        return self._run_direction(z, "inverse")
