@@ -119,6 +119,10 @@ int b2f_column_stats(const float *x, double *sum, double *sumsq, int64_t B, int3
 int32_t b2f_params_per_element(int32_t tkind, int32_t n_bins);
 int32_t b2f_padded_params(int32_t params_per_element);
 
+/* Diagnostic: one tcgen05 (kind::tf32) GEMM tile C[128,N] = A[128,K] * B[N,K]^T through the same descriptor and
+ * operand-layout code as the fused coupling kernel; used by the GPU tests to localise tensor-core layout bugs. */
+int b2f_debug_umma_gemm(const float *A, const float *B, float *C, int32_t N, int32_t K, void *stream);
+
 const char *b2f_last_error(void);
 int32_t b2f_abi_version(void);
 

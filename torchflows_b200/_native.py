@@ -55,6 +55,7 @@ def lib():
         L.b2f_transformer_apply.argtypes = [i32, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
+        L.b2f_debug_umma_gemm.argtypes = [vp, vp, vp, i32, i32, vp]
         _lib = L
     return _lib
 
@@ -147,3 +148,13 @@ def column_stats(x2: torch.Tensor):
     with torch.cuda.device(x2.device):
         check(lib().b2f_column_stats(ptr(x2), ptr(s), ptr(q), B, D, stream_ptr(x2.device)))
     return s, q
+
+
+def debug_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """C[128,N] = A[128,K] @ B[N,K]^T on the tensor cores (tf32), diagnostic entry point."""
+    A, B = require_cuda_f32(A, 'A'), require_cuda_f32(B, 'B')
+    assert A.shape[0] == 128 and A.shape[1] == B.shape[1]
+    C = torch.empty(128, B.shape[0], device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device):
+        check(lib().b2f_debug_umma_gemm(ptr(A), ptr(B), ptr(C), B.shape[0], A.shape[1], stream_ptr(A.device)))
+    return C
