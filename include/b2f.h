@@ -59,6 +59,15 @@ enum b2f_op_kind {
 #define B2F_FLAG_SEQ_LOGDET_EXACT 1 /* op flag: MADE_SEQ sums the true per-dimension log-dets instead of
                                        reproducing the reference's last-iteration value */
 
+#define B2F_FLAG_TC_OPERANDS 2      /* op flag (COUPLING, RQ): p[4], p[5] hold the tensor-core operand layouts:
+                                       p[4] = W1c: UMMA canonical K-major [32 x D/2] fp32 rounded to tf32 (rows >= H zero;
+                                              column k = physical index inside the source half);
+                                       p[5] = W2c: D/2/8 chunks, each canonical [192 x K2], K2 = roundup(H+2, 8):
+                                              row = 24*(element in chunk) + parameter, columns 0..H-1 = W2, column H / H+1
+                                              = tf32 hi / lo parts of b2, rest zero.  Byte offset of (row, k) in an operand
+                                              with K columns: (row/8)*K*32 + (k/4)*128 + (row%8)*16 + (k%4)*4 */
+#define B2F_FLAG_TC_FLIPPED 4       /* op flag: p[4] was laid out for a flipped tile (odd number of FLIP ops before) */
+
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
     int32_t tkind;    /* enum b2f_transformer */

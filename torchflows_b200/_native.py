@@ -15,6 +15,8 @@ T_SHIFT_ADD, T_SHIFT_SUB, T_AFFINE_FWD, T_AFFINE_INV, T_RQ_FWD, T_RQ_INV = range
 OP_ELEMENTWISE, OP_FLIP, OP_COUPLING, OP_MADE, OP_MADE_SEQ = range(5)
 MAX_OPS = 40
 FLAG_SEQ_LOGDET_EXACT = 1
+FLAG_TC_OPERANDS = 2
+FLAG_TC_FLIPPED = 4
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 

@@ -86,11 +86,69 @@ def kernel_params(op: LoweredOp) -> List[Optional[torch.Tensor]]:
     return out
 
 
-def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None):
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to the nearest tf32 value (10 explicit mantissa bits), kept in fp32 storage."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def umma_canonical(mat: torch.Tensor) -> torch.Tensor:
+    """[rows, K] -> flat tensor in the K-major no-swizzle UMMA operand order of csrc/b2f_umma.cuh:
+    float offset(row, k) = (row//8)*K*8 + (k//4)*32 + (row%8)*4 + k%4."""
+    rows, K = mat.shape
+    return mat.reshape(rows // 8, 8, K // 4, 4).permute(0, 2, 1, 3).contiguous().reshape(-1)
+
+
+def tc_eligible(op: LoweredOp, D: int) -> bool:
+    return (op.kind == N.OP_COUPLING and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV) and op.n_bins == 8
+            and D % 16 == 0 and 32 <= D <= 256 and 1 <= op.n_hidden <= 30)
+
+
+def tc_operands(op: LoweredOp, flipped: bool, D: int):
+    """Tensor-core operand layouts of a spline coupling layer (include/b2f.h, B2F_FLAG_TC_OPERANDS), cached per
+    parameter version: W1c [32 x D/2] and W2c [D/2/8 chunks][192 x K2] with the bias folded in as two K columns."""
+    W1, b1, W2, b2 = op.leafs
+    key = ('tc', bool(flipped))
+    ver = tuple((t.data_ptr(), t._version) for t in op.leafs)
+    cache = getattr(op.owner, '_b2f_cache', None)
+    if cache is None:
+        cache = {}
+        object.__setattr__(op.owner, '_b2f_cache', cache)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        H, Dh, P = W1.shape[0], D // 2, 23
+        W1p = W1.new_zeros(32, Dh)
+        W1p[:H] = W1.detach().flip(1) if flipped else W1.detach()
+        w1c = umma_canonical(round_tf32(W1p))
+        K2 = (H + 2 + 7) // 8 * 8
+        M = W2.new_zeros(Dh, 24, K2)
+        M[:, :P, :H] = round_tf32(W2.detach().reshape(Dh, P, H))
+        bias = b2.detach().reshape(Dh, P)
+        hi = round_tf32(bias)
+        M[:, :P, H] = hi
+        M[:, :P, H + 1] = round_tf32(bias - hi)
+        chunks = M.reshape(Dh // 8, 192, K2)
+        w2c = torch.cat([umma_canonical(c) for c in chunks])
+    out = (w1c, w2c)
+    cache[key] = (ver, out)
+    return out
+
+
+def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None,
+             D: Optional[int] = None):
     out = []
+    flipped = False
     for i, op in enumerate(ops):
+        p, flags = list(kernel_params(op)), op.flags
+        if op.kind == N.OP_FLIP:
+            flipped = not flipped
+        elif D is not None and grads is None and tc_eligible(op, D):
+            w1c, w2c = tc_operands(op, flipped, D)
+            p = p[:4] + [w1c, w2c]
+            flags |= N.FLAG_TC_OPERANDS | (N.FLAG_TC_FLIPPED if flipped else 0)
         out.append(dict(kind=op.kind, tkind=op.tkind, n_hidden=op.n_hidden, n_bins=op.n_bins, boundary=op.boundary,
-                        flags=op.flags, p=kernel_params(op), g=(grads[i] if grads is not None else [])))
+                        flags=flags, p=p, g=(grads[i] if grads is not None else [])))
     return out
 
 
@@ -108,7 +166,7 @@ class FlowFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2, cfg: _Cfg, *leafs):
-        y, ld, lp = N.flow_apply(op_dicts(cfg.ops), x2, True, True, cfg.want_log_prob, cfg.base_loc,
+        y, ld, lp = N.flow_apply(op_dicts(cfg.ops, D=x2.shape[1]), x2, True, True, cfg.want_log_prob, cfg.base_loc,
                                  cfg.base_log_scale, cfg.flags)
         ctx.cfg = cfg
         ctx.save_for_backward(x2, *leafs)
@@ -192,5 +250,6 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     if needs_grad:
         y, ld, lp = FlowFunction.apply(x2, _Cfg(ops, want_log_prob, base_loc, base_log_scale, flags), *leafs)
         return y, ld, (lp if want_log_prob else None)
-    y, ld, lp = N.flow_apply(op_dicts(ops), x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
+    y, ld, lp = N.flow_apply(op_dicts(ops, D=x2.shape[1]), x2.detach(), want_y, True, want_log_prob, base_loc,
+                             base_log_scale, flags)
     return y, ld, lp

@@ -229,6 +229,12 @@ static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 }  // namespace b2f
 
+namespace b2f {
+int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
+                       const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
+                       void* stream);   // b2f_flow_tc.cu
+}
+
 using namespace b2f;
 
 extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
@@ -237,6 +243,11 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
     if (!ops || n_ops < 0 || !x || D <= 0 || B < 0) return fail(B2F_ERR_INVALID, "b2f_flow_apply: bad arguments");
     if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: %d ops > B2F_MAX_OPS", n_ops);
     if (B == 0) return B2F_OK;
+    {
+        // CouplingRQNSF-shaped programs go to the tcgen05 kernel; everything else to the generic kernel below
+        const int rc = try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream);
+        if (rc != 0) return rc == 1 ? B2F_OK : rc;
+    }
     FlowArgs A;
     memset(&A, 0, sizeof(A));
     int Hmax = 1, has_seq = 0, has_rq = 0;

@@ -1,0 +1,447 @@
+// Tensor-core whole-flow kernel for rational-quadratic coupling flows (CouplingRQNSF): the conditioner GEMMs
+// run on tcgen05 (kind::tf32, accumulators in TMEM), the weight tiles are streamed by the TMA engine
+// (cp.async.bulk + mbarrier), and the spline transformer is the epilogue that reads its 23 parameters per
+// element straight out of TMEM.  One persistent CTA per SM; a tile = 128 samples (UMMA M = 128).
+//
+// Replaces the same reference code as b2f_flow.cu (bijections/base.py:203-232, layers_base.py:119-163,
+// transforms.py:293-307, spline/rational_quadratic.py:45-200, flows.py:628-648); the difference to the generic
+// kernel is only where the two Linear layers are evaluated.
+//
+// Shared memory (D = 256, H = 17: 213 KB):
+//   xlo, xhi   the two halves of the sample tile, each [128 x D/2] fp32 in the canonical K-major UMMA operand
+//              layout (b2f_umma.cuh).  They are BOTH the resident activations of the flow and the A operand of
+//              the first GEMM (the tensor core reads fp32 bit patterns as tf32), so x is never staged twice.
+//   w1         first Linear as B operand [32 x D/2] (hidden units padded to 32), bulk-copied per layer
+//   a2         tanh(hidden) as A operand of the second GEMM [128 x K2], K2 = roundup(H + 2, 8): columns H and
+//              H+1 are 1.0 and multiply the (hi, lo) split of the bias b2, so the bias is added by the MMA
+//   w2buf[2]   second Linear, one chunk = 8 target elements x 24 parameter rows = [192 x K2], double buffered
+// Tensor memory (512 columns): D2[0] cols 0..191, D2[1] cols 192..383 (chunk accumulators, ping-pong against the
+// epilogue), D1 cols 384..415 (hidden pre-activations).
+//
+// Warp roles: warps 0..15 epilogue (warp w owns TMEM lanes 32*(w%4).., and elements 2*(w/4), 2*(w/4)+1 of each
+// chunk; a thread owns one sample, so log-det accumulates in a register), warp 16 issues every tcgen05.mma,
+// warp 17 drives the TMA loads.  All hand-offs are mbarriers; waits are bounded (trap instead of hang).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "b2f_flow_device.cuh"
+#include "b2f_umma.cuh"
+
+namespace b2f {
+
+constexpr int kTcEpiWarps = 16;
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
+constexpr int kTcChunkElems = 8;                     // target elements per GEMM2 chunk
+constexpr int kTcChunkRows = kTcChunkElems * 24;     // 192 = UMMA N of GEMM2
+constexpr int kTcN1 = 32;                            // UMMA N of GEMM1 (hidden units, padded)
+constexpr int kTcTmemCols = 512;
+constexpr int kTcColD1 = 384;
+
+struct TcOp {
+    int kind, tkind, H, K2;
+    float boundary;
+    int flip_before;            // flip state when this op runs (host-computed)
+    const float* value;         // ELEMENTWISE: (D,2)
+    const float* b1;            // COUPLING: (32) padded
+    const float* w1c;           // canonical [32 x Ds]
+    const float* w2c;           // n_chunks x canonical [192 x K2]
+};
+
+struct TcArgs {
+    TcOp ops[B2F_MAX_OPS];
+    int n_ops, D, flags, n_tiles;
+    long long B;
+    const float* x;
+    float* y;
+    float* log_det;
+    float* log_prob;
+    const float* base_loc;
+    const float* base_log_scale;
+};
+
+struct TcSmem {
+    float* xlo;
+    float* xhi;
+    float* w1;
+    float* a2;
+    float* w2buf;      // two chunk buffers, w2stride floats apart
+    int w2stride;
+    float* ldp;     // [4][128]
+    float* ldacc;   // [128]
+    float* lpin;    // [128]
+    float* ea;      // [3*D]
+    float* ldc;     // [1]
+    uint64_t* bars; // see enum
+    uint32_t* tmem_ptr;
+};
+
+enum { BAR_W1_FULL = 0, BAR_W1_EMPTY, BAR_A1_READY, BAR_D1_FULL, BAR_A2_FULL, BAR_W2_FULL0, BAR_W2_FULL1,
+       BAR_W2_EMPTY0, BAR_W2_EMPTY1, BAR_D2_FULL0, BAR_D2_FULL1, BAR_D2_EMPTY0, BAR_D2_EMPTY1, BAR_COUNT };
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory"); }
+
+__device__ __forceinline__ float to_tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// physical location of logical column j: halves are [0, Dh) -> xlo, [Dh, D) -> xhi
+__device__ __forceinline__ float* xaddr(const TcSmem& s, int Dh, int m, int c) {
+    float* base = c < Dh ? s.xlo : s.xhi;
+    const int k = c < Dh ? c : c - Dh;
+    return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + umma::canon_off(m, k, Dh));
+}
+
+// chunk loop of one coupling layer for one epilogue thread: wait for the chunk's accumulator, pull the 24
+// parameter columns of each of its two elements out of TMEM, apply the spline, hand the buffer back.
+template <int TK, int MODE>
+__device__ __forceinline__ float tc_chunk_loop(const TcSmem& s, const TcOp& op, uint32_t tbase, uint32_t lane_addr,
+                                               int Dh, int m_t, int sub, int lane, uint32_t& cc) {
+    const int n_chunks = Dh / kTcChunkElems;
+    uint8_t* tgt = reinterpret_cast<uint8_t*>(op.flip_before ? s.xlo : s.xhi);   // logical target half
+    float ldpart = 0.0f;
+    for (int c = 0; c < n_chunks; ++c, ++cc) {
+        const int b = cc & 1;
+        umma::mbar_wait(&s.bars[BAR_D2_FULL0 + b], (cc >> 1) & 1);
+        umma::tc_fence_after_sync();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int el = sub * 2 + i;
+            const int e = c * kTcChunkElems + el;                  // logical target element
+            float acc[24];
+            const uint32_t ta = tbase + lane_addr + b * kTcChunkRows + el * 24;
+            umma::tmem_ld8_nowait<0>(ta, acc);
+            umma::tmem_ld8_nowait<8>(ta + 8, acc);
+            umma::tmem_ld8_nowait<16>(ta + 16, acc);
+            umma::tmem_ld_wait();
+            const int k_loc = op.flip_before ? Dh - 1 - e : e;
+            float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
+            float out, ld;
+            transform_element<TK, MODE, 24>(*px, acc, op.boundary, out, ld);
+            *px = out;
+            ldpart += ld;
+        }
+        umma::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) umma::mbar_arrive(&s.bars[BAR_D2_EMPTY0 + b]);
+    }
+    return ldpart;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_constant__ TcArgs A) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int D = A.D, Dh = D >> 1;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- carve shared memory -----------------------------------------------------------------------------
+    int K2max = 8;
+    for (int i = 0; i < A.n_ops; ++i)
+        if (A.ops[i].kind == B2F_OP_COUPLING) K2max = max(K2max, A.ops[i].K2);
+    TcSmem s;
+    uint8_t* p = smem_raw;
+    s.xlo = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
+    s.xhi = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
+    s.w1 = reinterpret_cast<float*>(p); p += kTcN1 * Dh * 4;
+    s.a2 = reinterpret_cast<float*>(p); p += 128 * K2max * 4;
+    s.w2buf = reinterpret_cast<float*>(p); p += 2 * kTcChunkRows * K2max * 4;
+    s.w2stride = kTcChunkRows * K2max;
+    s.ldp = reinterpret_cast<float*>(p); p += 4 * 128 * 4;
+    s.ldacc = reinterpret_cast<float*>(p); p += 128 * 4;
+    s.lpin = reinterpret_cast<float*>(p); p += 128 * 4;
+    s.ea = reinterpret_cast<float*>(p); p += 3 * D * 4;
+    s.ldc = reinterpret_cast<float*>(p); p += 16;
+    s.bars = reinterpret_cast<uint64_t*>(p); p += BAR_COUNT * 8;
+    s.tmem_ptr = reinterpret_cast<uint32_t*>(p);
+
+    if (tid == 0) {
+        umma::mbar_init(&s.bars[BAR_W1_FULL], 1);
+        umma::mbar_init(&s.bars[BAR_W1_EMPTY], 1);
+        umma::mbar_init(&s.bars[BAR_A1_READY], kTcEpiWarps);
+        umma::mbar_init(&s.bars[BAR_D1_FULL], 1);
+        umma::mbar_init(&s.bars[BAR_A2_FULL], 4);
+        for (int b = 0; b < 2; ++b) {
+            umma::mbar_init(&s.bars[BAR_W2_FULL0 + b], 1);
+            umma::mbar_init(&s.bars[BAR_W2_EMPTY0 + b], 1);
+            umma::mbar_init(&s.bars[BAR_D2_FULL0 + b], 1);
+            umma::mbar_init(&s.bars[BAR_D2_EMPTY0 + b], kTcEpiWarps);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == kTcEpiWarps) umma::tmem_alloc(s.tmem_ptr, kTcTmemCols);
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    umma::tc_fence_after_sync();
+    const uint32_t tbase = *s.tmem_ptr;
+
+    uint32_t lc = 0;   // coupling layers processed so far (all roles count identically)
+    uint32_t cc = 0;   // GEMM2 chunks processed so far
+
+    if (warp == kTcEpiWarps + 1) {
+        // ===================== TMA loader (one thread) =====================
+        if (lane == 0) {
+            for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+                for (int oi = 0; oi < A.n_ops; ++oi) {
+                    const TcOp& op = A.ops[oi];
+                    if (op.kind != B2F_OP_COUPLING) continue;
+                    umma::mbar_wait(&s.bars[BAR_W1_EMPTY], (lc & 1) ^ 1);
+                    const uint32_t w1_bytes = kTcN1 * Dh * 4;
+                    umma::mbar_arrive_expect_tx(&s.bars[BAR_W1_FULL], w1_bytes);
+                    umma::bulk_g2s(s.w1, op.w1c, w1_bytes, &s.bars[BAR_W1_FULL]);
+                    const int n_chunks = Dh / kTcChunkElems;
+                    const uint32_t ch_bytes = kTcChunkRows * op.K2 * 4;
+                    for (int c = 0; c < n_chunks; ++c, ++cc) {
+                        const int b = cc & 1;
+                        umma::mbar_wait(&s.bars[BAR_W2_EMPTY0 + b], ((cc >> 1) & 1) ^ 1);
+                        umma::mbar_arrive_expect_tx(&s.bars[BAR_W2_FULL0 + b], ch_bytes);
+                        umma::bulk_g2s(s.w2buf + b * s.w2stride, reinterpret_cast<const uint8_t*>(op.w2c) + (size_t)c * ch_bytes, ch_bytes,
+                                       &s.bars[BAR_W2_FULL0 + b]);
+                    }
+                    ++lc;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kTcEpiWarps) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+                for (int oi = 0; oi < A.n_ops; ++oi) {
+                    const TcOp& op = A.ops[oi];
+                    if (op.kind != B2F_OP_COUPLING) continue;
+                    const uint32_t ph = lc & 1;
+                    umma::mbar_wait(&s.bars[BAR_W1_FULL], ph);
+                    umma::mbar_wait(&s.bars[BAR_A1_READY], ph);
+                    umma::tc_fence_after_sync();
+                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T
+                    const uint32_t a1 = umma::smem_u32(op.flip_before ? s.xhi : s.xlo);
+                    const uint32_t b1a = umma::smem_u32(s.w1);
+                    const uint32_t idesc1 = umma::make_idesc_tf32(128, kTcN1);
+                    for (int ks = 0; ks < Dh / 8; ++ks)
+                        umma::mma_tf32_ss(tbase + kTcColD1, umma::make_smem_desc(a1 + ks * 256, 128, Dh * 32),
+                                          umma::make_smem_desc(b1a + ks * 256, 128, Dh * 32), idesc1, ks > 0);
+                    umma::mma_commit(&s.bars[BAR_D1_FULL]);
+                    umma::mma_commit(&s.bars[BAR_W1_EMPTY]);
+                    umma::mbar_wait(&s.bars[BAR_A2_FULL], ph);
+                    umma::tc_fence_after_sync();
+                    const uint32_t a2a = umma::smem_u32(s.a2);
+                    const uint32_t idesc2 = umma::make_idesc_tf32(128, kTcChunkRows);
+                    const int n_chunks = Dh / kTcChunkElems;
+                    for (int c = 0; c < n_chunks; ++c, ++cc) {
+                        const int b = cc & 1;
+                        const uint32_t ph2 = (cc >> 1) & 1;
+                        umma::mbar_wait(&s.bars[BAR_W2_FULL0 + b], ph2);
+                        umma::mbar_wait(&s.bars[BAR_D2_EMPTY0 + b], ph2 ^ 1);
+                        umma::tc_fence_after_sync();
+                        const uint32_t wb = umma::smem_u32(s.w2buf + b * s.w2stride);
+                        for (int ks = 0; ks < op.K2 / 8; ++ks)
+                            umma::mma_tf32_ss(tbase + b * kTcChunkRows, umma::make_smem_desc(a2a + ks * 256, 128, op.K2 * 32),
+                                              umma::make_smem_desc(wb + ks * 256, 128, op.K2 * 32), idesc2, ks > 0);
+                        umma::mma_commit(&s.bars[BAR_D2_FULL0 + b]);
+                        umma::mma_commit(&s.bars[BAR_W2_EMPTY0 + b]);
+                    }
+                    ++lc;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3, sub = warp >> 2;          // TMEM lane quarter, element pair inside a chunk
+        const int m_t = q * 32 + lane;                    // sample owned in the transformer phase
+        const int rg = warp;                              // 8-row group owned in the elementwise / IO phases
+        const int r8 = lane & 7, kq = lane >> 3;          // row inside the group, 16-byte chunk inside a 64-byte run
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+            const long long row0 = (long long)tile * 128;
+            const int rows = (int)min(128LL, A.B - row0);
+            // ---- load: a warp moves an 8-row group; 8 lanes x 16 B fill one core matrix (conflict-free) ----
+            {
+                const int m = rg * 8 + r8;
+                const bool live = m < rows;
+                const float4* src = reinterpret_cast<const float4*>(A.x + (row0 + m) * D);
+                for (int kc = kq; kc < D / 4; kc += 4) {
+                    const float4 v = live ? __ldg(src + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(xaddr(s, Dh, m, 4 * kc)) = v;
+                }
+            }
+            if (tid < 128) s.ldacc[tid] = 0.0f;
+            if (tid == 0) s.ldc[0] = 0.0f;
+            epi_sync();
+            int flip = 0;
+            const bool want_lp = A.log_prob != nullptr;
+            // Gaussian base density of rows (warp owns its 8-row group; 4 lanes per row, shuffle reduction)
+            auto base_logp = [&]() {
+                const int m = rg * 8 + r8;
+                float acc = 0.0f;
+                for (int kc = kq; kc < D / 4; kc += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(xaddr(s, Dh, m, 4 * kc));
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = 4 * kc + i, j = flip ? D - 1 - c : c;
+                        const float loc = A.base_loc ? __ldg(A.base_loc + j) : 0.0f;
+                        const float lsc = A.base_log_scale ? __ldg(A.base_log_scale + j) : 0.0f;
+                        acc += gauss_logp(vv[i], loc, lsc);
+                    }
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                if (kq == 0) s.lpin[m] = acc;
+            };
+            if (want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp();
+
+            for (int oi = 0; oi < A.n_ops; ++oi) {
+                const TcOp& op = A.ops[oi];
+                if (op.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
+                if (op.kind == B2F_OP_ELEMENTWISE) {
+                    for (int j = tid; j < D; j += kTcEpiWarps * 32) {
+                        float a, la;
+                        affine_scale<0>(__ldg(op.value + 2 * j), a, la);
+                        s.ea[j] = a; s.ea[D + j] = __ldg(op.value + 2 * j + 1); s.ea[2 * D + j] = la;
+                    }
+                    epi_sync();
+                    const bool fwd = op.tkind == B2F_T_AFFINE_FWD;
+                    const int m = rg * 8 + r8;
+                    for (int kc = kq; kc < D / 4; kc += 4) {
+                        float4* px = reinterpret_cast<float4*>(xaddr(s, Dh, m, 4 * kc));
+                        float4 v = *px;
+                        float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int c = 4 * kc + i, j = flip ? D - 1 - c : c;
+                            vv[i] = fwd ? fmaf(s.ea[j], vv[i], s.ea[D + j]) : (vv[i] - s.ea[D + j]) / s.ea[j];
+                        }
+                        *px = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                    }
+                    if (warp == 0) {
+                        float sum = 0.0f;
+                        for (int j = lane; j < D; j += 32) sum += s.ea[2 * D + j];
+                        sum = warp_sum(sum);
+                        if (lane == 0) s.ldc[0] += fwd ? sum : -sum;
+                    }
+                    epi_sync();
+                    continue;
+                }
+                // ---------------- coupling layer ----------------
+                const uint32_t ph = lc & 1;
+                umma::fence_proxy_async_smem();            // our generic-proxy writes to xlo/xhi -> tensor core
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&s.bars[BAR_A1_READY]);
+                if (warp < 4) {
+                    // hidden epilogue: D1 -> +b1 -> tanh -> tf32 -> a2 (A operand of GEMM2), bias columns = 1
+                    umma::mbar_wait(&s.bars[BAR_D1_FULL], ph);
+                    umma::tc_fence_after_sync();
+                    const int K2 = op.K2, H = op.H;
+                    uint8_t* a2row = reinterpret_cast<uint8_t*>(s.a2);
+#pragma unroll
+                    for (int c0 = 0; c0 < kTcN1; c0 += 8) {
+                        float v[8];
+                        umma::tmem_ld8(tbase + lane_addr + kTcColD1 + c0, v);
+                        umma::tmem_ld_wait();
+                        if (c0 < K2) {
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int j = c0 + i;
+                                o[i] = j < H ? to_tf32_rn(tanhf(v[i] + __ldg(op.b1 + j))) : ((j == H || j == H + 1) ? 1.0f : 0.0f);
+                            }
+                            *reinterpret_cast<float4*>(a2row + umma::canon_off(m_t, c0, K2)) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(a2row + umma::canon_off(m_t, c0 + 4, K2)) = make_float4(o[4], o[5], o[6], o[7]);
+                        }
+                    }
+                    umma::tc_fence_before_sync();
+                    umma::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&s.bars[BAR_A2_FULL]);
+                }
+                float ldpart;
+                if (op.tkind == B2F_T_RQ_FWD) ldpart = tc_chunk_loop<B2F_T_RQ_FWD, MODE>(s, op, tbase, lane_addr, Dh, m_t, sub, lane, cc);
+                else ldpart = tc_chunk_loop<B2F_T_RQ_INV, MODE>(s, op, tbase, lane_addr, Dh, m_t, sub, lane, cc);
+                s.ldp[sub * 128 + m_t] = ldpart;
+                epi_sync();
+                if (tid < 128) s.ldacc[tid] += (s.ldp[tid] + s.ldp[128 + tid]) + (s.ldp[256 + tid] + s.ldp[384 + tid]);
+                epi_sync();
+                ++lc;
+            }
+            // ---- outputs of this tile ----
+            if (want_lp && !(A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp();
+            epi_sync();
+            if (tid < rows) {
+                const float ld = s.ldacc[tid] + s.ldc[0];
+                if (A.log_det) A.log_det[row0 + tid] = ld;
+                if (want_lp) A.log_prob[row0 + tid] = s.lpin[tid] + ld;
+            }
+            if (A.y) {
+                const int m = rg * 8 + r8;
+                if (m < rows) {
+                    float4* dst = reinterpret_cast<float4*>(A.y + (row0 + m) * D);
+                    for (int kc = kq; kc < D / 4; kc += 4)
+                        dst[kc] = *reinterpret_cast<const float4*>(xaddr(s, Dh, m, 4 * kc));   // host guarantees flip == 0 here
+                }
+            }
+            epi_sync();   // the tile buffers are reused by the next tile's load
+        }
+    }
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kTcEpiWarps) umma::tmem_dealloc(tbase, kTcTmemCols);
+}
+
+}  // namespace b2f
+
+namespace b2f {
+
+// Returns 1 if the tensor-core kernel was launched, 0 if the program is not eligible (caller falls through to the
+// generic kernel -- same library, same results up to tf32 rounding of the conditioner), < 0 on error.
+int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
+                       const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
+                       void* stream) {
+    if (getenv("B2F_DISABLE_TC")) return 0;
+    if (D % 16 != 0 || D < 32 || D > 256) return 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (y && (reinterpret_cast<uintptr_t>(y) & 15))) return 0;
+    int flip = 0, n_coupling = 0, K2max = 8;
+    TcArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int i = 0; i < n_ops; ++i) {
+        const b2f_op_t& o = ops[i];
+        TcOp& t = A.ops[i];
+        t.kind = o.kind; t.tkind = o.tkind; t.H = o.n_hidden; t.boundary = o.boundary; t.flip_before = flip;
+        if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
+        if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
+        if (o.kind != B2F_OP_COUPLING) return 0;
+        if (o.tkind != B2F_T_RQ_FWD && o.tkind != B2F_T_RQ_INV) return 0;
+        if (!(o.flags & B2F_FLAG_TC_OPERANDS) || !o.p[4] || !o.p[5] || !o.p[1]) return 0;
+        if (o.n_bins != 8 || o.n_hidden < 1 || o.n_hidden > 30) return 0;
+        if (((o.flags & B2F_FLAG_TC_FLIPPED) != 0) != (flip != 0))
+            return fail(B2F_ERR_INVALID, "op %d: tensor-core operands were laid out for the wrong flip state", i);
+        t.K2 = (o.n_hidden + 2 + 7) / 8 * 8;
+        K2max = std::max(K2max, t.K2);
+        t.b1 = (const float*)o.p[1]; t.w1c = (const float*)o.p[4]; t.w2c = (const float*)o.p[5];
+        if ((reinterpret_cast<uintptr_t>(t.w1c) & 15) || (reinterpret_cast<uintptr_t>(t.w2c) & 15)) return 0;
+        ++n_coupling;
+    }
+    if (flip != 0 || n_coupling == 0) return 0;
+    const int Dh = D / 2;
+    const size_t smem = (size_t)2 * 128 * Dh * 4 + (size_t)kTcN1 * Dh * 4 + (size_t)128 * K2max * 4 +
+                        (size_t)2 * kTcChunkRows * K2max * 4 + (size_t)(4 * 128 + 128 + 128 + 3 * D) * 4 + 16 +
+                        BAR_COUNT * 8 + 16;
+    if (smem > 227 * 1024) return 0;
+    A.n_ops = n_ops; A.D = D; A.flags = flags; A.B = B;
+    A.n_tiles = (int)((B + 127) / 128);
+    A.x = x; A.y = y; A.log_det = log_det; A.log_prob = log_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(A.n_tiles, n_sm);
+    auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_tc_kernel<0> : flow_tc_kernel<1>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute(tc): %s", cudaGetErrorString(ce));
+    kern<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
+    const int rc = check_launch("b2f_flow_apply (tensor-core kernel)");
+    return rc == B2F_OK ? 1 : rc;
+}
+
+}  // namespace b2f

@@ -73,6 +73,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 consecutive columns into v[OFF..OFF+8) (register-resident: constant indices); valid after tmem_ld_wait()
+template <int OFF, int N>
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[N]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[OFF + 0]), "=f"(v[OFF + 1]), "=f"(v[OFF + 2]), "=f"(v[OFF + 3]), "=f"(v[OFF + 4]),
+                   "=f"(v[OFF + 5]), "=f"(v[OFF + 6]), "=f"(v[OFF + 7])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -------------------------------------------------------------------------------------------------------
