@@ -36,17 +36,16 @@
 #define MAX_BINS 64
 
 static float oexp(float t) {
-    /* exp for t <= 0: n = rint(t*log2e), Cody-Waite reduction, degree-6 polynomial, exponent add */
+    /* exp for t <= 0: n = rint(t*log2e), f = t - n*ln2 (one fma), degree-6 polynomial, exponent add */
     if (t < -86.0f) t = -86.0f;
     const float magic = 12582912.0f;
     float r = fmaf(t, 0x1.715476p+0f, magic);
     float n = r - magic;
-    float f = fmaf(n, -0x1.62e4p-1f, t);
-    f = fmaf(n, -0x1.7f7d1cp-20f, f);
-    float p = 0x1.6ae72p-10f;
-    p = fmaf(p, f, 0x1.126792p-7f);
-    p = fmaf(p, f, 0x1.555822p-5f);
-    p = fmaf(p, f, 0x1.55541ap-3f);
+    float f = fmaf(n, -0x1.62e430p-1f, t);
+    float p = 0x1.6ada7ap-10f;
+    p = fmaf(p, f, 0x1.127528p-7f);
+    p = fmaf(p, f, 0x1.55585ep-5f);
+    p = fmaf(p, f, 0x1.5554p-3f);
     p = fmaf(p, f, 0x1.fffffcp-2f);
     p = fmaf(p, f, 1.0f);
     p = fmaf(p, f, 1.0f);

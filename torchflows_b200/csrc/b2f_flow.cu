@@ -163,17 +163,24 @@ __global__ void __launch_bounds__(512) flow_kernel(const __grid_constant__ FlowA
         const DevOp& op = A.ops[oi];
         if (op.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
         if (op.kind == B2F_OP_ELEMENTWISE) {
-            elementwise_stage(ea, op, D);
+            auto get = [&](int i) { return EwOp{A.ops[i].kind, A.ops[i].tkind, A.ops[i].p0}; };
+            const int n_run = elementwise_stage_run(ea, get, oi, A.n_ops, D, tid, NT);
             __syncthreads();
-            const bool fwd = op.tkind == B2F_T_AFFINE_FWD;
-            elementwise_apply(t, ea, fwd);
-            if (warp == 0) {   // log-det = +-sum_j log alpha_j, identical for every sample
+            for (int m = warp; m < TM; m += NW) {
+                float* xr = t.xt + m * XS;
+                for (int j = lane; j < D; j += 32) {
+                    const int c = t.col(j);
+                    xr[c] = fmaf(ea[j], xr[c], ea[D + j]);
+                }
+            }
+            if (warp == 0) {   // log-det of the run, identical for every sample
                 float s = 0.0f;
                 for (int j = lane; j < D; j += 32) s += ea[2 * D + j];
                 s = warp_sum(s);
-                if (lane == 0) ldc[0] += fwd ? s : -s;
+                if (lane == 0) ldc[0] += s;
             }
             __syncthreads();
+            oi += n_run - 1;
             continue;
         }
         const bool coupling = op.kind == B2F_OP_COUPLING;

@@ -154,6 +154,30 @@ __device__ __forceinline__ void elementwise_apply(const Tile& t, const float* ea
     }
 }
 
+// A run of consecutive elementwise layers is ONE affine map per column, z = A_j*x + B_j (composition of
+// a*x+b and (x-b)/a steps); the batch-independent log-det of the run is sum_j L_j.  `get(i)` returns the
+// (kind, tkind, value pointer) of op i.  Stages ea[j] = A_j, ea[D+j] = B_j, ea[2D+j] = L_j and returns how many
+// ops the run covers (>= 1).
+struct EwOp { int kind, tkind; const float* value; };
+template <class Get>
+__device__ __forceinline__ int elementwise_stage_run(float* ea, const Get& get, int oi, int n_ops, int D, int tid, int nthreads) {
+    int n_run = 1;
+    while (oi + n_run < n_ops && get(oi + n_run).kind == B2F_OP_ELEMENTWISE) ++n_run;
+    for (int j = tid; j < D; j += nthreads) {
+        float Aj = 1.0f, Bj = 0.0f, Lj = 0.0f;
+        for (int r = 0; r < n_run; ++r) {
+            const EwOp o = get(oi + r);
+            float a, la;
+            affine_scale<0>(__ldg(o.value + 2 * j), a, la);
+            const float b = __ldg(o.value + 2 * j + 1);
+            if (o.tkind == B2F_T_AFFINE_FWD) { Aj *= a; Bj = fmaf(a, Bj, b); Lj += la; }
+            else { const float ia = 1.0f / a; Aj *= ia; Bj = (Bj - b) * ia; Lj -= la; }
+        }
+        ea[j] = Aj; ea[D + j] = Bj; ea[2 * D + j] = Lj;
+    }
+    return n_run;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

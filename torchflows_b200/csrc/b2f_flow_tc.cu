@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                 for (int oi = 0; oi < A.n_ops; ++oi) {
                     const TcOp& op = A.ops[oi];
                     if (op.kind != B2F_OP_COUPLING) continue;
-                    umma::mbar_wait(&s.bars[BAR_W1_EMPTY], (lc & 1) ^ 1);
+                    umma::mbar_wait_backoff(&s.bars[BAR_W1_EMPTY], (lc & 1) ^ 1);
                     const uint32_t w1_bytes = kTcN1 * Dh * 4;
                     umma::mbar_arrive_expect_tx(&s.bars[BAR_W1_FULL], w1_bytes);
                     umma::bulk_g2s(s.w1, op.w1c, w1_bytes, &s.bars[BAR_W1_FULL]);
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     const uint32_t ch_bytes = kTcChunkRows * op.K2 * 4;
                     for (int c = 0; c < n_chunks; ++c, ++cc) {
                         const int b = cc & 1;
-                        umma::mbar_wait(&s.bars[BAR_W2_EMPTY0 + b], ((cc >> 1) & 1) ^ 1);
+                        umma::mbar_wait_backoff(&s.bars[BAR_W2_EMPTY0 + b], ((cc >> 1) & 1) ^ 1);
                         umma::mbar_arrive_expect_tx(&s.bars[BAR_W2_FULL0 + b], ch_bytes);
                         umma::bulk_g2s(s.w2buf + b * s.w2stride, reinterpret_cast<const uint8_t*>(op.w2c) + (size_t)c * ch_bytes, ch_bytes,
                                        &s.bars[BAR_W2_FULL0 + b]);
@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     const TcOp& op = A.ops[oi];
                     if (op.kind != B2F_OP_COUPLING) continue;
                     const uint32_t ph = lc & 1;
-                    umma::mbar_wait(&s.bars[BAR_W1_FULL], ph);
-                    umma::mbar_wait(&s.bars[BAR_A1_READY], ph);
+                    umma::mbar_wait_backoff(&s.bars[BAR_W1_FULL], ph);
+                    umma::mbar_wait_backoff(&s.bars[BAR_A1_READY], ph);
                     umma::tc_fence_after_sync();
                     // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T
                     const uint32_t a1 = umma::smem_u32(op.flip_before ? s.xhi : s.xlo);
@@ -232,8 +232,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     for (int c = 0; c < n_chunks; ++c, ++cc) {
                         const int b = cc & 1;
                         const uint32_t ph2 = (cc >> 1) & 1;
-                        umma::mbar_wait(&s.bars[BAR_W2_FULL0 + b], ph2);
-                        umma::mbar_wait(&s.bars[BAR_D2_EMPTY0 + b], ph2 ^ 1);
+                        umma::mbar_wait_backoff(&s.bars[BAR_W2_FULL0 + b], ph2);
+                        umma::mbar_wait_backoff(&s.bars[BAR_D2_EMPTY0 + b], ph2 ^ 1);
                         umma::tc_fence_after_sync();
                         const uint32_t wb = umma::smem_u32(s.w2buf + b * s.w2stride);
                         for (int ks = 0; ks < op.K2 / 8; ++ks)
@@ -297,13 +297,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                 const TcOp& op = A.ops[oi];
                 if (op.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
                 if (op.kind == B2F_OP_ELEMENTWISE) {
-                    for (int j = tid; j < D; j += kTcEpiWarps * 32) {
-                        float a, la;
-                        affine_scale<0>(__ldg(op.value + 2 * j), a, la);
-                        s.ea[j] = a; s.ea[D + j] = __ldg(op.value + 2 * j + 1); s.ea[2 * D + j] = la;
-                    }
+                    auto get = [&](int i) { return EwOp{A.ops[i].kind, A.ops[i].tkind, A.ops[i].value}; };
+                    const int n_run = elementwise_stage_run(s.ea, get, oi, A.n_ops, D, tid, kTcEpiWarps * 32);
                     epi_sync();
-                    const bool fwd = op.tkind == B2F_T_AFFINE_FWD;
                     const int m = rg * 8 + r8;
                     for (int kc = kq; kc < D / 4; kc += 4) {
                         float4* px = reinterpret_cast<float4*>(xaddr(s, Dh, m, 4 * kc));
@@ -312,7 +308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int c = 4 * kc + i, j = flip ? D - 1 - c : c;
-                            vv[i] = fwd ? fmaf(s.ea[j], vv[i], s.ea[D + j]) : (vv[i] - s.ea[D + j]) / s.ea[j];
+                            vv[i] = fmaf(s.ea[j], vv[i], s.ea[D + j]);
                         }
                         *px = make_float4(vv[0], vv[1], vv[2], vv[3]);
                     }
@@ -320,9 +316,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                         float sum = 0.0f;
                         for (int j = lane; j < D; j += 32) sum += s.ea[2 * D + j];
                         sum = warp_sum(sum);
-                        if (lane == 0) s.ldc[0] += fwd ? sum : -sum;
+                        if (lane == 0) s.ldc[0] += sum;
                     }
                     epi_sync();
+                    oi += n_run - 1;
                     continue;
                 }
                 // ---------------- coupling layer ----------------
