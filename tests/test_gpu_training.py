@@ -148,3 +148,50 @@ def test_fit_options_smoke(dev):
     flow = Flow(MAF(4)).to(dev)
     flow.fit(torch.randn(5000, 4), n_epochs=12, batch_size='adaptive', w_train=torch.rand(5000))
     assert not flow.training
+
+
+def test_composite_path_matches_fused_path(dev):
+    """Layers outside the fused kernels' budget (e.g. D=1024 with n_hidden=1024) run as a composite: conditioner as
+    library GEMMs + stand-alone transformer kernels.  Same weights through both paths must agree (values and gradients)."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF, RealNVP
+    for cls, D in ((CouplingRQNSF, 16), (RealNVP, 10)):
+        torch.manual_seed(3)
+        fused = Flow(cls(D)).to(dev).eval()
+        comp = Flow(cls(D)).to(dev).eval()
+        comp.load_state_dict(fused.state_dict())
+        for layer in comp.bijection.layers:
+            if hasattr(layer, '_fusable'):
+                layer._fusable = False
+            if hasattr(layer, 'use_global_parameters'):
+                layer.lower = lambda direction: None          # elementwise layers through the transformer kernel
+        assert comp.bijection.lower('forward') is None
+        x = torch.randn(257, D, device=dev)
+        outs = []
+        for flow in (fused, comp):
+            xi = x.clone().requires_grad_(True)
+            loss = flow._base_batch_loss((xi, torch.ones(257, device=dev)))
+            loss.backward()
+            outs.append((loss.detach(), xi.grad, {k: p.grad for k, p in flow.named_parameters() if p.grad is not None}))
+            with torch.no_grad():
+                outs[-1] += (flow._sample_from_base(x, no_grad=True),)
+        assert abs(float(outs[0][0]) - float(outs[1][0])) < 1e-5 * (1 + abs(float(outs[0][0])))
+        assert rel(outs[1][1], outs[0][1]) < 1e-3
+        for k, g in outs[0][2].items():
+            if g.numel() and g.norm() > 0:
+                assert rel(outs[1][2][k], g) < 2e-3, k
+        assert rel(outs[1][3], outs[0][3]) < 1e-4
+
+
+def test_wide_config_fit_step_runs(dev):
+    """BASELINE configs[4] shape (scaled-down batch): one fit step of CouplingRQNSF(1024, n_hidden=1024) is finite."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF
+    torch.manual_seed(0)
+    flow = Flow(CouplingRQNSF(1024, conditioner_kwargs={'n_hidden': 1024})).to(dev)
+    assert sum(p.numel() for p in flow.parameters() if p.requires_grad) == 25195520
+    x = torch.randn(512, 1024, device=dev)
+    flow.train()
+    l0 = float(flow.train_step(x))
+    l1 = float(flow.train_step(x))
+    assert l0 == l0 and l1 == l1 and abs(l1) < 1e6

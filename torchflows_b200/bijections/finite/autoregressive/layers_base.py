@@ -28,6 +28,14 @@ def _no_context(context_shape, what: str):
                                   '(SURVEY section 8f-1); construct with context_shape=None')
 
 
+def _fits_fused_kernel(n_dim: int, n_hidden: int) -> bool:
+    """Mirror of the shared-memory budget of csrc/b2f_flow.cu at its smallest tile (32 samples): the sample tile
+    [32][D|1] plus the hidden activations [32][H|1] (twice for the backward kernel's gradient tile) must fit in
+    ~200 KB.  Wider layers (e.g. D=1024 with n_hidden=1024) run as a composite: library GEMMs for the conditioner and
+    the stand-alone transformer kernel."""
+    return 4 * (2 * 32 * (n_dim | 1) + 2 * 32 * (n_hidden | 1) + 3 * n_dim + 32 * 24 * 8 + 1024) <= 200 * 1024
+
+
 def _transformer_fusable(tr) -> bool:
     if isinstance(tr, RationalQuadratic):
         return tr.n_bins == 8
@@ -79,7 +87,8 @@ class CouplingBijection(AutoregressiveBijection):
         self.coupling = coupling
         ct = conditioner_transform
         self._fusable = (isinstance(coupling, HalfSplit) and type(ct) is FeedForward and ct.n_layers == 2
-                         and ct.nonlinearity is nn.Tanh and ct.is_plain and _transformer_fusable(transformer))
+                         and ct.nonlinearity is nn.Tanh and ct.is_plain and _transformer_fusable(transformer)
+                         and _fits_fused_kernel(self.n_dim, ct.n_hidden))
 
     # -- reference API ---------------------------------------------------------------------------------------
     def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
@@ -115,13 +124,21 @@ class CouplingBijection(AutoregressiveBijection):
         """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""
         batch_shape = get_batch_shape(x, self.event_shape)
         xf = flatten_event(x, self.event_shape)
-        src, tgt = self.coupling.source_mask.view(-1).to(x.device), self.coupling.target_mask.view(-1).to(x.device)
-        h = self.conditioner_transform(xf[..., src], context=context).view(*batch_shape,
-                                                                           *self.transformer.parameter_shape)
         fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse
-        yb, log_det = fn(xf[..., tgt].contiguous(), h)
-        out = xf.clone()
-        out[..., tgt] = yb
+        if isinstance(self.coupling, HalfSplit):
+            ds = self.n_dim // 2
+            xa, xb = xf[..., :ds], xf[..., ds:]
+            h = self.conditioner_transform(xa, context=context).view(*batch_shape, *self.transformer.parameter_shape)
+            yb, log_det = fn(xb.contiguous(), h)
+            out = torch.cat([xa, yb.reshape(*batch_shape, -1)], dim=-1)
+        else:
+            src = self.coupling.source_mask.view(-1).to(x.device)
+            tgt = self.coupling.target_mask.view(-1).to(x.device)
+            h = self.conditioner_transform(xf[..., src], context=context).view(*batch_shape,
+                                                                               *self.transformer.parameter_shape)
+            yb, log_det = fn(xf[..., tgt].contiguous(), h)
+            out = xf.clone()
+            out[..., tgt] = yb
         return unflatten_event(out, self.event_shape), log_det
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -215,7 +232,7 @@ class ElementwiseBijection(AutoregressiveBijection):
 
     def lower(self, direction: str):
         tk = self._tkind(direction)
-        if tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
+        if tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV) and _fits_fused_kernel(self.n_dim, 1):
             return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
         return None
 
@@ -223,7 +240,7 @@ class ElementwiseBijection(AutoregressiveBijection):
         if self.lower(direction) is not None:
             return self._run_fused(x, direction)
         batch_shape = get_batch_shape(x, self.event_shape)
-        h = self.prepare_h(None, batch_shape).contiguous()
+        h = self.prepare_h(None, batch_shape)          # stride-0 view: the kernel broadcasts it
         fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse
         return fn(x, h)
 

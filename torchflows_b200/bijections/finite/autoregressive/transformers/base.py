@@ -42,18 +42,22 @@ class ElementwiseTransformerFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2, h3, tkind, n_bins, boundary):
-        out, ld, _ = N.transformer_apply(tkind, x2, h3, h3.shape[1] * h3.shape[2], n_bins, boundary)
+        # h3: (n_rows, E, P), or (1, E, P) = one parameter set broadcast over all rows (row stride 0)
+        stride = 0 if h3.shape[0] == 1 and x2.shape[0] != 1 else h3.shape[1] * h3.shape[2]
+        out, ld, _ = N.transformer_apply(tkind, x2, h3, stride, n_bins, boundary)
         ctx.save_for_backward(x2, h3)
-        ctx.meta = (tkind, n_bins, boundary)
+        ctx.meta = (tkind, n_bins, boundary, stride)
         return out, ld
 
     @staticmethod
     def backward(ctx, gout, gld):
         x2, h3 = ctx.saved_tensors
-        tkind, n_bins, boundary = ctx.meta
+        tkind, n_bins, boundary, stride = ctx.meta
         gout = None if gout is None else gout.contiguous()
         gld = None if gld is None else gld.contiguous()
-        gx, gh = N.transformer_backward(tkind, x2, h3, h3.shape[1] * h3.shape[2], gout, gld, n_bins, boundary)
+        gx, gh = N.transformer_backward(tkind, x2, h3, stride, gout, gld, n_bins, boundary)
+        if gh.shape[0] != h3.shape[0]:
+            gh = gh.sum(dim=0, keepdim=True)
         return gx, gh, None, None, None
 
 
@@ -87,14 +91,24 @@ class ScalarTransformer(TensorTransformer):
         batch_shape = get_batch_shape(x, self.event_shape)
         E, P = self.n_dim, self.n_parameters_per_element
         x2 = N.require_cuda_f32(x, 'transformer input').reshape(-1, E)
-        h3 = N.require_cuda_f32(h, 'transformer parameters').reshape(-1, E, P)
-        if h3.shape[0] != x2.shape[0]:
-            raise ValueError(f'parameter batch {tuple(h.shape)} does not match input batch {tuple(x.shape)}')
+        n_batch = len(batch_shape)
+        if n_batch > 0 and h.dim() == n_batch + len(self.parameter_shape) and all(s == 0 for s in h.stride()[:n_batch]) \
+                and x2.shape[0] > 1:
+            # parameters broadcast over the batch (ElementwiseBijection.prepare_h): hand the kernel ONE copy
+            h3 = h[(0,) * n_batch].reshape(1, E, P)
+            if not h3.is_cuda or h3.dtype != torch.float32:
+                raise N.B2FError('transformer parameters must be CUDA float32')
+            h3 = h3.contiguous()
+        else:
+            h3 = N.require_cuda_f32(h, 'transformer parameters').reshape(-1, E, P)
+            if h3.shape[0] != x2.shape[0]:
+                raise ValueError(f'parameter batch {tuple(h.shape)} does not match input batch {tuple(x.shape)}')
         n_bins, boundary = self._kernel_args()
         if torch.is_grad_enabled() and (x2.requires_grad or h3.requires_grad):
             out, ld = ElementwiseTransformerFunction.apply(x2, h3, tkind, n_bins, boundary)
         else:
-            out, ld, _ = N.transformer_apply(tkind, x2, h3, E * P, n_bins, boundary)
+            stride = 0 if h3.shape[0] == 1 and x2.shape[0] != 1 else E * P
+            out, ld, _ = N.transformer_apply(tkind, x2, h3, stride, n_bins, boundary)
         return out.reshape(x.shape), ld.reshape(batch_shape)
 
     def forward(self, x: torch.Tensor, h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -42,10 +42,13 @@ class ReversePermutationMatrix(PermutationMatrix):
         super().__init__(event_shape, forward_permutation=torch.arange(n - 1, -1, -1).view(*event_shape), **kwargs)
 
     def lower(self, direction: str):
+        from torchflows_b200.bijections.finite.autoregressive.layers_base import _fits_fused_kernel
+        if not _fits_fused_kernel(self.n_dim, 1):
+            return None          # very wide events: plain index flip (InvertibleMatrix.forward / inverse)
         return [prog.LoweredOp(kind=N.OP_FLIP, owner=self)]
 
     def forward(self, x, context=None):
-        return self._run_fused(x, 'forward')
+        return self._run_fused(x, 'forward') if self.lower('forward') is not None else super().forward(x, context)
 
     def inverse(self, z, context=None):
-        return self._run_fused(z, 'inverse')
+        return self._run_fused(z, 'inverse') if self.lower('inverse') is not None else super().inverse(z, context)

@@ -173,20 +173,7 @@ class BaseFlow(nn.Module):
                 lo, hi = shard_bounds(stop - start, rank, world)
                 idx = slice(start + lo, start + hi) if order is None else order[start + lo:start + hi]
                 xb, wb = x_dev[idx], w_dev[idx]
-                self._optimizer.zero_grad()
-                if world == 1:
-                    loss = self._base_batch_loss((xb, wb), reduction=torch.mean, use_regularization=True)
-                else:
-                    # local sum / global count, so that the mean over ranks of the gradients is the gradient of the
-                    # global-batch mean; the regularisation term is identical on every rank
-                    lp = self.log_prob(xb)
-                    loss = -(lp * wb).sum() * (world / (stop - start)) / self.event_size + self.regularization()
-                loss_value = loss.detach()
-                if world > 1:
-                    import torch.distributed as dist
-                    loss_value = loss_value.clone()
-                    dist.all_reduce(loss_value, op=dist.ReduceOp.SUM)
-                    loss_value /= world
+                loss, loss_value = self._loss_and_backward_inputs(xb, wb, stop - start, world)
                 if not torch.isfinite(loss_value):
                     self.load_state_dict(best_weights)       # roll back (flows.py:387-393)
                     warnings.warn('Flow training diverged. Reverting to previous weights.')
@@ -231,6 +218,37 @@ class BaseFlow(nn.Module):
         if keep_best_weights:
             self.load_state_dict(best_weights)
         self.eval()
+
+    def _loss_and_backward_inputs(self, xb, wb, n_global: int, world: int):
+        """Loss of this rank's slice of a minibatch, scaled so that the mean over ranks of the gradients is the gradient
+        of the global-batch loss -mean(w*log_prob)/event_size + regularization (flows.py:199-224); returns the local
+        loss tensor (to call backward on) and the global loss value (all-reduced when world > 1)."""
+        self._optimizer.zero_grad()
+        if world == 1:
+            loss = self._base_batch_loss((xb, wb), reduction=torch.mean, use_regularization=True)
+            return loss, loss.detach()
+        import torch.distributed as dist
+        lp = self.log_prob(xb)
+        loss = -(lp * wb).sum() * (world / n_global) / self.event_size + self.regularization()
+        loss_value = loss.detach().clone()
+        dist.all_reduce(loss_value, op=dist.ReduceOp.SUM)
+        loss_value /= world
+        return loss, loss_value
+
+    def train_step(self, xb: torch.Tensor, wb: torch.Tensor = None, n_global: int = None):
+        """One optimisation step exactly as the inner loop of ``fit`` does it (forward, backward, gradient all-reduce
+        when distributed, AdamW).  ``xb`` is this rank's slice; ``n_global`` the size of the global minibatch."""
+        rank, world = _dist_info()
+        if self._optimizer is None:
+            self._optimizer = torch.optim.AdamW(self.parameters(), lr=0.05)
+        if wb is None:
+            wb = torch.ones(len(xb), device=xb.device)
+        loss, loss_value = self._loss_and_backward_inputs(xb, wb, n_global or len(xb) * world, world)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients([p for p in self.parameters() if p.requires_grad], world)
+        self._optimizer.step()
+        return loss_value
 
     def variational_fit(self, *args, **kwargs):
         raise NotImplementedError('variational_fit (gradients through the sampling direction) is listed as the next '
