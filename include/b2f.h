@@ -85,6 +85,10 @@ typedef struct b2f_op {
 #define B2F_FLOW_MODE_PRECISE 2  /* accurate libm-grade exp/log everywhere (default: SFU approximations after
                                     the bin search; knots and bin indices are identical in both modes) */
 
+#define B2F_FLOW_MODE_FAST_KNOTS 4 /* opt-in: spline knots from SFU exponentials (ex2.approx) instead of the
+                                     deterministic polynomial; ~25 %% fewer instructions per element, values within
+                                     the same tolerances, but bin indices are no longer bit-reproducible on a CPU */
+
 /* Runs `n_ops` layers over x:(B,D) in ONE kernel: y:(B,D) (nullable), log_det:(B) (nullable),
  * log_prob:(B) (nullable; adds the DiagonalGaussian log-density with base_loc / base_log_scale:(D),
  * both nullable = standard normal).  Replaces BijectiveComposition.forward / inverse

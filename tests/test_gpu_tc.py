@@ -80,3 +80,29 @@ def test_tensor_core_flow_matches_generic_kernel_and_oracle(D, B):
     xs_ref, lps_ref = oracle.sample_from_noise(z[:nb], return_log_prob=True)
     assert ((tc[4][:nb].double().cpu() - lps_ref.double()).abs() / (1 + lps_ref.double().abs())).max().item() < 2e-4
     assert ((tc[3][:nb].double().cpu() - xs_ref.double()).abs() / (1 + xs_ref.double().abs())).max().item() < 2e-3
+
+
+def test_fast_math_mode_stays_within_tolerance():
+    """set_math_mode('fast') (SFU exponentials for the knots) is opt-in: log_prob within the north-star tolerance of the
+    default mode, outputs within the spline tolerance; bin indices may differ only at ties (counted through z)."""
+    import torchflows_b200
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF, MaskedAutoregressiveRQNSF
+    dev = torch.device('cuda:0')
+    for cls, D in ((CouplingRQNSF, 256), (CouplingRQNSF, 30), (MaskedAutoregressiveRQNSF, 16)):
+        torch.manual_seed(1)
+        flow = Flow(cls(D)).to(dev).eval()
+        x = torch.randn(3000, D, device=dev) * 1.5
+        res = {}
+        for mode in ('default', 'fast', 'precise'):
+            torchflows_b200.set_math_mode(mode)
+            try:
+                with torch.no_grad():
+                    z, ld = flow.bijection.forward(x)
+                    res[mode] = (flow.log_prob(x).double(), z.double())
+            finally:
+                torchflows_b200.set_math_mode('default')
+        for mode in ('fast', 'precise'):
+            lp_err = ((res[mode][0] - res['default'][0]).abs() / (1 + res['default'][0].abs())).max().item()
+            z_err = ((res[mode][1] - res['default'][1]).abs() / (1 + res['default'][1].abs())).max().item()
+            assert lp_err < 1e-4 and z_err < 5e-4, (cls.__name__, D, mode, lp_err, z_err)

@@ -5,5 +5,6 @@ reference's module paths and ``state_dict`` layout.  Compute goes through hand-w
 C ABI (include/b2f.h, torchflows_b200/lib/libb2f.so); there is no CPU fallback."""
 from torchflows_b200._version import __version__
 from torchflows_b200.flows import Flow
+from torchflows_b200._program import set_math_mode
 
-__all__ = ['Flow', '__version__']
+__all__ = ['Flow', 'set_math_mode', '__version__']

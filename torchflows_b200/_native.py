@@ -19,6 +19,7 @@ FLAG_TC_OPERANDS = 2
 FLAG_TC_FLIPPED = 4
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
+FLOW_MODE_FAST_KNOTS = 4
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
                 T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}

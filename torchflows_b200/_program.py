@@ -227,12 +227,31 @@ class FlowFunction(torch.autograd.Function):
         return (gx if need_gx else None, None, *leaf_grads)
 
 
+_MODE_FLAGS = {'default': 0, 'precise': N.FLOW_MODE_PRECISE, 'fast': N.FLOW_MODE_FAST_KNOTS}
+_mode = 'default'
+
+
+def set_math_mode(mode: str) -> str:
+    """Arithmetic mode of the fused flow kernels (process-wide); returns the previous mode.
+    'default': deterministic spline knots (bin indices bit-reproducible against the CPU oracle), SFU approximations
+               only after the bin search.
+    'precise': libm-grade exp / log / division everywhere.
+    'fast'   : additionally takes the softmax exponentials of the knots from the SFU: fewest instructions, same value
+               tolerances, bin indices may differ from the oracle at exact ties."""
+    global _mode
+    if mode not in _MODE_FLAGS:
+        raise ValueError(f'mode must be one of {sorted(_MODE_FLAGS)}')
+    previous, _mode = _mode, mode
+    return previous
+
+
 def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False, base_loc=None, base_log_scale=None,
                 flags=0, want_y=True):
     """x2: (B, D).  Returns y, log_det, log_prob (None unless requested).  Programs longer than B2F_MAX_OPS are
     chained (log-dets add, the base density is evaluated by the last launch)."""
     x2 = N.require_cuda_f32(x2, 'input')
     ops = list(ops)
+    flags |= _MODE_FLAGS[_mode]
     if len(ops) > N.MAX_OPS:
         if flags & N.FLOW_LOGP_OF_INPUT:
             raise N.B2FError('program too long for LOGP_OF_INPUT')

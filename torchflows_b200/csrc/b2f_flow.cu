@@ -313,7 +313,7 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
     A.TM = TM; A.logTM = ilog2(TM); A.G = TM / 32; A.WPG = (NT / 32) / A.G;
     const long long grid = (B + TM - 1) / TM;
     if (grid > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: batch too large for one launch");
-    auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_kernel<0> : flow_kernel<1>;
+    auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_kernel<0> : ((flags & B2F_FLOW_MODE_FAST_KNOTS) ? flow_kernel<2> : flow_kernel<1>);
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);

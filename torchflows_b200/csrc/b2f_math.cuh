@@ -142,7 +142,23 @@ struct RqSel {           // what the evaluation needs from the bin that was foun
 // (i in [0, 3*nb-1): widths logits, heights offsets, interior derivative logits).
 // NB > 0: compile-time bin count (fully unrolled, registers only); NB == 0: run-time nb <= kRqMaxBins.
 // INV selects the search key: knots_x for the forward map, knots_y for the inverse (rational_quadratic.py:82,147).
-template <int NB, bool INV, class H>
+// MODE 2 ("fast knots", opt-in): the softmax exponentials come from the SFU (ex2.approx) and the normalisation from
+// rcp.approx + Newton; knots then agree with the deterministic ones to ~2 ulp of the boundary and the bin index can
+// differ at exact ties -- tolerance-checked, not bit-checked.
+template <int MODE> B2F_HD float knot_exp(float t) {
+#if defined(__CUDA_ARCH__)
+    if (MODE >= 2) return __expf(t);
+#endif
+    return exp_det(t);
+}
+template <int MODE> B2F_HD float knot_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    if (MODE >= 2) return m_rcp<1>(x);
+#endif
+    return r_rcp(x);
+}
+
+template <int NB, bool INV, int MODE, class H>
 B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel& s) {
     const int nb = NB > 0 ? NB : nb_rt;
     float ex[NB > 0 ? NB : kRqMaxBins], ey[NB > 0 ? NB : kRqMaxBins];
@@ -158,13 +174,13 @@ B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel&
     float sx = 0.0f, sy = 0.0f;
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
-        ex[j] = exp_det(r_add(ex[j], -mx));
-        ey[j] = exp_det(r_add(ey[j], -my));
+        ex[j] = knot_exp<MODE>(r_add(ex[j], -mx));
+        ey[j] = knot_exp<MODE>(r_add(ey[j], -my));
         sx = r_add(sx, ex[j]); sy = r_add(sy, ey[j]);
     }
     // sizes_j = 1e-3 + (1 - 1e-3*nb) * softmax_j   (rational_quadratic.py:46-47)
     const float c1 = (float)(1.0 - 1e-3 * (double)nb);   // Python double, cast once (rational_quadratic.py:47)
-    const float gx = r_mul(c1, r_rcp(sx)), gy = r_mul(c1, r_rcp(sy));
+    const float gx = r_mul(c1, knot_rcp<MODE>(sx)), gy = r_mul(c1, knot_rcp<MODE>(sy));
     const float span = r_add(hi, -lo);
     float cx = 0.0f, cy = 0.0f;
     bool prev_below = true;                         // knot_0 = lo < v always (strict in-bounds test)
@@ -208,19 +224,33 @@ template <int MODE> B2F_HD void rq_eval_fwd(float v, const RqSel& s, float& out,
     // true (IEEE) divisions as in the reference: out = y_k + num/den cancels against y_k ~ -b, so an
     // ulp of num/den is worth ulp(b) in the output
     e.w = s.xk1 - s.xk; e.hgt = s.yk1 - s.yk;
-    e.s = e.hgt / e.w;
+    float xr;
+    if (MODE >= 1) {                 // one reciprocal (rcp.approx + Newton, ~1 ulp) shared by both quotients
+        const float iw = m_rcp<MODE>(e.w);
+        e.s = e.hgt * iw;
+        xr = (v - s.xk) * iw;
+    } else {
+        e.s = e.hgt / e.w;
+        xr = (v - s.xk) / e.w;
+    }
     e.d0 = rq_delta<MODE>(s.ud0); e.d1 = rq_delta<MODE>(s.ud1);
     e.t1 = e.d1 + e.d0 - 2.0f * e.s;
-    const float xr = (v - s.xk) / e.w;
     e.xi = fminf(fmaxf(xr, 0.0f), 1.0f);
     e.clipped = (xr < 0.0f) || (xr > 1.0f);
     e.q = e.xi * (1.0f - e.xi);
     const float num = e.hgt * (e.s * e.xi * e.xi + e.d0 * e.q);
     e.den = e.s + e.t1 * e.q;
-    out = s.yk + num / e.den;
     const float om = 1.0f - e.xi;
     e.M = e.d1 * e.xi * e.xi + 2.0f * e.s * e.q + e.d0 * om * om;
-    ld = rq_logdet<MODE>(e);
+    if (MODE >= 1) {                 // one reciprocal of the denominator for the value and the log-det
+        const float iden = m_rcp<MODE>(e.den);
+        out = fmaf(num, iden, s.yk);
+        const float r = e.s * iden;
+        ld = m_log<MODE>(r * r * e.M);
+    } else {
+        out = s.yk + num / e.den;
+        ld = rq_logdet<MODE>(e);
+    }
 }
 
 // inverse evaluation inside bin k (rational_quadratic.py:153-181)
@@ -251,7 +281,7 @@ template <int NB, bool INV, int MODE, class H>
 B2F_HD void rq_apply(float v, const H& h, int nb_rt, float boundary, float& out, float& ld, int& k) {
     if (!(v > -boundary && v < boundary)) { out = v; ld = 0.0f; k = -1; return; }
     RqSel s; RqEval e;
-    rq_select<NB, INV>(v, h, nb_rt, -boundary, boundary, s);
+    rq_select<NB, INV, MODE>(v, h, nb_rt, -boundary, boundary, s);
     if (INV) rq_eval_inv<MODE>(v, s, out, ld, e); else rq_eval_fwd<MODE>(v, s, out, ld, e);
     k = s.k;
 }
@@ -272,7 +302,7 @@ B2F_HD void rq_backward_fwd(float v, const H& h, int nb_rt, float boundary, floa
     }
     const float lo = -boundary, hi = boundary;
     RqSel s; RqEval e; float out, ld;
-    rq_select<NB, false>(v, h, nb, lo, hi, s);
+    rq_select<NB, false, 0>(v, h, nb, lo, hi, s);
     rq_eval_fwd<MODE>(v, s, out, ld, e);
     const int k = s.k;
     const float xi = e.xi, q = e.q, sk = e.s, d0 = e.d0, d1 = e.d1, t1 = e.t1, Dn = e.den, M = e.M;
