@@ -98,14 +98,27 @@ def umma_canonical(mat: torch.Tensor) -> torch.Tensor:
     return mat.reshape(rows // 8, 8, K // 4, 4).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
 
+_TC_GEOM = {  # transformer kind -> (parameter columns per element CPE, elements per GEMM2 chunk EPC, 3xTF32 split)
+    N.T_RQ_FWD: (24, 8, False), N.T_RQ_INV: (24, 8, False),
+    N.T_AFFINE_FWD: (2, 64, True), N.T_AFFINE_INV: (2, 64, True),
+    N.T_SHIFT_ADD: (1, 128, True), N.T_SHIFT_SUB: (1, 128, True),
+}
+
+
 def tc_eligible(op: LoweredOp, D: int) -> bool:
-    return (op.kind == N.OP_COUPLING and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV) and op.n_bins == 8
-            and D % 16 == 0 and 32 <= D <= 256 and 1 <= op.n_hidden <= 30)
+    """Mirror of try_launch_flow_tc's per-op conditions (csrc/b2f_flow_tc.cu)."""
+    if op.kind != N.OP_COUPLING or op.tkind not in _TC_GEOM or D % 16 != 0 or D < 32:
+        return False
+    x3 = _TC_GEOM[op.tkind][2]
+    if x3:
+        return D <= 128 and 1 <= op.n_hidden <= 20
+    return op.n_bins == 8 and D <= 256 and 1 <= op.n_hidden <= 30
 
 
 def tc_operands(op: LoweredOp, flipped: bool, D: int):
-    """Tensor-core operand layouts of a spline coupling layer (include/b2f.h, B2F_FLAG_TC_OPERANDS), cached per
-    parameter version: W1c [32 x D/2] and W2c [D/2/8 chunks][192 x K2] with the bias folded in as two K columns."""
+    """Tensor-core operand layouts of a coupling layer (include/b2f.h, B2F_FLAG_TC_OPERANDS), cached per parameter
+    version: W1c [32 x K1] and W2c [chunks][N2 x K2] with the bias folded in as two K columns.  Affine / shift layers
+    use the 3xTF32 split along K: [w_hi | w_lo | w_hi]."""
     W1, b1, W2, b2 = op.leafs
     key = ('tc', bool(flipped))
     ver = tuple((t.data_ptr(), t._version) for t in op.leafs)
@@ -116,19 +129,34 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
+    cpe, epc, x3 = _TC_GEOM[op.tkind]
     with torch.no_grad():
-        H, Dh, P = W1.shape[0], D // 2, 23
-        W1p = W1.new_zeros(32, Dh)
-        W1p[:H] = W1.detach().flip(1) if flipped else W1.detach()
-        w1c = umma_canonical(round_tf32(W1p))
-        K2 = (H + 2 + 7) // 8 * 8
-        M = W2.new_zeros(Dh, 24, K2)
-        M[:, :P, :H] = round_tf32(W2.detach().reshape(Dh, P, H))
+        H, Dh = W1.shape[0], D // 2
+        P = params_per_element(op.tkind, op.n_bins)
+        w1 = W1.detach().flip(1) if flipped else W1.detach()
+        w1_hi = round_tf32(w1)
+        W1p = W1.new_zeros(32, (3 if x3 else 1) * Dh)
+        W1p[:H, :Dh] = w1_hi
+        if x3:
+            W1p[:H, Dh:2 * Dh] = round_tf32(w1 - w1_hi)
+            W1p[:H, 2 * Dh:] = w1_hi
+        w1c = umma_canonical(W1p)
+        K2 = ((3 if x3 else 1) * H + 2 + 7) // 8 * 8
+        n_chunks = (Dh + epc - 1) // epc
+        M = W2.new_zeros(n_chunks * epc, cpe, K2)
+        w2 = W2.detach().reshape(Dh, P, H)
+        w2_hi = round_tf32(w2)
+        M[:Dh, :P, :H] = w2_hi
+        kb = H
+        if x3:
+            M[:Dh, :P, H:2 * H] = round_tf32(w2 - w2_hi)
+            M[:Dh, :P, 2 * H:3 * H] = w2_hi
+            kb = 3 * H
         bias = b2.detach().reshape(Dh, P)
-        hi = round_tf32(bias)
-        M[:, :P, H] = hi
-        M[:, :P, H + 1] = round_tf32(bias - hi)
-        chunks = M.reshape(Dh // 8, 192, K2)
+        b_hi = round_tf32(bias)
+        M[:Dh, :P, kb] = b_hi
+        M[:Dh, :P, kb + 1] = round_tf32(bias - b_hi)
+        chunks = M.reshape(n_chunks, epc * cpe, K2)
         w2c = torch.cat([umma_canonical(c) for c in chunks])
     out = (w1c, w2c)
     cache[key] = (ver, out)

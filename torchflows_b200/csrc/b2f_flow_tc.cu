@@ -1,26 +1,33 @@
-// Tensor-core whole-flow kernel for rational-quadratic coupling flows (CouplingRQNSF): the conditioner GEMMs
-// run on tcgen05 (kind::tf32, accumulators in TMEM), the weight tiles are streamed by the TMA engine
-// (cp.async.bulk + mbarrier), and the spline transformer is the epilogue that reads its 23 parameters per
-// element straight out of TMEM.  One persistent CTA per SM; a tile = 128 samples (UMMA M = 128).
+// Tensor-core whole-flow kernel for coupling flows: the conditioner GEMMs run on tcgen05 (kind::tf32,
+// accumulators in TMEM), the weight tiles are streamed by the TMA engine (cp.async.bulk + mbarrier), and the
+// transformer (rational-quadratic spline, affine or shift) is the epilogue that reads its parameters straight out of
+// TMEM.  One persistent CTA per SM; a tile = 128 samples (UMMA M = 128).
 //
 // Replaces the same reference code as b2f_flow.cu (bijections/base.py:203-232, layers_base.py:119-163,
-// transforms.py:293-307, spline/rational_quadratic.py:45-200, flows.py:628-648); the difference to the generic
-// kernel is only where the two Linear layers are evaluated.
+// transforms.py:293-307, transformers/linear/affine.py:39-59,149-159, spline/rational_quadratic.py:45-200,
+// flows.py:628-648); the difference to the generic kernel is only where the two Linear layers are evaluated.
 //
-// Shared memory (D = 256, H = 17: 213 KB):
+// Precision.  Spline layers: single-pass TF32 (log_prob stays within 1e-4 abs/rel).  Affine and
+// shift layers need an fp32-faithful conditioner (their log-det is a plain sum of conditioner outputs), so they use
+// the 3xTF32 split  a*w ~= a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  laid out along K: A = [a | a | a_lo], B = [w_hi | w_lo |
+// w_hi] (the tensor core truncates the fp32 `a` to a_hi by itself; a_lo = a - trunc(a) is exact in fp32).
+//
+// Shared memory (CouplingRQNSF D = 256, H = 17: 199 KB; RealNVP D = 64, H = 9: 112 KB):
 //   xlo, xhi   the two halves of the sample tile, each [128 x D/2] fp32 in the canonical K-major UMMA operand
 //              layout (b2f_umma.cuh).  They are BOTH the resident activations of the flow and the A operand of
 //              the first GEMM (the tensor core reads fp32 bit patterns as tf32), so x is never staged twice.
-//   w1         first Linear as B operand [32 x D/2] (hidden units padded to 32), bulk-copied per layer
-//   a2         tanh(hidden) as A operand of the second GEMM [128 x K2], K2 = roundup(H + 2, 8): columns H and
-//              H+1 are 1.0 and multiply the (hi, lo) split of the bias b2, so the bias is added by the MMA
-//   w2buf[2]   second Linear, one chunk = 8 target elements x 24 parameter rows = [192 x K2], double buffered
-// Tensor memory (512 columns): D2[0] cols 0..191, D2[1] cols 192..383 (chunk accumulators, ping-pong against the
+//   xl3        3xTF32 only: low parts of the source half [128 x D/2]
+//   w1         first Linear as B operand [32 x K1], K1 = D/2 or 3*D/2, bulk-copied per layer
+//   a2         tanh(hidden) as A operand of the second GEMM [128 x K2]; two extra columns are 1.0 and multiply the
+//              (hi, lo) split of the bias b2, so the bias is added by the MMA
+//   w2buf[2]   second Linear, one chunk = EPC target elements x CPE parameter columns = [N2 x K2], double buffered
+//              (spline: 8 x 24 = 192, affine: 64 x 2 = 128, shift: 128 x 1 = 128)
+// Tensor memory (512 columns): D2[0] cols 0.., D2[1] cols 192.. (chunk accumulators, ping-pong against the
 // epilogue), D1 cols 384..415 (hidden pre-activations).
 //
-// Warp roles: warps 0..15 epilogue (warp w owns TMEM lanes 32*(w%4).., and elements 2*(w/4), 2*(w/4)+1 of each
-// chunk; a thread owns one sample, so log-det accumulates in a register), warp 16 issues every tcgen05.mma,
-// warp 17 drives the TMA loads.  All hand-offs are mbarriers; waits are bounded (trap instead of hang).
+// Warp roles: warps 0..15 epilogue (warp w owns TMEM lanes 32*(w%4).. and a quarter of each chunk's elements; a
+// thread owns one sample, so log-det accumulates in a register), warp 16 issues every tcgen05.mma, warp 17 drives
+// the TMA loads.  All hand-offs are mbarriers; waits are bounded (trap instead of hang).
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,14 +40,22 @@ namespace b2f {
 
 constexpr int kTcEpiWarps = 16;
 constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
-constexpr int kTcChunkElems = 8;                     // target elements per GEMM2 chunk
-constexpr int kTcChunkRows = kTcChunkElems * 24;     // 192 = UMMA N of GEMM2
+constexpr int kTcBufCols = 192;                      // TMEM columns reserved per GEMM2 accumulator buffer
 constexpr int kTcN1 = 32;                            // UMMA N of GEMM1 (hidden units, padded)
 constexpr int kTcTmemCols = 512;
 constexpr int kTcColD1 = 384;
 
+// chunk geometry of GEMM2 per transformer family: CPE parameter columns per element, EPC elements per chunk
+template <int TK> struct TcGeom { static constexpr int CPE = 24, EPC = 8; };                    // RQ spline
+template <> struct TcGeom<B2F_T_AFFINE_FWD> { static constexpr int CPE = 2, EPC = 64; };
+template <> struct TcGeom<B2F_T_AFFINE_INV> { static constexpr int CPE = 2, EPC = 64; };
+template <> struct TcGeom<B2F_T_SHIFT_ADD> { static constexpr int CPE = 1, EPC = 128; };
+template <> struct TcGeom<B2F_T_SHIFT_SUB> { static constexpr int CPE = 1, EPC = 128; };
+
 struct TcOp {
     int kind, tkind, H, K2;
+    int x3;                     // 3xTF32 operand split (affine / shift layers)
+    int n_chunks, N2;           // GEMM2: chunks per layer, UMMA N of a chunk
     float boundary;
     int flip_before;            // flip state when this op runs (host-computed)
     const float* value;         // ELEMENTWISE: (D,2)
@@ -64,6 +79,7 @@ struct TcArgs {
 struct TcSmem {
     float* xlo;
     float* xhi;
+    float* xl3;
     float* w1;
     float* a2;
     float* w2buf;      // two chunk buffers, w2stride floats apart
@@ -95,34 +111,58 @@ __device__ __forceinline__ float* xaddr(const TcSmem& s, int Dh, int m, int c) {
     return reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(base) + umma::canon_off(m, k, Dh));
 }
 
-// chunk loop of one coupling layer for one epilogue thread: wait for the chunk's accumulator, pull the 24
-// parameter columns of each of its two elements out of TMEM, apply the spline, hand the buffer back.
+// chunk loop of one coupling layer for one epilogue thread: wait for the chunk's accumulator, pull this warp's
+// parameter columns out of TMEM, apply the transformer to its elements, hand the buffer back.
 template <int TK, int MODE>
 __device__ __forceinline__ float tc_chunk_loop(const TcSmem& s, const TcOp& op, uint32_t tbase, uint32_t lane_addr,
                                                int Dh, int m_t, int sub, int lane, uint32_t& cc) {
-    const int n_chunks = Dh / kTcChunkElems;
+    constexpr int CPE = TcGeom<TK>::CPE, EPC = TcGeom<TK>::EPC, EPS = EPC / 4;   // elements per epilogue sub-warp
     uint8_t* tgt = reinterpret_cast<uint8_t*>(op.flip_before ? s.xlo : s.xhi);   // logical target half
     float ldpart = 0.0f;
-    for (int c = 0; c < n_chunks; ++c, ++cc) {
+    for (int c = 0; c < op.n_chunks; ++c, ++cc) {
         const int b = cc & 1;
         umma::mbar_wait(&s.bars[BAR_D2_FULL0 + b], (cc >> 1) & 1);
         umma::tc_fence_after_sync();
+        const uint32_t tcol = tbase + lane_addr + b * kTcBufCols + sub * (EPS * CPE);
+        if constexpr (CPE == 24) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int el = sub * 2 + i;
-            const int e = c * kTcChunkElems + el;                  // logical target element
-            float acc[24];
-            const uint32_t ta = tbase + lane_addr + b * kTcChunkRows + el * 24;
-            umma::tmem_ld8_nowait<0>(ta, acc);
-            umma::tmem_ld8_nowait<8>(ta + 8, acc);
-            umma::tmem_ld8_nowait<16>(ta + 16, acc);
+            for (int i = 0; i < EPS; ++i) {
+                const int e = c * EPC + sub * EPS + i;                 // logical target element
+                float acc[24];
+                umma::tmem_ld8_nowait<0>(tcol + i * 24, acc);
+                umma::tmem_ld8_nowait<8>(tcol + i * 24 + 8, acc);
+                umma::tmem_ld8_nowait<16>(tcol + i * 24 + 16, acc);
+                umma::tmem_ld_wait();
+                const int k_loc = op.flip_before ? Dh - 1 - e : e;
+                float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
+                float out, ld;
+                transform_element<TK, MODE, 24>(*px, acc, op.boundary, out, ld);
+                *px = out;
+                ldpart += ld;
+            }
+        } else {
+            static_assert(EPS * CPE == 32, "affine / shift chunks hand 32 TMEM columns to every epilogue warp");
+            float u[32];
+            umma::tmem_ld8_nowait<0>(tcol, u);
+            umma::tmem_ld8_nowait<8>(tcol + 8, u);
+            umma::tmem_ld8_nowait<16>(tcol + 16, u);
+            umma::tmem_ld8_nowait<24>(tcol + 24, u);
             umma::tmem_ld_wait();
-            const int k_loc = op.flip_before ? Dh - 1 - e : e;
-            float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
-            float out, ld;
-            transform_element<TK, MODE, 24>(*px, acc, op.boundary, out, ld);
-            *px = out;
-            ldpart += ld;
+#pragma unroll
+            for (int i = 0; i < EPS; ++i) {
+                const int e = c * EPC + sub * EPS + i;
+                if (e < Dh) {
+                    float acc[CPE];
+#pragma unroll
+                    for (int p = 0; p < CPE; ++p) acc[p] = u[i * CPE + p];
+                    const int k_loc = op.flip_before ? Dh - 1 - e : e;
+                    float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
+                    float out, ld;
+                    transform_element<TK, MODE, CPE>(*px, acc, op.boundary, out, ld);
+                    *px = out;
+                    ldpart += ld;
+                }
+            }
         }
         umma::tc_fence_before_sync();
         __syncwarp();
@@ -137,17 +177,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
     const int D = A.D, Dh = D >> 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- carve shared memory -----------------------------------------------------------------------------
-    int K2max = 8;
+    int K2max = 8, K1max = Dh, W2max = 0, any_x3 = 0;
     for (int i = 0; i < A.n_ops; ++i)
-        if (A.ops[i].kind == B2F_OP_COUPLING) K2max = max(K2max, A.ops[i].K2);
+        if (A.ops[i].kind == B2F_OP_COUPLING) {
+            K2max = max(K2max, A.ops[i].K2);
+            K1max = max(K1max, (A.ops[i].x3 ? 3 : 1) * Dh);
+            W2max = max(W2max, A.ops[i].N2 * A.ops[i].K2);
+            any_x3 |= A.ops[i].x3;
+        }
     TcSmem s;
     uint8_t* p = smem_raw;
     s.xlo = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
     s.xhi = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
-    s.w1 = reinterpret_cast<float*>(p); p += kTcN1 * Dh * 4;
+    s.xl3 = reinterpret_cast<float*>(p); p += any_x3 ? 128 * Dh * 4 : 0;
+    s.w1 = reinterpret_cast<float*>(p); p += kTcN1 * K1max * 4;
     s.a2 = reinterpret_cast<float*>(p); p += 128 * K2max * 4;
-    s.w2buf = reinterpret_cast<float*>(p); p += 2 * kTcChunkRows * K2max * 4;
-    s.w2stride = kTcChunkRows * K2max;
+    s.w2buf = reinterpret_cast<float*>(p); p += 2 * W2max * 4;
+    s.w2stride = W2max;
     s.ldp = reinterpret_cast<float*>(p); p += 4 * 128 * 4;
     s.ldacc = reinterpret_cast<float*>(p); p += 128 * 4;
     s.lpin = reinterpret_cast<float*>(p); p += 128 * 4;
@@ -187,12 +233,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     const TcOp& op = A.ops[oi];
                     if (op.kind != B2F_OP_COUPLING) continue;
                     umma::mbar_wait_backoff(&s.bars[BAR_W1_EMPTY], (lc & 1) ^ 1);
-                    const uint32_t w1_bytes = kTcN1 * Dh * 4;
+                    const uint32_t w1_bytes = kTcN1 * (op.x3 ? 3 : 1) * Dh * 4;
                     umma::mbar_arrive_expect_tx(&s.bars[BAR_W1_FULL], w1_bytes);
                     umma::bulk_g2s(s.w1, op.w1c, w1_bytes, &s.bars[BAR_W1_FULL]);
-                    const int n_chunks = Dh / kTcChunkElems;
-                    const uint32_t ch_bytes = kTcChunkRows * op.K2 * 4;
-                    for (int c = 0; c < n_chunks; ++c, ++cc) {
+                    const uint32_t ch_bytes = op.N2 * op.K2 * 4;
+                    for (int c = 0; c < op.n_chunks; ++c, ++cc) {
                         const int b = cc & 1;
                         umma::mbar_wait_backoff(&s.bars[BAR_W2_EMPTY0 + b], ((cc >> 1) & 1) ^ 1);
                         umma::mbar_arrive_expect_tx(&s.bars[BAR_W2_FULL0 + b], ch_bytes);
@@ -215,21 +260,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     umma::mbar_wait_backoff(&s.bars[BAR_W1_FULL], ph);
                     umma::mbar_wait_backoff(&s.bars[BAR_A1_READY], ph);
                     umma::tc_fence_after_sync();
-                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T
-                    const uint32_t a1 = umma::smem_u32(op.flip_before ? s.xhi : s.xlo);
+                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T   (3xTF32: K blocks [x | x | x_lo] . [w_hi | w_lo | w_hi])
+                    const uint32_t a_src = umma::smem_u32(op.flip_before ? s.xhi : s.xlo);
+                    const uint32_t a_lo3 = umma::smem_u32(s.xl3);
                     const uint32_t b1a = umma::smem_u32(s.w1);
                     const uint32_t idesc1 = umma::make_idesc_tf32(128, kTcN1);
-                    for (int ks = 0; ks < Dh / 8; ++ks)
-                        umma::mma_tf32_ss(tbase + kTcColD1, umma::make_smem_desc(a1 + ks * 256, 128, Dh * 32),
-                                          umma::make_smem_desc(b1a + ks * 256, 128, Dh * 32), idesc1, ks > 0);
+                    const int nblk = op.x3 ? 3 : 1, kpb = Dh / 8;
+                    for (int blk = 0; blk < nblk; ++blk)
+                        for (int ks = 0; ks < kpb; ++ks)
+                            umma::mma_tf32_ss(tbase + kTcColD1,
+                                              umma::make_smem_desc((blk < 2 ? a_src : a_lo3) + ks * 256, 128, Dh * 32),
+                                              umma::make_smem_desc(b1a + (blk * kpb + ks) * 256, 128, nblk * Dh * 32), idesc1,
+                                              (blk | ks) > 0);
                     umma::mma_commit(&s.bars[BAR_D1_FULL]);
                     umma::mma_commit(&s.bars[BAR_W1_EMPTY]);
                     umma::mbar_wait(&s.bars[BAR_A2_FULL], ph);
                     umma::tc_fence_after_sync();
                     const uint32_t a2a = umma::smem_u32(s.a2);
-                    const uint32_t idesc2 = umma::make_idesc_tf32(128, kTcChunkRows);
-                    const int n_chunks = Dh / kTcChunkElems;
-                    for (int c = 0; c < n_chunks; ++c, ++cc) {
+                    const uint32_t idesc2 = umma::make_idesc_tf32(128, op.N2);
+                    for (int c = 0; c < op.n_chunks; ++c, ++cc) {
                         const int b = cc & 1;
                         const uint32_t ph2 = (cc >> 1) & 1;
                         umma::mbar_wait_backoff(&s.bars[BAR_W2_FULL0 + b], ph2);
@@ -237,7 +286,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                         umma::tc_fence_after_sync();
                         const uint32_t wb = umma::smem_u32(s.w2buf + b * s.w2stride);
                         for (int ks = 0; ks < op.K2 / 8; ++ks)
-                            umma::mma_tf32_ss(tbase + b * kTcChunkRows, umma::make_smem_desc(a2a + ks * 256, 128, op.K2 * 32),
+                            umma::mma_tf32_ss(tbase + b * kTcBufCols, umma::make_smem_desc(a2a + ks * 256, 128, op.K2 * 32),
                                               umma::make_smem_desc(wb + ks * 256, 128, op.K2 * 32), idesc2, ks > 0);
                         umma::mma_commit(&s.bars[BAR_D2_FULL0 + b]);
                         umma::mma_commit(&s.bars[BAR_W2_EMPTY0 + b]);
@@ -324,39 +373,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                 }
                 // ---------------- coupling layer ----------------
                 const uint32_t ph = lc & 1;
-                umma::fence_proxy_async_smem();            // our generic-proxy writes to xlo/xhi -> tensor core
+                if (op.x3) {
+                    // low parts of the source half for the 3xTF32 split: x_lo = x - trunc_tf32(x), exact in fp32
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(op.flip_before ? s.xhi : s.xlo);
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(s.xl3);
+                    const int m = rg * 8 + r8;
+                    for (int kc = kq; kc < Dh / 4; kc += 4) {
+                        const uint32_t off = umma::canon_off(m, 4 * kc, Dh);
+                        const float4 v = *reinterpret_cast<const float4*>(src + off);
+                        float4 lo;
+                        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4*>(dst + off) = lo;
+                    }
+                }
+                umma::fence_proxy_async_smem();            // our generic-proxy writes to xlo/xhi/xl3 -> tensor core
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&s.bars[BAR_A1_READY]);
                 if (warp < 4) {
-                    // hidden epilogue: D1 -> +b1 -> tanh -> tf32 -> a2 (A operand of GEMM2), bias columns = 1
+                    // hidden epilogue: D1 -> +b1 -> tanh -> tf32 (hi, and lo for 3xTF32) -> a2 (A operand of GEMM2);
+                    // the two bias columns are 1.0
                     umma::mbar_wait(&s.bars[BAR_D1_FULL], ph);
                     umma::tc_fence_after_sync();
                     const int K2 = op.K2, H = op.H;
-                    uint8_t* a2row = reinterpret_cast<uint8_t*>(s.a2);
+                    uint8_t* a2b = reinterpret_cast<uint8_t*>(s.a2);
+                    for (int k4 = 0; k4 < K2; k4 += 4)
+                        *reinterpret_cast<float4*>(a2b + umma::canon_off(m_t, k4, K2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    auto put = [&](int k, float val) { *reinterpret_cast<float*>(a2b + umma::canon_off(m_t, k, K2)) = val; };
 #pragma unroll
                     for (int c0 = 0; c0 < kTcN1; c0 += 8) {
                         float v[8];
                         umma::tmem_ld8(tbase + lane_addr + kTcColD1 + c0, v);
                         umma::tmem_ld_wait();
-                        if (c0 < K2) {
-                            float o[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int j = c0 + i;
-                                o[i] = j < H ? to_tf32_rn(tanhf(v[i] + __ldg(op.b1 + j))) : ((j == H || j == H + 1) ? 1.0f : 0.0f);
+                        for (int i = 0; i < 8; ++i) {
+                            const int j = c0 + i;
+                            if (j < H) {
+                                const float t = tanhf(v[i] + __ldg(op.b1 + j));
+                                const float hi = to_tf32_rn(t);
+                                put(j, hi);
+                                if (op.x3) { put(H + j, hi); put(2 * H + j, to_tf32_rn(t - hi)); }
                             }
-                            *reinterpret_cast<float4*>(a2row + umma::canon_off(m_t, c0, K2)) = make_float4(o[0], o[1], o[2], o[3]);
-                            *reinterpret_cast<float4*>(a2row + umma::canon_off(m_t, c0 + 4, K2)) = make_float4(o[4], o[5], o[6], o[7]);
                         }
                     }
+                    const int kb = (op.x3 ? 3 : 1) * H;
+                    put(kb, 1.0f); put(kb + 1, 1.0f);
                     umma::tc_fence_before_sync();
                     umma::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&s.bars[BAR_A2_FULL]);
                 }
-                float ldpart;
-                if (op.tkind == B2F_T_RQ_FWD) ldpart = tc_chunk_loop<B2F_T_RQ_FWD, MODE>(s, op, tbase, lane_addr, Dh, m_t, sub, lane, cc);
-                else ldpart = tc_chunk_loop<B2F_T_RQ_INV, MODE>(s, op, tbase, lane_addr, Dh, m_t, sub, lane, cc);
+                float ldpart = 0.0f;
+#define B2F_TC_CASE(TKV) case TKV: ldpart = tc_chunk_loop<TKV, MODE>(s, op, tbase, lane_addr, Dh, m_t, sub, lane, cc); break;
+                switch (op.tkind) {
+                    B2F_TC_CASE(B2F_T_RQ_FWD)
+                    B2F_TC_CASE(B2F_T_RQ_INV)
+                    B2F_TC_CASE(B2F_T_AFFINE_FWD)
+                    B2F_TC_CASE(B2F_T_AFFINE_INV)
+                    B2F_TC_CASE(B2F_T_SHIFT_ADD)
+                    B2F_TC_CASE(B2F_T_SHIFT_SUB)
+                }
+#undef B2F_TC_CASE
                 s.ldp[sub * 128 + m_t] = ldpart;
                 epi_sync();
                 if (tid < 128) s.ldacc[tid] += (s.ldp[tid] + s.ldp[128 + tid]) + (s.ldp[256 + tid] + s.ldp[384 + tid]);
@@ -399,7 +478,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
     if (getenv("B2F_DISABLE_TC")) return 0;
     if (D % 16 != 0 || D < 32 || D > 256) return 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (y && (reinterpret_cast<uintptr_t>(y) & 15))) return 0;
-    int flip = 0, n_coupling = 0, K2max = 8;
+    int flip = 0, n_coupling = 0, K2max = 8, K1max = D / 2, W2max = 0, any_x3 = 0;
     TcArgs A;
     memset(&A, 0, sizeof(A));
     for (int i = 0; i < n_ops; ++i) {
@@ -409,22 +488,34 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
         if (o.kind != B2F_OP_COUPLING) return 0;
-        if (o.tkind != B2F_T_RQ_FWD && o.tkind != B2F_T_RQ_INV) return 0;
         if (!(o.flags & B2F_FLAG_TC_OPERANDS) || !o.p[4] || !o.p[5] || !o.p[1]) return 0;
-        if (o.n_bins != 8 || o.n_hidden < 1 || o.n_hidden > 30) return 0;
+        const bool rq = o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV;
+        const int Dh_ = D / 2;
+        int cpe, epc;
+        if (rq) { cpe = 24; epc = 8; if (o.n_bins != 8) return 0; }
+        else if (o.tkind == B2F_T_AFFINE_FWD || o.tkind == B2F_T_AFFINE_INV) { cpe = 2; epc = 64; }
+        else if (o.tkind == B2F_T_SHIFT_ADD || o.tkind == B2F_T_SHIFT_SUB) { cpe = 1; epc = 128; }
+        else return 0;
+        t.x3 = rq ? 0 : 1;
+        const int kin = (t.x3 ? 3 : 1) * o.n_hidden + 2;
+        t.K2 = (kin + 7) / 8 * 8;
+        if (o.n_hidden < 1 || o.n_hidden > 32 || t.K2 > 64) return 0;
         if (((o.flags & B2F_FLAG_TC_FLIPPED) != 0) != (flip != 0))
             return fail(B2F_ERR_INVALID, "op %d: tensor-core operands were laid out for the wrong flip state", i);
-        t.K2 = (o.n_hidden + 2 + 7) / 8 * 8;
+        t.N2 = epc * cpe;
+        t.n_chunks = (Dh_ + epc - 1) / epc;
         K2max = std::max(K2max, t.K2);
+        K1max = std::max(K1max, (t.x3 ? 3 : 1) * Dh_);
+        W2max = std::max(W2max, t.N2 * t.K2);
+        any_x3 |= t.x3;
         t.b1 = (const float*)o.p[1]; t.w1c = (const float*)o.p[4]; t.w2c = (const float*)o.p[5];
         if ((reinterpret_cast<uintptr_t>(t.w1c) & 15) || (reinterpret_cast<uintptr_t>(t.w2c) & 15)) return 0;
         ++n_coupling;
     }
     if (flip != 0 || n_coupling == 0) return 0;
     const int Dh = D / 2;
-    const size_t smem = (size_t)2 * 128 * Dh * 4 + (size_t)kTcN1 * Dh * 4 + (size_t)128 * K2max * 4 +
-                        (size_t)2 * kTcChunkRows * K2max * 4 + (size_t)(4 * 128 + 128 + 128 + 3 * D) * 4 + 16 +
-                        BAR_COUNT * 8 + 16;
+    const size_t smem = (size_t)(2 + any_x3) * 128 * Dh * 4 + (size_t)kTcN1 * K1max * 4 + (size_t)128 * K2max * 4 +
+                        (size_t)2 * W2max * 4 + (size_t)(4 * 128 + 128 + 128 + 3 * D) * 4 + 16 + BAR_COUNT * 8 + 16;
     if (smem > 227 * 1024) return 0;
     A.n_ops = n_ops; A.D = D; A.flags = flags; A.B = B;
     A.n_tiles = (int)((B + 127) / 128);
