@@ -316,9 +316,14 @@ def run_fit(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
-    D, H, per_gpu = 1024, 1024, args.rows or 16384
+    if args.workload == 'w1024fit':
+        D, H, per_gpu = 1024, 1024, args.rows or 16384
+        kwargs = {'conditioner_kwargs': {'n_hidden': H}}
+    else:      # q256fit: default CouplingRQNSF(256) through the fused backward kernel
+        D, H, per_gpu = 256, 17, args.rows or 131072
+        kwargs = {}
     torch.manual_seed(0)
-    flow = Flow(CouplingRQNSF(D, conditioner_kwargs={'n_hidden': H})).to(dev)
+    flow = Flow(CouplingRQNSF(D, **kwargs)).to(dev)
     n_params = sum(p.numel() for p in flow.parameters() if p.requires_grad)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x = torch.randn(per_gpu, D, device=dev, generator=g)
@@ -348,7 +353,8 @@ def run_fit(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'CouplingRQNSF n_dim={D} n_hidden={H}: Flow.fit step (fwd + bwd + all-reduce + AdamW), '
                                    f'{per_gpu} rows per GPU', 'trainable_parameters': n_params,
-                       'path': 'composite (library GEMMs for the conditioner, b2f transformer kernels)'},
+                       'path': 'composite (library GEMMs for the conditioner, b2f transformer kernels)' if D > 512
+                       else 'fused (b2f_flow_apply + b2f_flow_backward)'},
             'final_loss': float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -360,12 +366,12 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='q256', choices=sorted(WORKLOADS) + ['w1024fit'])
+    ap.add_argument('--workload', default='q256', choices=sorted(WORKLOADS) + ['w1024fit', 'q256fit'])
     ap.add_argument('--rows', type=int, default=0, help='override rows per GPU')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
-    if args.workload == 'w1024fit':
+    if args.workload in ('w1024fit', 'q256fit'):
         run_fit(args)
     elif args.impl == 'reference':
         run_reference(args)

@@ -48,7 +48,9 @@ def _lp_and_sample(flow, x, z):
 @pytest.mark.parametrize('preset,D,B', [('CouplingRQNSF', 256, 1000), ('CouplingRQNSF', 64, 4096 + 77),
                                         ('CouplingRQNSF', 128, 128), ('CouplingRQNSF', 32, 5),
                                         ('RealNVP', 64, 3000), ('NICE', 64, 1111), ('RealNVP', 128, 777),
-                                        ('InverseRealNVP', 32, 300), ('NICE', 128, 129)])
+                                        ('InverseRealNVP', 32, 300), ('NICE', 128, 129), ('MAF', 128, 700),
+                                        ('MaskedAutoregressiveRQNSF', 128, 333), ('IAF', 64, 200), ('MAF', 32, 64),
+                                        ('MaskedAutoregressiveRQNSF', 48, 130)])
 def test_tensor_core_flow_matches_generic_kernel_and_oracle(preset, D, B):
     """Coupling presets through the tcgen05 kernel vs the generic fp32 kernel (B2F_DISABLE_TC=1) and the CPU oracle.
     Spline layers run the conditioner in single-pass tf32 (max |d log_prob| 0.037 at |log_prob| ~
@@ -77,7 +79,7 @@ def test_tensor_core_flow_matches_generic_kernel_and_oracle(preset, D, B):
         tol = (1e-4 if 'log' in n else 2e-3) if 'RQNSF' in preset else 2e-5
         err = ((a - b).abs() / (1 + b.abs())).max().item()
         assert err < tol, (n, err)
-    nb = min(B, 512)
+    nb = min(B, 512 if 'Masked' not in preset and preset not in ('MAF', 'IAF') else 48)
     lp_ref = oracle.log_prob(x[:nb]).double()
     assert ((tc[0][:nb].double().cpu() - lp_ref).abs() / (1 + lp_ref.abs())).max().item() < 1e-4
     xs_ref, lps_ref = oracle.sample_from_noise(z[:nb], return_log_prob=True)

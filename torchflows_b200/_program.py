@@ -107,7 +107,7 @@ _TC_GEOM = {  # transformer kind -> (parameter columns per element CPE, elements
 
 def tc_eligible(op: LoweredOp, D: int) -> bool:
     """Mirror of try_launch_flow_tc's per-op conditions (csrc/b2f_flow_tc.cu)."""
-    if op.kind != N.OP_COUPLING or op.tkind not in _TC_GEOM or D % 16 != 0 or D < 32:
+    if op.kind not in (N.OP_COUPLING, N.OP_MADE) or op.tkind not in _TC_GEOM or D % 16 != 0 or D < 32:
         return False
     x3 = _TC_GEOM[op.tkind][2]
     if x3:
@@ -130,16 +130,21 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
     if hit is not None and hit[0] == ver:
         return hit[1]
     cpe, epc, x3 = _TC_GEOM[op.tkind]
+    made = op.kind == N.OP_MADE
     with torch.no_grad():
-        H, Dh = W1.shape[0], D // 2
+        if made:       # masks folded into the weight tiles
+            W1, W2 = W1.detach() * op.consts[0], W2.detach() * op.consts[1]
+        H = W1.shape[0]
+        Ks = D if made else D // 2           # source columns (K of GEMM1), in PHYSICAL order
+        Dh = D if made else D // 2           # target elements
         P = params_per_element(op.tkind, op.n_bins)
         w1 = W1.detach().flip(1) if flipped else W1.detach()
         w1_hi = round_tf32(w1)
-        W1p = W1.new_zeros(32, (3 if x3 else 1) * Dh)
-        W1p[:H, :Dh] = w1_hi
+        W1p = W1.new_zeros(32, (3 if x3 else 1) * Ks)
+        W1p[:H, :Ks] = w1_hi
         if x3:
-            W1p[:H, Dh:2 * Dh] = round_tf32(w1 - w1_hi)
-            W1p[:H, 2 * Dh:] = w1_hi
+            W1p[:H, Ks:2 * Ks] = round_tf32(w1 - w1_hi)
+            W1p[:H, 2 * Ks:] = w1_hi
         w1c = umma_canonical(W1p)
         K2 = ((3 if x3 else 1) * H + 2 + 7) // 8 * 8
         n_chunks = (Dh + epc - 1) // epc

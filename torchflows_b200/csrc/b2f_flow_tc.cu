@@ -55,6 +55,7 @@ template <> struct TcGeom<B2F_T_SHIFT_SUB> { static constexpr int CPE = 1, EPC =
 struct TcOp {
     int kind, tkind, H, K2;
     int x3;                     // 3xTF32 operand split (affine / shift layers)
+    int made;                   // masked autoregressive one-pass layer: source = target = all D columns
     int n_chunks, N2;           // GEMM2: chunks per layer, UMMA N of a chunk
     float boundary;
     int flip_before;            // flip state when this op runs (host-computed)
@@ -117,7 +118,13 @@ template <int TK, int MODE>
 __device__ __forceinline__ float tc_chunk_loop(const TcSmem& s, const TcOp& op, uint32_t tbase, uint32_t lane_addr,
                                                int Dh, int m_t, int sub, int lane, uint32_t& cc) {
     constexpr int CPE = TcGeom<TK>::CPE, EPC = TcGeom<TK>::EPC, EPS = EPC / 4;   // elements per epilogue sub-warp
-    uint8_t* tgt = reinterpret_cast<uint8_t*>(op.flip_before ? s.xlo : s.xhi);   // logical target half
+    const int D = 2 * Dh, n_tgt = op.made ? D : Dh, t0 = op.made ? 0 : Dh;
+    // logical target element e lives at logical column t0 + e = physical column (flip ? D-1-col : col)
+    auto tgt_ptr = [&](int e) {
+        const int col = t0 + e, c = op.flip_before ? D - 1 - col : col;
+        uint8_t* base = reinterpret_cast<uint8_t*>(c < Dh ? s.xlo : s.xhi);
+        return reinterpret_cast<float*>(base + umma::canon_off(m_t, c < Dh ? c : c - Dh, Dh));
+    };
     float ldpart = 0.0f;
     for (int c = 0; c < op.n_chunks; ++c, ++cc) {
         const int b = cc & 1;
@@ -133,8 +140,7 @@ __device__ __forceinline__ float tc_chunk_loop(const TcSmem& s, const TcOp& op, 
                 umma::tmem_ld8_nowait<8>(tcol + i * 24 + 8, acc);
                 umma::tmem_ld8_nowait<16>(tcol + i * 24 + 16, acc);
                 umma::tmem_ld_wait();
-                const int k_loc = op.flip_before ? Dh - 1 - e : e;
-                float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
+                float* px = tgt_ptr(e);
                 float out, ld;
                 transform_element<TK, MODE, 24>(*px, acc, op.boundary, out, ld);
                 *px = out;
@@ -151,12 +157,11 @@ __device__ __forceinline__ float tc_chunk_loop(const TcSmem& s, const TcOp& op, 
 #pragma unroll
             for (int i = 0; i < EPS; ++i) {
                 const int e = c * EPC + sub * EPS + i;
-                if (e < Dh) {
+                if (e < n_tgt) {
                     float acc[CPE];
 #pragma unroll
                     for (int p = 0; p < CPE; ++p) acc[p] = u[i * CPE + p];
-                    const int k_loc = op.flip_before ? Dh - 1 - e : e;
-                    float* px = reinterpret_cast<float*>(tgt + umma::canon_off(m_t, k_loc, Dh));
+                    float* px = tgt_ptr(e);
                     float out, ld;
                     transform_element<TK, MODE, CPE>(*px, acc, op.boundary, out, ld);
                     *px = out;
@@ -179,17 +184,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
     // ---- carve shared memory -----------------------------------------------------------------------------
     int K2max = 8, K1max = Dh, W2max = 0, any_x3 = 0;
     for (int i = 0; i < A.n_ops; ++i)
-        if (A.ops[i].kind == B2F_OP_COUPLING) {
+        if (A.ops[i].kind == B2F_OP_COUPLING || A.ops[i].kind == B2F_OP_MADE) {
             K2max = max(K2max, A.ops[i].K2);
-            K1max = max(K1max, (A.ops[i].x3 ? 3 : 1) * Dh);
+            K1max = max(K1max, (A.ops[i].x3 ? 3 : 1) * (A.ops[i].made ? D : Dh));
             W2max = max(W2max, A.ops[i].N2 * A.ops[i].K2);
-            any_x3 |= A.ops[i].x3;
+            any_x3 = max(any_x3, A.ops[i].x3 ? (A.ops[i].made ? 2 : 1) : 0);
         }
     TcSmem s;
     uint8_t* p = smem_raw;
     s.xlo = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
     s.xhi = reinterpret_cast<float*>(p); p += 128 * Dh * 4;
-    s.xl3 = reinterpret_cast<float*>(p); p += any_x3 ? 128 * Dh * 4 : 0;
+    s.xl3 = reinterpret_cast<float*>(p); p += any_x3 * 128 * Dh * 4;      // low parts of one or both halves
     s.w1 = reinterpret_cast<float*>(p); p += kTcN1 * K1max * 4;
     s.a2 = reinterpret_cast<float*>(p); p += 128 * K2max * 4;
     s.w2buf = reinterpret_cast<float*>(p); p += 2 * W2max * 4;
@@ -231,9 +236,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
                 for (int oi = 0; oi < A.n_ops; ++oi) {
                     const TcOp& op = A.ops[oi];
-                    if (op.kind != B2F_OP_COUPLING) continue;
+                    if (op.kind != B2F_OP_COUPLING && op.kind != B2F_OP_MADE) continue;
                     umma::mbar_wait_backoff(&s.bars[BAR_W1_EMPTY], (lc & 1) ^ 1);
-                    const uint32_t w1_bytes = kTcN1 * (op.x3 ? 3 : 1) * Dh * 4;
+                    const uint32_t w1_bytes = kTcN1 * (op.x3 ? 3 : 1) * (op.made ? D : Dh) * 4;
                     umma::mbar_arrive_expect_tx(&s.bars[BAR_W1_FULL], w1_bytes);
                     umma::bulk_g2s(s.w1, op.w1c, w1_bytes, &s.bars[BAR_W1_FULL]);
                     const uint32_t ch_bytes = op.N2 * op.K2 * 4;
@@ -255,23 +260,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
             for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
                 for (int oi = 0; oi < A.n_ops; ++oi) {
                     const TcOp& op = A.ops[oi];
-                    if (op.kind != B2F_OP_COUPLING) continue;
+                    if (op.kind != B2F_OP_COUPLING && op.kind != B2F_OP_MADE) continue;
                     const uint32_t ph = lc & 1;
                     umma::mbar_wait_backoff(&s.bars[BAR_W1_FULL], ph);
                     umma::mbar_wait_backoff(&s.bars[BAR_A1_READY], ph);
                     umma::tc_fence_after_sync();
-                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T   (3xTF32: K blocks [x | x | x_lo] . [w_hi | w_lo | w_hi])
-                    const uint32_t a_src = umma::smem_u32(op.flip_before ? s.xhi : s.xlo);
-                    const uint32_t a_lo3 = umma::smem_u32(s.xl3);
+                    // GEMM1: D1[128 x 32] = x_src[128 x Ks] * W1c[32 x Ks]^T.  Source = one half (coupling) or both halves in
+                    // physical order (MADE).  3xTF32: K blocks [x | x | x_lo] . [w_hi | w_lo | w_hi].
+                    const uint32_t xlo_a = umma::smem_u32(s.xlo), xhi_a = umma::smem_u32(s.xhi), xl3_a = umma::smem_u32(s.xl3);
                     const uint32_t b1a = umma::smem_u32(s.w1);
                     const uint32_t idesc1 = umma::make_idesc_tf32(128, kTcN1);
-                    const int nblk = op.x3 ? 3 : 1, kpb = Dh / 8;
+                    const int nblk = op.x3 ? 3 : 1, nseg = op.made ? 2 : 1, kpb = Dh / 8;
+                    const uint32_t sbo_b = nblk * nseg * Dh * 32;
+                    int kidx = 0;
                     for (int blk = 0; blk < nblk; ++blk)
-                        for (int ks = 0; ks < kpb; ++ks)
-                            umma::mma_tf32_ss(tbase + kTcColD1,
-                                              umma::make_smem_desc((blk < 2 ? a_src : a_lo3) + ks * 256, 128, Dh * 32),
-                                              umma::make_smem_desc(b1a + (blk * kpb + ks) * 256, 128, nblk * Dh * 32), idesc1,
-                                              (blk | ks) > 0);
+                        for (int seg = 0; seg < nseg; ++seg) {
+                            uint32_t a_base;
+                            if (blk < 2) a_base = op.made ? (seg == 0 ? xlo_a : xhi_a) : (op.flip_before ? xhi_a : xlo_a);
+                            else a_base = xl3_a + seg * 128 * Dh * 4;
+                            for (int ks = 0; ks < kpb; ++ks, ++kidx)
+                                umma::mma_tf32_ss(tbase + kTcColD1, umma::make_smem_desc(a_base + ks * 256, 128, Dh * 32),
+                                                  umma::make_smem_desc(b1a + kidx * 256, 128, sbo_b), idesc1, kidx > 0);
+                        }
                     umma::mma_commit(&s.bars[BAR_D1_FULL]);
                     umma::mma_commit(&s.bars[BAR_W1_EMPTY]);
                     umma::mbar_wait(&s.bars[BAR_A2_FULL], ph);
@@ -374,19 +384,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                 // ---------------- coupling layer ----------------
                 const uint32_t ph = lc & 1;
                 if (op.x3) {
-                    // low parts of the source half for the 3xTF32 split: x_lo = x - trunc_tf32(x), exact in fp32
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(op.flip_before ? s.xhi : s.xlo);
-                    uint8_t* dst = reinterpret_cast<uint8_t*>(s.xl3);
+                    // low parts of the source columns for the 3xTF32 split: x_lo = x - trunc_tf32(x), exact in fp32
+                    const int nseg = op.made ? 2 : 1;
                     const int m = rg * 8 + r8;
-                    for (int kc = kq; kc < Dh / 4; kc += 4) {
-                        const uint32_t off = umma::canon_off(m, 4 * kc, Dh);
-                        const float4 v = *reinterpret_cast<const float4*>(src + off);
-                        float4 lo;
-                        lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                        lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                        lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                        lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                        *reinterpret_cast<float4*>(dst + off) = lo;
+                    for (int seg = 0; seg < nseg; ++seg) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(
+                            op.made ? (seg == 0 ? s.xlo : s.xhi) : (op.flip_before ? s.xhi : s.xlo));
+                        uint8_t* dst = reinterpret_cast<uint8_t*>(s.xl3) + seg * 128 * Dh * 4;
+                        for (int kc = kq; kc < Dh / 4; kc += 4) {
+                            const uint32_t off = umma::canon_off(m, 4 * kc, Dh);
+                            const float4 v = *reinterpret_cast<const float4*>(src + off);
+                            float4 lo;
+                            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                            *reinterpret_cast<float4*>(dst + off) = lo;
+                        }
                     }
                 }
                 umma::fence_proxy_async_smem();            // our generic-proxy writes to xlo/xhi/xl3 -> tensor core
@@ -487,7 +501,8 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         t.kind = o.kind; t.tkind = o.tkind; t.H = o.n_hidden; t.boundary = o.boundary; t.flip_before = flip;
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
-        if (o.kind != B2F_OP_COUPLING) return 0;
+        if (o.kind != B2F_OP_COUPLING && o.kind != B2F_OP_MADE) return 0;
+        t.made = o.kind == B2F_OP_MADE;
         if (!(o.flags & B2F_FLAG_TC_OPERANDS) || !o.p[4] || !o.p[5] || !o.p[1]) return 0;
         const bool rq = o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV;
         const int Dh_ = D / 2;
@@ -503,11 +518,11 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         if (((o.flags & B2F_FLAG_TC_FLIPPED) != 0) != (flip != 0))
             return fail(B2F_ERR_INVALID, "op %d: tensor-core operands were laid out for the wrong flip state", i);
         t.N2 = epc * cpe;
-        t.n_chunks = (Dh_ + epc - 1) / epc;
+        t.n_chunks = ((t.made ? D : Dh_) + epc - 1) / epc;
         K2max = std::max(K2max, t.K2);
-        K1max = std::max(K1max, (t.x3 ? 3 : 1) * Dh_);
+        K1max = std::max(K1max, (t.x3 ? 3 : 1) * (t.made ? D : Dh_));
         W2max = std::max(W2max, t.N2 * t.K2);
-        any_x3 |= t.x3;
+        any_x3 = std::max(any_x3, t.x3 ? (t.made ? 2 : 1) : 0);
         t.b1 = (const float*)o.p[1]; t.w1c = (const float*)o.p[4]; t.w2c = (const float*)o.p[5];
         if ((reinterpret_cast<uintptr_t>(t.w1c) & 15) || (reinterpret_cast<uintptr_t>(t.w2c) & 15)) return 0;
         ++n_coupling;
