@@ -209,13 +209,51 @@ def fit_cases():
     return cases
 
 
+CONTEXT_CASES = [
+    # (preset, event_shape, context_shape, batch_shape)   -- test/constants.py:5 context shapes
+    ('RealNVP', (3,), (2,), (7,)),
+    ('NICE', (3, 5, 2), (3,), (5, 2)),
+    ('CouplingRQNSF', (8,), (3, 5, 2), (9,)),
+    ('MAF', (5,), (2,), (11,)),
+    ('IAF', (2,), (3, 5, 2), (6,)),
+    ('MaskedAutoregressiveRQNSF', (4,), (3,), (5,)),
+    ('InverseAutoregressiveRQNSF', (3,), (2,), (4,)),
+]
+
+
+def context_cases():
+    """Context-conditioned presets: x, context -> z, log_det, log_prob, inverse; gradients of the loss."""
+    cases = []
+    for n, (preset, event_shape, context_shape, batch_shape) in enumerate(CONTEXT_CASES):
+        torch.manual_seed(900 + n)
+        flow = Flow(getattr(ref_arch, preset)(event_shape, context_shape=context_shape))
+        flow.eval()
+        x = torch.randn(*batch_shape, *event_shape)
+        c = torch.randn(*batch_shape, *context_shape)
+        with torch.no_grad():
+            z, ld_f = flow.bijection.forward(x, context=c)
+            lp = flow.log_prob(x, context=c)
+            xr, ld_r = flow.bijection.inverse(z, context=c)
+        sd = {k: v.clone() for k, v in flow.state_dict().items()}
+        xg = x.clone().reshape(-1, *event_shape).requires_grad_(True)
+        cg = c.reshape(-1, *context_shape)
+        loss = flow._base_batch_loss((xg, torch.ones(len(xg)), cg))
+        loss.backward()
+        grads = {k: p.grad.clone() for k, p in flow.named_parameters() if p.grad is not None and p.numel()}
+        cases.append(dict(preset=preset, event_shape=event_shape, context_shape=context_shape, state_dict=sd, x=x,
+                          context=c, z=z, ld_f=ld_f, log_prob=lp, xr=xr, ld_r=ld_r, loss=loss.detach().clone(),
+                          grad_x=xg.grad.clone(), grads=grads))
+    return cases
+
+
 def main():
     torch.set_num_threads(1)   # fixed reduction order on the generating side
     torch.save(transformer_cases(), os.path.join(OUT, 'transformers.pt'))
     torch.save(preset_cases(), os.path.join(OUT, 'presets.pt'))
     torch.save(grad_cases(), os.path.join(OUT, 'grads.pt'))
     torch.save(fit_cases(), os.path.join(OUT, 'fit.pt'))
-    for f in ('transformers.pt', 'presets.pt', 'grads.pt', 'fit.pt'):
+    torch.save(context_cases(), os.path.join(OUT, 'context.pt'))
+    for f in ('transformers.pt', 'presets.pt', 'grads.pt', 'fit.pt', 'context.pt'):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')
 
 

@@ -174,3 +174,60 @@ def test_deepcopy_and_cuda_inputs(name):
         flow.fit(x.reshape(-1, *event_shape), n_epochs=3)
         flow.fit(x.reshape(-1, *event_shape).cuda(), n_epochs=3)
         deepcopy(flow)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# context-conditioned parametrisations (test/constants.py:5), SURVEY section 8f-1
+# ---------------------------------------------------------------------------------------------------------------------
+CONTEXT_SHAPES = [(2,), (3,), (3, 5, 2)]
+
+
+@pytest.mark.parametrize('name', ['NICE', 'RealNVP', 'CouplingRQNSF', 'MAF', 'IAF', 'InverseAutoregressiveRQNSF',
+                                  'MaskedAutoregressiveRQNSF'])
+@pytest.mark.parametrize('batch_shape', [(2,), (5, 2, 3)])
+@pytest.mark.parametrize('event_shape', EVENT_SHAPES)
+@pytest.mark.parametrize('context_shape', CONTEXT_SHAPES)
+def test_presets_with_context(name, batch_shape, event_shape, context_shape):
+    """test/test_reconstruction_bijections.py:146-178 with context and test/test_autograd_bijections.py:41-54."""
+    from torchflows_b200 import Flow
+    torch.manual_seed(0)
+    x = torch.randn(*batch_shape, *event_shape, device=DEV)
+    c = torch.randn(*batch_shape, *context_shape, device=DEV)
+    bij = getattr(_presets(), name)(event_shape, context_shape=context_shape).to(DEV)
+    z, ld_f = bij.forward(x, context=c)
+    xr, ld_i = bij.inverse(z, context=c)
+    assert z.shape == x.shape and ld_f.shape == ld_i.shape == batch_shape
+    assert torch.allclose(x, xr, atol=ATOL) and torch.allclose(ld_f, -ld_i, atol=ATOL)
+    if name not in ('IAF', 'InverseAutoregressiveRQNSF'):
+        xc = x.clone().requires_grad_(True)
+        lp = Flow(bij).to(DEV).log_prob(xc, context=c)
+        g = torch.autograd.grad(lp.mean(), xc)[0]
+        assert lp.shape == batch_shape and g.shape == x.shape and g.isfinite().all()
+
+
+@pytest.mark.parametrize('name', ['ElementwiseAffine', 'ElementwiseShift', 'ElementwiseRQSpline', 'ActNorm'])
+@pytest.mark.parametrize('context_shape', CONTEXT_SHAPES)
+def test_elementwise_with_context(name, context_shape):
+    from torchflows_b200.bijections.finite.autoregressive import layers
+    torch.manual_seed(0)
+    event_shape, batch_shape = (3, 5, 2), (5, 2)
+    layer = getattr(layers, name)(event_shape, context_shape=context_shape).to(DEV)
+    x = torch.randn(*batch_shape, *event_shape, device=DEV)
+    c = torch.randn(*batch_shape, *context_shape, device=DEV)
+    _z, _ = layer.forward(x, context=c)
+    xr, _ = layer.inverse(_z, context=c)
+    assert torch.allclose(x, xr, atol=ATOL)
+
+
+def test_fit_and_sample_with_context():
+    """test/test_fit.py:156-182 and flows.py:680-692 (both context broadcasting options of Flow.sample)."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import RealNVP
+    torch.manual_seed(0)
+    for n_train, context_shape in ((10, (2,)), (2200, (3, 5, 2))):
+        flow = Flow(RealNVP((3,), context_shape=context_shape)).to(DEV)
+        x, c = torch.randn(n_train, 3), torch.randn(n_train, *context_shape)
+        flow.fit(x, n_epochs=2, context_train=c, x_val=torch.randn(5, 3), context_val=torch.randn(5, *context_shape))
+        a = flow.sample(4, context=torch.randn(4, *context_shape))               # one context per sample
+        b = flow.sample(6, context=torch.randn(2, *context_shape))               # 6 samples for each of 2 contexts
+        assert a.shape == (4, 3) and b.shape == (6, 2, 3)

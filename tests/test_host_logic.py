@@ -76,8 +76,11 @@ def test_lowering_programs():
     # non-default conditioner depth is decided at construction: composite, not fused
     deep = RealNVP(4, conditioner_kwargs={'n_layers': 3}).eval()
     assert deep.layers[2].lower('forward') is None and deep.lower('forward') is None
-    with pytest.raises(NotImplementedError):
-        RealNVP(4, context_shape=(2,))
+    # context-conditioned couplings / elementwise layers are composites; MADE layers stay fused (the context provably
+    # never reaches their outputs), ActNorm and the permutations ignore the context
+    ctx = RealNVP(4, context_shape=(2,)).eval()
+    assert ctx.lower('forward') is None and ctx.layers[2].lower('forward') is None and ctx.layers[3].lower('forward')
+    assert MAF(4, context_shape=(2,)).eval().layers[2].lower('forward') is not None
 
 
 def test_tile_layout_round_trip():

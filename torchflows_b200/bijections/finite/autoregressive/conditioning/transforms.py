@@ -162,7 +162,7 @@ class MADE(ElementwiseConditionerTransform):
     def predict_theta_flat(self, x: torch.Tensor, context: torch.Tensor = None):
         theta = self.sequential(self.context_combiner(x, context))
         if self.global_parameter_mask is None:
-            return torch.flatten(theta, start_dim=theta.dim() - len(self.input_event_shape))
+            return theta          # already flat: (*batch, n_out * P)
         return theta[..., ~self.global_parameter_mask]
 
 

@@ -22,12 +22,6 @@ from torchflows_b200.bijections.finite.autoregressive.transformers.spline.ration
 from torchflows_b200.utils import flatten_event, get_batch_shape, unflatten_event
 
 
-def _no_context(context_shape, what: str):
-    if context_shape is not None:
-        raise NotImplementedError(f'{what}: context-conditioned flows are not part of the B200 hot path yet '
-                                  '(SURVEY section 8f-1); construct with context_shape=None')
-
-
 def _fits_fused_kernel(n_dim: int, n_hidden: int) -> bool:
     """Mirror of the shared-memory budget of csrc/b2f_flow.cu at its smallest tile (32 samples): the sample tile
     [32][D|1] plus the hidden activations [32][H|1] (twice for the backward kernel's gradient tile) must fit in
@@ -73,7 +67,6 @@ class CouplingBijection(AutoregressiveBijection):
                  coupling: PartialCoupling = None, conditioner_transform_class: Type[ConditionerTransform] = FeedForward,
                  coupling_kwargs: dict = None, conditioner_kwargs: dict = None, transformer_kwargs: dict = None,
                  l2_regularization: bool = True, **kwargs):
-        _no_context(context_shape, type(self).__name__)
         coupling_kwargs, conditioner_kwargs = coupling_kwargs or {}, conditioner_kwargs or {}
         transformer_kwargs = transformer_kwargs or {}
         if coupling is None:
@@ -86,9 +79,11 @@ class CouplingBijection(AutoregressiveBijection):
                          context_shape=context_shape, l2_regularization=l2_regularization, **kwargs)
         self.coupling = coupling
         ct = conditioner_transform
-        self._fusable = (isinstance(coupling, HalfSplit) and type(ct) is FeedForward and ct.n_layers == 2
-                         and ct.nonlinearity is nn.Tanh and ct.is_plain and _transformer_fusable(transformer)
-                         and _fits_fused_kernel(self.n_dim, ct.n_hidden))
+        # a context tensor is concatenated to the conditioner input (conditioning/context.py:46-60): such layers run
+        # as a composite (conditioner = library GEMMs on [x_A, context], transformer = stand-alone kernel)
+        self._fusable = (context_shape is None and isinstance(coupling, HalfSplit) and type(ct) is FeedForward
+                         and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
+                         and _transformer_fusable(transformer) and _fits_fused_kernel(self.n_dim, ct.n_hidden))
 
     # -- reference API ---------------------------------------------------------------------------------------
     def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
@@ -159,7 +154,6 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
     def __init__(self, event_shape, transformer_class: Type[ScalarTransformer], context_shape=None,
                  transformer_kwargs: dict = None, conditioner_kwargs: dict = None, l2_regularization: bool = True,
                  **kwargs):
-        _no_context(context_shape, type(self).__name__)
         conditioner_kwargs, transformer_kwargs = conditioner_kwargs or {}, transformer_kwargs or {}
         transformer = transformer_class(event_shape=event_shape, **transformer_kwargs)
         conditioner_transform = MADE(input_event_shape=event_shape, transformed_event_shape=event_shape,
@@ -171,15 +165,29 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
         if not (ct.n_layers == 2 and ct.is_plain and _transformer_fusable(transformer)):
             raise NotImplementedError('masked autoregressive layers are implemented for the default MADE depth '
                                       '(n_layers=2), predicted parameters only, and n_bins=8 splines')
-        self.register_buffer('_fin_steps', ct.finalisation_steps(), persistent=False)
+        # With a context, MADE concatenates it to x and gives the context columns degrees n_dim+1.. (transforms.py:
+        # 222-226).  Hidden units that see a context column therefore have a degree > n_dim, and the strict output mask
+        # (transforms.py:254) cuts every such unit off from every output: the context provably never reaches h.  The
+        # fused kernels therefore use the first n_dim input columns only; the check below guards the argument.
+        self._n_context_cols = ct.n_input_event_dims - self.n_dim
+        if self._n_context_cols > 0:
+            m1, m2 = ct.sequential[0].mask, ct.sequential[2].mask
+            sees_context = (m1[:, self.n_dim:] != 0).any(dim=1).float()
+            if float((m2 @ sees_context).abs().sum()) != 0.0:
+                raise NotImplementedError('MADE masks let the context reach the outputs; this configuration is not fused')
+        fin = ct.sequential[0].mask[:, :self.n_dim].sum(dim=1).to(torch.int32)
+        self.register_buffer('_fin_steps', fin, persistent=False)
 
     def _lower(self, one_pass: bool, transformer_direction: str):
         seq = self.conditioner_transform.sequential
         n_bins, boundary = self._spline_args()
         flags = 0 if self.sequential_log_det_reference_quirk else N.FLAG_SEQ_LOGDET_EXACT
-        consts = [seq[0].mask, seq[2].mask] + ([] if one_pass else [self._fin_steps])
+        w1, m1 = seq[0].weight, seq[0].mask
+        if self._n_context_cols > 0:
+            w1, m1 = w1[:, :self.n_dim], m1[:, :self.n_dim]
+        consts = [m1, seq[2].mask] + ([] if one_pass else [self._fin_steps])
         return [prog.LoweredOp(kind=N.OP_MADE if one_pass else N.OP_MADE_SEQ, tkind=self._tkind(transformer_direction),
-                               leafs=[seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias], consts=consts,
+                               leafs=[w1, seq[0].bias, seq[2].weight, seq[2].bias], consts=consts,
                                n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, flags=flags, owner=self)]
 
     def lower(self, direction: str):
@@ -211,41 +219,55 @@ class ElementwiseBijection(AutoregressiveBijection):
                  transformer_kwargs: dict = None, fill_value: Union[float, torch.Tensor] = None,
                  conditioner_transform_class: Type[ConditionerTransform] = Linear, conditioner_kwargs: dict = None,
                  **kwargs):
-        _no_context(context_shape, type(self).__name__)
         transformer = transformer_class(event_shape=event_shape, **(transformer_kwargs or {}))
-        if fill_value is None:
-            value = torch.randn(*transformer.parameter_shape)
-        elif isinstance(fill_value, torch.Tensor):
-            if fill_value.shape != transformer.parameter_shape:
-                raise ValueError('Shape of fill_value must match the transformer parameter shape')
-            value = fill_value
+        if context_shape is None:
+            if fill_value is None:
+                value = torch.randn(*transformer.parameter_shape)
+            elif isinstance(fill_value, torch.Tensor):
+                if fill_value.shape != transformer.parameter_shape:
+                    raise ValueError('Shape of fill_value must match the transformer parameter shape')
+                value = fill_value
+            else:
+                value = torch.full(size=tuple(transformer.parameter_shape), fill_value=float(fill_value))
+            super().__init__(event_shape=event_shape, context_shape=None, transformer=transformer,
+                             conditioner_transform=None, **kwargs)
+            self.register_parameter('value', nn.Parameter(value))
+            self.use_global_parameters = True
         else:
-            value = torch.full(size=tuple(transformer.parameter_shape), fill_value=float(fill_value))
-        super().__init__(event_shape=event_shape, context_shape=None, transformer=transformer,
-                         conditioner_transform=None, **kwargs)
-        self.register_parameter('value', nn.Parameter(value))
-        self.use_global_parameters = True
+            # parameters predicted from the context by a conditioner (default: one Linear layer), layers_base.py:281-296
+            conditioner_transform = conditioner_transform_class(
+                input_event_shape=None, context_shape=context_shape, parameter_shape=transformer.parameter_shape,
+                **(conditioner_kwargs or {}))
+            super().__init__(event_shape=event_shape, context_shape=context_shape, transformer=transformer,
+                             conditioner_transform=conditioner_transform, **kwargs)
+            self.register_buffer('value', torch.empty(size=()))
+            self.use_global_parameters = False
 
     def prepare_h(self, context: torch.Tensor, batch_shape):
-        """Parameters broadcast over the batch as a stride-0 view (no copy)."""
-        return self.value.expand(*batch_shape, *self.value.shape)
+        """Global parameters: broadcast over the batch as a stride-0 view (no copy).  Context-conditioned: predicted."""
+        if self.use_global_parameters:
+            return self.value.expand(*batch_shape, *self.value.shape)
+        if context is None:
+            raise RuntimeError('Context must be provided')
+        return self.conditioner_transform(x=None, context=context)
 
     def lower(self, direction: str):
         tk = self._tkind(direction)
-        if tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV) and _fits_fused_kernel(self.n_dim, 1):
+        if (self.use_global_parameters and tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV)
+                and _fits_fused_kernel(self.n_dim, 1)):
             return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
         return None
 
-    def _run_direction(self, x, direction):
+    def _run_direction(self, x, direction, context=None):
         if self.lower(direction) is not None:
             return self._run_fused(x, direction)
         batch_shape = get_batch_shape(x, self.event_shape)
-        h = self.prepare_h(None, batch_shape)          # stride-0 view: the kernel broadcasts it
+        h = self.prepare_h(context, batch_shape)       # stride-0 view (global) or per-sample parameters (context)
         fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse
         return fn(x, h)
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_direction(x, "forward")
+        return self._run_direction(x, "forward", context)
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_direction(z, "inverse")
+        return self._run_direction(z, "inverse", context)

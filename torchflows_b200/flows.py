@@ -118,8 +118,6 @@ class BaseFlow(nn.Module):
         if not any(p.requires_grad for p in params):
             self.eval()
             return
-        if context_train is not None or context_val is not None:
-            raise NotImplementedError('context-conditioned training is not part of the B200 hot path yet')
         device = self.get_device()
         rank, world = _dist_info()
         n_train = len(x_train)
@@ -138,6 +136,18 @@ class BaseFlow(nn.Module):
         if len(w_dev) != n_train:
             raise ValueError(f'Expected same number of training data and training weights, '
                              f'but found {n_train} and {len(w_dev)}')
+        c_dev = None
+        if context_train is not None:
+            if len(context_train) != n_train:
+                raise ValueError(f'Expected same number of training data and training contexts, '
+                                 f'but found {n_train} and {len(context_train)}')
+            c_dev = context_train.to(device=device, dtype=torch.float32)
+        cv_dev = None
+        if x_val is not None and context_val is not None:
+            if len(context_val) != len(x_val):
+                raise ValueError(f'Expected same number of validation data and validation contexts, '
+                                 f'but found {len(x_val)} and {len(context_val)}')
+            cv_dev = context_val.to(device=device, dtype=torch.float32)
         if x_val is not None:
             xv_dev = x_val.to(device=device, dtype=torch.float32)
             wv_dev = (torch.ones(len(x_val)) if w_val is None else w_val).to(device=device, dtype=torch.float32)
@@ -173,7 +183,8 @@ class BaseFlow(nn.Module):
                 lo, hi = shard_bounds(stop - start, rank, world)
                 idx = slice(start + lo, start + hi) if order is None else order[start + lo:start + hi]
                 xb, wb = x_dev[idx], w_dev[idx]
-                loss, loss_value = self._loss_and_backward_inputs(xb, wb, stop - start, world)
+                cb = None if c_dev is None else c_dev[idx]
+                loss, loss_value = self._loss_and_backward_inputs(xb, wb, stop - start, world, cb)
                 if not torch.isfinite(loss_value):
                     self.load_state_dict(best_weights)       # roll back (flows.py:387-393)
                     warnings.warn('Flow training diverged. Reverting to previous weights.')
@@ -201,8 +212,8 @@ class BaseFlow(nn.Module):
                     acc = 0.0
                     for start in range(0, len(xv_dev), batch_size):
                         sl = slice(start, start + batch_size)
-                        acc += float(self._base_batch_loss((xv_dev[sl], wv_dev[sl]), reduction=torch.sum,
-                                                           use_regularization=False))
+                        vb = (xv_dev[sl], wv_dev[sl]) if cv_dev is None else (xv_dev[sl], wv_dev[sl], cv_dev[sl])
+                        acc += float(self._base_batch_loss(vb, reduction=torch.sum, use_regularization=False))
                 val_loss = acc / len(xv_dev)
                 if val_loss < best_val_loss:
                     best_val_loss, best_val_epoch = val_loss, epoch
@@ -219,16 +230,17 @@ class BaseFlow(nn.Module):
             self.load_state_dict(best_weights)
         self.eval()
 
-    def _loss_and_backward_inputs(self, xb, wb, n_global: int, world: int):
+    def _loss_and_backward_inputs(self, xb, wb, n_global: int, world: int, cb=None):
         """Loss of this rank's slice of a minibatch, scaled so that the mean over ranks of the gradients is the gradient
         of the global-batch loss -mean(w*log_prob)/event_size + regularization (flows.py:199-224); returns the local
         loss tensor (to call backward on) and the global loss value (all-reduced when world > 1)."""
         self._optimizer.zero_grad()
         if world == 1:
-            loss = self._base_batch_loss((xb, wb), reduction=torch.mean, use_regularization=True)
+            batch = (xb, wb) if cb is None else (xb, wb, cb)
+            loss = self._base_batch_loss(batch, reduction=torch.mean, use_regularization=True)
             return loss, loss.detach()
         import torch.distributed as dist
-        lp = self.log_prob(xb)
+        lp = self.log_prob(xb, context=cb)
         loss = -(lp * wb).sum() * (world / n_global) / self.event_size + self.regularization()
         loss_value = loss.detach().clone()
         dist.all_reduce(loss_value, op=dist.ReduceOp.SUM)
@@ -305,10 +317,27 @@ class Flow(BaseFlow):
         ``base.log_prob(z) + log_det_inverse`` exactly as in the reference (flows.py:710-712)."""
         if isinstance(sample_shape, int):
             sample_shape = (sample_shape,)
-        if context is not None:
-            raise NotImplementedError('context-conditioned sampling is not part of the B200 hot path yet')
-        z = self.base_sample(sample_shape=sample_shape)
-        return self._sample_from_base(z, no_grad, return_log_prob)
+        sample_shape = tuple(sample_shape)
+        if context is None:
+            z = self.base_sample(sample_shape=sample_shape)
+            return self._sample_from_base(z, no_grad, return_log_prob)
+        # context-conditioned (flows.py:680-692): either one context per sampled element, or one context tensor per
+        # entry of `context` for which `sample_shape` samples each are drawn
+        context = context.to(self.get_device())
+        if tuple(get_batch_shape(context, self.context_shape)) != sample_shape:
+            z = self.base_sample(sample_shape=(*sample_shape, len(context)))
+            context = context[None].expand(*sample_shape, *context.shape).contiguous() if len(sample_shape) == 1 else \
+                context[(None,) * len(sample_shape)].expand(*sample_shape, *context.shape).contiguous()
+        else:
+            z = self.base_sample(sample_shape=sample_shape)
+        if no_grad:
+            with torch.no_grad():
+                x, log_det = self.bijection.inverse(z.detach(), context=context)[:2]
+        else:
+            x, log_det = self.bijection.inverse(z, context=context)[:2]
+        if return_log_prob:
+            return x, self.base_log_prob(z) + log_det
+        return x
 
     def _sample_from_base(self, z: torch.Tensor, no_grad: bool = False, return_log_prob: bool = False):
         """The deterministic part of ``sample``: push base draws ``z`` through the inverse bijection."""
