@@ -238,3 +238,24 @@ def test_context_presets_vs_golden(golden, dev, idx):
             assert rel(params[k].grad, g) < tol, k
         elif params[k].grad is not None:
             assert params[k].grad.abs().max().item() < 1e-6, k
+
+
+def test_empty_batch_and_odd_shapes(dev):
+    """Edge cases: empty batch, single row, odd D, batch not a multiple of the tile, through every kernel family."""
+    import torchflows_b200.architectures as arch
+    from torchflows_b200 import Flow
+    torch.manual_seed(0)
+    for preset, D, B in (('CouplingRQNSF', 32, 130), ('RealNVP', 32, 129), ('NICE', 64, 5), ('MAF', 32, 70),
+                         ('MaskedAutoregressiveRQNSF', 32, 33), ('RealNVP', 3, 7), ('CouplingRQNSF', 7, 65), ('IAF', 5, 1)):
+        flow = Flow(getattr(arch, preset)(D)).to(dev).eval()
+        x = torch.randn(B, D, device=dev)
+        with torch.no_grad():
+            lp = flow.log_prob(x)
+            assert lp.shape == (B,) and torch.isfinite(lp).all()
+            assert flow.log_prob(x[:0]).shape == (0,)
+            z, ld = flow.bijection.forward(x[:0])
+            assert z.shape == (0, D) and ld.shape == (0,)
+            xs, lps = flow.sample(B, return_log_prob=True)
+            assert xs.shape == (B, D) and torch.isfinite(xs).all() and torch.isfinite(lps).all()
+            # row i of a batch does not depend on the other rows or on the tile it lands in
+            assert torch.equal(flow.log_prob(x[B // 2:B // 2 + 1]), lp[B // 2:B // 2 + 1])

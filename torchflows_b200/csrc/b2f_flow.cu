@@ -247,6 +247,7 @@ using namespace b2f;
 extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
                               float* log_prob, const float* base_loc, const float* base_log_scale, int64_t B,
                               int32_t D, int32_t flags, void* stream) {
+    if (B == 0 && n_ops >= 0 && D > 0) return B2F_OK;      // empty batch: nothing to do (pointers may be null)
     if (!ops || n_ops < 0 || !x || D <= 0 || B < 0) return fail(B2F_ERR_INVALID, "b2f_flow_apply: bad arguments");
     if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: %d ops > B2F_MAX_OPS", n_ops);
     if (B == 0) return B2F_OK;

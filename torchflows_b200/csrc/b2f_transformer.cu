@@ -142,6 +142,7 @@ using namespace b2f;
 extern "C" int b2f_transformer_apply(int32_t tkind, const float* x, const float* h, float* out, float* log_det,
                                      int32_t* k_out, int64_t n_rows, int32_t n_event, int64_t h_row_stride,
                                      int32_t n_bins, float boundary, int32_t flags, void* stream) {
+    if (n_rows == 0 && n_event > 0) return B2F_OK;
     if (!x || !h || !out || n_rows < 0 || n_event <= 0 || h_row_stride < 0)
         return fail(B2F_ERR_INVALID, "b2f_transformer_apply: bad arguments");
     const bool rq = tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV;
@@ -170,6 +171,7 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
                                         const float* glog_det, float* gx, float* gh, int64_t n_rows, int32_t n_event,
                                         int64_t h_row_stride, int32_t n_bins, float boundary, int32_t flags,
                                         void* stream) {
+    if (n_rows == 0 && n_event > 0) return B2F_OK;
     if (!x || !h || !gx || !gh || n_rows < 0 || n_event <= 0 || h_row_stride < 0)
         return fail(B2F_ERR_INVALID, "b2f_transformer_backward: bad arguments");
     if (tkind == B2F_T_RQ_INV)
@@ -193,6 +195,7 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
 }
 
 extern "C" int b2f_column_stats(const float* x, double* sum, double* sumsq, int64_t B, int32_t D, void* stream) {
+    if (B == 0 && D > 0) return B2F_OK;
     if (!x || !sum || !sumsq || B < 0 || D <= 0) return fail(B2F_ERR_INVALID, "b2f_column_stats: bad arguments");
     if (B == 0) return B2F_OK;
     const int block = 128;
