@@ -214,31 +214,41 @@ def run_ours(args):
         x_host.copy_(x)
         lp_host = torch.empty(B, pin_memory=True)
         xs_host = torch.empty(B, D, pin_memory=True)
-        copy_stream = torch.cuda.Stream(device=dev)
+        h2d_stream = torch.cuda.Stream(device=dev)
+        d2h_stream = torch.cuda.Stream(device=dev)
 
         def e2e_step():
-            # chunked so that the H2D of chunk i+1 and the D2H of chunk i-1 overlap the kernels of chunk i
-            events = []
-            for s in range(0, B, rows_c):
-                with torch.cuda.stream(copy_stream):
+            # Chunked and interleaved: while the kernels of chunk i run, chunk i+1 of x is on its way up (H2D) and the
+            # samples of chunk i-1 are on their way down (D2H) -- the two PCIe directions are used at the same time.
+            chunks = list(range(0, B, rows_c))
+            staged = {}
+
+            def stage(s):
+                with torch.cuda.stream(h2d_stream):
                     xc = x_host[s:s + rows_c].to(dev, non_blocking=True)
                     e = torch.cuda.Event()
-                    e.record(copy_stream)
+                    e.record(h2d_stream)
+                staged[s] = (xc, e)
+
+            stage(chunks[0])
+            for i, s in enumerate(chunks):
+                if i + 1 < len(chunks):
+                    stage(chunks[i + 1])
+                xc, e = staged.pop(s)
                 stream.wait_event(e)
-                lpc = flow.log_prob(xc)
+                lpc = flow.log_prob(xc)                                   # public API, device chunk
                 xc.record_stream(stream)
-                lp_host[s:s + rows_c].copy_(lpc, non_blocking=True)
-            for s in range(0, B, rows_c):
                 n = min(rows_c, B - s)
-                xsc = flow.sample(n, no_grad=True)                       # draws z on the device, inverse pass
+                xsc = flow.sample(n, no_grad=True)                        # draws z on the device, inverse pass
                 done = torch.cuda.Event()
                 done.record(stream)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done)
+                with torch.cuda.stream(d2h_stream):
+                    d2h_stream.wait_event(done)
+                    lp_host[s:s + n].copy_(lpc, non_blocking=True)
                     xs_host[s:s + n].copy_(xsc, non_blocking=True)
-                    xsc.record_stream(copy_stream)
-                events.append(done)
-            stream.wait_stream(copy_stream)
+                    lpc.record_stream(d2h_stream)
+                    xsc.record_stream(d2h_stream)
+            stream.wait_stream(d2h_stream)
 
         e2e_step()
         sync_all()
