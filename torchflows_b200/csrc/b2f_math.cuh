@@ -71,6 +71,61 @@ B2F_HD float exp_det(float t) {
     return i2f(f2i(p) + (int32_t)((uint32_t)f2i(r) << 23)); // multiply by 2^n through the exponent field
 }
 
+// ---- packed pairs: Blackwell executes two fp32 operations per lane in one FFMA2 / FADD2 / FMUL2 instruction
+// (PTX fma.rn.f32x2 ...).  Each half is the same correctly rounded IEEE operation as the scalar form, so results are
+// bit-identical to r_fma / r_add / r_mul; the spline evaluates its two softmaxes (widths, heights) as such pairs.
+struct f2 { float x, y; };
+B2F_HD f2 mk2(float x, float y) { f2 r; r.x = x; r.y = y; return r; }
+B2F_HD f2 pk_fma(f2 a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__)
+    f2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n\t mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t mov.b64 rc, {%6,%7};\n\t"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n\t mov.b64 {%0,%1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#else
+    return mk2(r_fma(a.x, b.x, c.x), r_fma(a.y, b.y, c.y));
+#endif
+}
+B2F_HD f2 pk_add(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    f2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t add.rn.f32x2 rd, ra, rb;\n\t"
+        " mov.b64 {%0,%1}, rd; }" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return mk2(r_add(a.x, b.x), r_add(a.y, b.y));
+#endif
+}
+B2F_HD f2 pk_mul(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+    f2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2,%3};\n\t mov.b64 rb, {%4,%5};\n\t mul.rn.f32x2 rd, ra, rb;\n\t"
+        " mov.b64 {%0,%1}, rd; }" : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#else
+    return mk2(r_mul(a.x, b.x), r_mul(a.y, b.y));
+#endif
+}
+// exp_det on both halves (same operation sequence as the scalar exp_det above)
+B2F_HD f2 exp_det2(f2 t) {
+    t.x = fmaxf(t.x, -86.0f); t.y = fmaxf(t.y, -86.0f);
+    const float kMagic = 12582912.0f;
+    const f2 r = pk_fma(t, mk2(0x1.715476p+0f, 0x1.715476p+0f), mk2(kMagic, kMagic));
+    const f2 n = pk_add(r, mk2(-kMagic, -kMagic));
+    const f2 f = pk_fma(n, mk2(-0x1.62e430p-1f, -0x1.62e430p-1f), t);
+    f2 p = mk2(0x1.6ada7ap-10f, 0x1.6ada7ap-10f);
+    p = pk_fma(p, f, mk2(0x1.127528p-7f, 0x1.127528p-7f));
+    p = pk_fma(p, f, mk2(0x1.55585ep-5f, 0x1.55585ep-5f));
+    p = pk_fma(p, f, mk2(0x1.5554p-3f, 0x1.5554p-3f));
+    p = pk_fma(p, f, mk2(0x1.fffffcp-2f, 0x1.fffffcp-2f));
+    p = pk_fma(p, f, mk2(1.0f, 1.0f));
+    p = pk_fma(p, f, mk2(1.0f, 1.0f));
+    p.x = i2f(f2i(p.x) + (int32_t)((uint32_t)f2i(r.x) << 23));
+    p.y = i2f(f2i(p.y) + (int32_t)((uint32_t)f2i(r.y) << 23));
+    return p;
+}
+
 // ---- math that is tolerance-checked only -------------------------------------------------------------
 // MODE 0: accurate library functions.  MODE 1: SFU approximations (ex2/lg2/rcp.approx) on the device.
 template <int MODE> B2F_HD float m_exp(float x) {
@@ -145,12 +200,6 @@ struct RqSel {           // what the evaluation needs from the bin that was foun
 // MODE 2 ("fast knots", opt-in): the softmax exponentials come from the SFU (ex2.approx) and the normalisation from
 // rcp.approx + Newton; knots then agree with the deterministic ones to ~2 ulp of the boundary and the bin index can
 // differ at exact ties -- tolerance-checked, not bit-checked.
-template <int MODE> B2F_HD float knot_exp(float t) {
-#if defined(__CUDA_ARCH__)
-    if (MODE >= 2) return __expf(t);
-#endif
-    return exp_det(t);
-}
 template <int MODE> B2F_HD float knot_rcp(float x) {
 #if defined(__CUDA_ARCH__)
     if (MODE >= 2) return m_rcp<1>(x);
@@ -158,41 +207,49 @@ template <int MODE> B2F_HD float knot_rcp(float x) {
     return r_rcp(x);
 }
 
+template <int MODE> B2F_HD f2 knot_exp2(f2 t) {
+#if defined(__CUDA_ARCH__)
+    if (MODE >= 2) return mk2(__expf(t.x), __expf(t.y));
+#endif
+    return exp_det2(t);
+}
+
 template <int NB, bool INV, int MODE, class H>
 B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel& s) {
     const int nb = NB > 0 ? NB : nb_rt;
-    float ex[NB > 0 ? NB : kRqMaxBins], ey[NB > 0 ? NB : kRqMaxBins];
+    f2 e[NB > 0 ? NB : kRqMaxBins];            // .x: widths softmax, .y: heights softmax, evaluated in lock-step
     // logits: widths u_x; heights u_x + u_y/1000 (rational_quadratic.py:75-76)
     float mx = -INFINITY, my = -INFINITY;
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
         const float ux = h(j);
         const float ty = r_fma(h(nb + j), 0x1.0624dep-10f, ux);
-        ex[j] = ux; ey[j] = ty;
+        e[j] = mk2(ux, ty);
         mx = fmaxf(mx, ux); my = fmaxf(my, ty);
     }
-    float sx = 0.0f, sy = 0.0f;
+    const f2 negm = mk2(-mx, -my);
+    f2 sum = mk2(0.0f, 0.0f);
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
-        ex[j] = knot_exp<MODE>(r_add(ex[j], -mx));
-        ey[j] = knot_exp<MODE>(r_add(ey[j], -my));
-        sx = r_add(sx, ex[j]); sy = r_add(sy, ey[j]);
+        e[j] = knot_exp2<MODE>(pk_add(e[j], negm));
+        sum = pk_add(sum, e[j]);
     }
     // sizes_j = 1e-3 + (1 - 1e-3*nb) * softmax_j   (rational_quadratic.py:46-47)
     const float c1 = (float)(1.0 - 1e-3 * (double)nb);   // Python double, cast once (rational_quadratic.py:47)
-    const float gx = r_mul(c1, knot_rcp<MODE>(sx)), gy = r_mul(c1, knot_rcp<MODE>(sy));
+    const f2 g = mk2(r_mul(c1, knot_rcp<MODE>(sum.x)), r_mul(c1, knot_rcp<MODE>(sum.y)));
     const float span = r_add(hi, -lo);
-    float cx = 0.0f, cy = 0.0f;
+    const f2 span2 = mk2(span, span), lo2 = mk2(lo, lo), minb2 = mk2(kRqMinBin, kRqMinBin);
+    f2 c = mk2(0.0f, 0.0f);
     bool prev_below = true;                         // knot_0 = lo < v always (strict in-bounds test)
     s.xk = lo; s.yk = lo; s.xk1 = hi; s.yk1 = hi; s.ud0 = kRqEdgeU; s.ud1 = kRqEdgeU; s.k = 0;
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
         // cumsum, then (hi-lo)*c + lo as two rounded steps, ends pinned (rational_quadratic.py:48-52)
-        cx = r_add(cx, r_fma(ex[j], gx, kRqMinBin));
-        cy = r_add(cy, r_fma(ey[j], gy, kRqMinBin));
+        c = pk_add(c, pk_fma(e[j], g, minb2));
         const bool last = (j == nb - 1);
-        const float kx = last ? hi : r_add(r_mul(span, cx), lo);    // knot_{j+1}
-        const float ky = last ? hi : r_add(r_mul(span, cy), lo);
+        const f2 kn = pk_add(pk_mul(span2, c), lo2);
+        const float kx = last ? hi : kn.x;                           // knot_{j+1}
+        const float ky = last ? hi : kn.y;
         const float ud = last ? kRqEdgeU : h(2 * nb + j);           // derivative logit of knot_{j+1}
         // searchsorted(right=False) - 1  ==  #{knots < v} - 1      (rational_quadratic.py:82)
         const bool below = (INV ? ky : kx) < v;
