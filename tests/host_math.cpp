@@ -48,6 +48,17 @@ void hm_rq_backward(const float* x, const float* h, const float* gz, const float
     }
 }
 
+void hm_rq_backward_inv(const float* z, const float* h, const float* gx, const float* gl, float* dz, float* dh, int64_t n,
+                        int nb, float b) {
+    const int P = 3 * nb - 1;
+    for (int64_t i = 0; i < n; ++i) {
+        HPtr hp{h + i * P};
+        GPtr gp{dh + i * P};
+        if (nb == 8) rq_backward_inv<8, 0>(z[i], hp, nb, b, gx[i], gl[i], dz[i], gp);
+        else rq_backward_inv<0, 0>(z[i], hp, nb, b, gx[i], gl[i], dz[i], gp);
+    }
+}
+
 void hm_affine(const float* x, const float* h, float* out, float* ld, int64_t n, int inverse) {
     for (int64_t i = 0; i < n; ++i) {
         if (inverse) affine_inv<0>(x[i], h[2 * i], h[2 * i + 1], out[i], ld[i]);

@@ -50,6 +50,14 @@ def rq_backward(x, h, gz, gl, n_bins, boundary):
     return torch.from_numpy(dv), torch.from_numpy(dh)
 
 
+def rq_backward_inv(z, h, gx, gl, n_bins, boundary):
+    zs, hs, gxs, gls = _np(z), _np(h), _np(gx), _np(gl)
+    dz, dh = np.empty_like(zs), np.empty_like(hs)
+    lib().hm_rq_backward_inv(_p(zs), _p(hs), _p(gxs), _p(gls), _p(dz), _p(dh), ctypes.c_int64(zs.size),
+                             ctypes.c_int(n_bins), ctypes.c_float(boundary))
+    return torch.from_numpy(dz), torch.from_numpy(dh)
+
+
 def affine(x, h, inverse):
     xs, hs = _np(x), _np(h)
     out, ld = np.empty_like(xs), np.empty_like(xs)

@@ -138,3 +138,31 @@ def test_hostmath_affine_backward_vs_autograd(inverse):
     dx, dh = hostmath.affine_backward(x, h, gz, gl, inverse)
     assert (dx.double() - xd.grad).norm() / xd.grad.norm() < 1e-5
     assert (dh.double() - hd.grad).norm() / hd.grad.norm() < 1e-5
+
+
+@pytest.mark.parametrize('n_bins', [8, 4])
+def test_hostmath_rq_inverse_backward_vs_autograd(n_bins):
+    """Backward of the inverse-direction spline (implicit function theorem) against autograd through
+    the oracle's rq_inverse."""
+    g = torch.Generator().manual_seed(21)
+    n = 4096
+    z = torch.randn(n, generator=g) * 3
+    z[:3] = torch.tensor([60.0, -70.0, 0.0])
+    h = torch.randn(n, 3 * n_bins - 1, generator=g)
+    gx, gl = torch.randn(n, generator=g), torch.randn(n, generator=g)
+
+    def autograd(dt):
+        zd, hd = z.to(dt).requires_grad_(True), h.to(dt).requires_grad_(True)
+        x, ld = fo.rq_inverse(zd[:, None], hd[:, None, :], n_bins=n_bins, boundary=50.0)
+        (x[:, 0] * gx.to(dt)).sum().add((ld * gl.to(dt)).sum()).backward()
+        return zd.grad.double(), hd.grad.double()
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm()).item()
+
+    z64, h64 = autograd(torch.float64)
+    z32, h32 = autograd(torch.float32)
+    dz, dh = hostmath.rq_backward_inv(z, h, gx, gl, n_bins, 50.0)
+    assert rel(dz.double(), z64) <= 3 * rel(z32, z64) + 1e-5
+    assert rel(dh.double(), h64) <= 3 * rel(h32, h64) + 1e-5
+    assert dz[0] == gx[0] and (dh[:2] == 0).all()

@@ -217,7 +217,8 @@ class FlowFunction(torch.autograd.Function):
             raise NotImplementedError('backward through the sequential direction of a masked autoregressive layer '
                                       '(IAF density / MAF sampling gradients) is not part of the fused hot path yet')
         if cfg.flags & N.FLOW_LOGP_OF_INPUT:
-            raise NotImplementedError('backward of Flow.sample(return_log_prob=True) is not fused yet')
+            raise NotImplementedError('the fused LOGP_OF_INPUT variant is inference-only; with gradients Flow.sample '
+                                      'evaluates the base density separately')
         dev = x2.device
         grads, leaf_grads = [], []
         for op in ops:

@@ -68,7 +68,9 @@ __device__ __forceinline__ void transformer_backward_element(float v, const floa
         auto g = [&](int i, float val) { dh[i] = val; };
         rq_backward_fwd<8, MODE>(v, h, 8, boundary, GZ, GL, dv, g);
     } else {
-        dv = 0.0f;   // RQ_INV backward is rejected on the host
+        auto h = [&](int i) { return acc[i]; };
+        auto g = [&](int i, float val) { dh[i] = val; };
+        rq_backward_inv<8, MODE>(v, h, 8, boundary, GZ, GL, dv, g);
     }
 }
 
@@ -132,6 +134,7 @@ __device__ __forceinline__ void run_transform_backward(const BTile& b, const Bwd
         case B2F_T_AFFINE_FWD: transform_pass_backward<B2F_T_AFFINE_FWD, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_AFFINE_INV: transform_pass_backward<B2F_T_AFFINE_INV, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_RQ_FWD: transform_pass_backward<B2F_T_RQ_FWD, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_RQ_INV: transform_pass_backward<B2F_T_RQ_INV, MODE>(b, op, t0, n_tgt); break;
         default: break;
     }
 }
@@ -144,6 +147,7 @@ __device__ __forceinline__ void run_transform_forward(const Tile& t, const DevOp
         case B2F_T_AFFINE_FWD: transform_pass<B2F_T_AFFINE_FWD, MODE>(t, op, t0, n_tgt); break;
         case B2F_T_AFFINE_INV: transform_pass<B2F_T_AFFINE_INV, MODE>(t, op, t0, n_tgt); break;
         case B2F_T_RQ_FWD: transform_pass<B2F_T_RQ_FWD, MODE>(t, op, t0, n_tgt); break;
+        case B2F_T_RQ_INV: transform_pass<B2F_T_RQ_INV, MODE>(t, op, t0, n_tgt); break;
         default: break;
     }
 }
@@ -345,9 +349,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
             case B2F_OP_COUPLING: case B2F_OP_MADE: {
                 if (!o.p[0] || !o.p[1] || !o.p[2] || !o.p[3] || o.n_hidden <= 0)
                     return fail(B2F_ERR_INVALID, "op %d: conditioner parameters missing", i);
-                if (o.tkind == B2F_T_RQ_INV)
-                    return fail(B2F_ERR_UNSUPPORTED, "op %d: backward of the inverse-direction spline is not fused", i);
-                if (o.tkind == B2F_T_RQ_FWD && o.n_bins != 8)
+                if ((o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV) && o.n_bins != 8)
                     return fail(B2F_ERR_UNSUPPORTED, "op %d: fused RQ spline needs n_bins == 8", i);
                 const bool any_g = o.g[0] || o.g[1] || o.g[2] || o.g[3];
                 if (any_g && !(o.g[0] && o.g[1] && o.g[2] && o.g[3]))

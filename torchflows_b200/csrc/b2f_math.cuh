@@ -432,6 +432,41 @@ B2F_HD void rq_backward_fwd(float v, const H& h, int nb_rt, float boundary, floa
     }
 }
 
+// ---- backward of the inverse-direction spline (implicit function theorem) ------------------------
+// x = f^{-1}(z; h), ld_inv = -ld_f(x; h).  With upstream GX = dL/dx and GL = dL/dld_inv, f' = d f / d x and
+// l_v = d ld_f / d x evaluated at the recovered x (ld_inv = -ld_f):  Gtot = GX - GL*l_v, dL/dz = Gtot / f'; the
+// parameter gradients are the forward-direction expressions evaluated at x with
+// (GZ, GL_f) := (-Gtot / f', -GL).
+template <int NB, int MODE, class H, class G>
+B2F_HD void rq_backward_inv(float z, const H& h, int nb_rt, float boundary, float GX, float GL, float& dz, const G& gout) {
+    const int nb = NB > 0 ? NB : nb_rt;
+    if (!(z > -boundary && z < boundary)) {
+        dz = GX;
+#pragma unroll
+        for (int i = 0; i < 3 * nb - 1; ++i) gout(i, 0.0f);
+        return;
+    }
+    float x, ldi; int k;
+    rq_apply<NB, true, 0>(z, h, nb, boundary, x, ldi, k);
+    if (!(x > -boundary && x < boundary)) {           // rounding pushed x onto the boundary: identity tail
+        dz = GX;
+#pragma unroll
+        for (int i = 0; i < 3 * nb - 1; ++i) gout(i, 0.0f);
+        return;
+    }
+    RqSel s; RqEval e; float out, ldf;
+    rq_select<NB, false, 0>(x, h, nb, -boundary, boundary, s);
+    rq_eval_fwd<0>(x, s, out, ldf, e);
+    const float iDn = 1.0f / e.den, iM = 1.0f / e.M, iw = 1.0f / e.w, om = 1.0f - e.xi;
+    const float fprime = e.hgt * e.s * e.M * iDn * iDn * iw;
+    const float ld_xi = (2.0f * e.d1 * e.xi + 2.0f * e.s * (1.0f - 2.0f * e.xi) - 2.0f * e.d0 * om) * iM
+                        - 2.0f * e.t1 * (1.0f - 2.0f * e.xi) * iDn;
+    const float Gtot = GX - GL * ld_xi * iw;
+    dz = Gtot / fprime;
+    float dv_unused;
+    rq_backward_fwd<NB, MODE>(x, h, nb, boundary, -dz, -GL, dv_unused, gout);
+}
+
 // ---- backward of Affine forward / inverse and Shift (Appendix D, last paragraph) ------------------------------
 template <int MODE>
 B2F_HD void affine_fwd_backward(float x, float u0, float GZ, float GL, float& dx, float& du0, float& du1) {

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) transformer_backward_kernel(
     else if constexpr (TK == B2F_T_AFFINE_FWD) affine_fwd_backward<MODE>(v, __ldg(he), GZ, GL, dv, ge[0], ge[1]);
     else if constexpr (TK == B2F_T_AFFINE_INV) affine_inv_backward<MODE>(v, __ldg(he), __ldg(he + 1), GZ, GL, dv, ge[0], ge[1]);
     else if constexpr (TK == B2F_T_RQ_FWD) rq_backward_fwd<NB, MODE>(v, HGlobal{he}, nb, boundary, GZ, GL, dv, GGlobal{ge});
+    else rq_backward_inv<NB, MODE>(v, HGlobal{he}, nb, boundary, GZ, GL, dv, GGlobal{ge});
     gx[idx] = dv;
 }
 
@@ -174,9 +175,7 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
     if (n_rows == 0 && n_event > 0) return B2F_OK;
     if (!x || !h || !gx || !gh || n_rows < 0 || n_event <= 0 || h_row_stride < 0)
         return fail(B2F_ERR_INVALID, "b2f_transformer_backward: bad arguments");
-    if (tkind == B2F_T_RQ_INV)
-        return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_backward: inverse-direction spline backward is not fused");
-    if (tkind == B2F_T_RQ_FWD && (n_bins < 1 || n_bins > kRqMaxBins || !(boundary > 0.0f)))
+    if ((tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV) && (n_bins < 1 || n_bins > kRqMaxBins || !(boundary > 0.0f)))
         return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_backward: n_bins=%d", n_bins);
     if (n_rows == 0) return B2F_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -189,6 +188,7 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
         B2F_DISPATCH(B2F_T_AFFINE_FWD)
         B2F_DISPATCH(B2F_T_AFFINE_INV)
         B2F_DISPATCH(B2F_T_RQ_FWD)
+        B2F_DISPATCH(B2F_T_RQ_INV)
     }
 #undef B2F_DISPATCH
     return fail(B2F_ERR_INVALID, "b2f_transformer_backward: unknown transformer kind %d", tkind);

@@ -262,12 +262,124 @@ class BaseFlow(nn.Module):
         self._optimizer.step()
         return loss_value
 
-    def variational_fit(self, *args, **kwargs):
-        raise NotImplementedError('variational_fit (gradients through the sampling direction) is listed as the next '
-                                  'step after the maximum-likelihood hot path (SURVEY section 8f-2)')
+    # -- KL(p || q) and stochastic variational inference (flows.py:81-197, 457-603) --------------------------------
+    def _loss_kl_p_to_q(self, data: torch.Tensor, log_prob_target_data: torch.Tensor, use_regularization: bool = True):
+        """mean(log p(x) - log q(x)) + regularization   (flows.py:81-94)."""
+        dev = self.get_device()
+        loss = torch.mean(log_prob_target_data.to(dev) - self.log_prob(data.to(dev)))
+        if use_regularization:
+            loss = loss + self.regularization()
+        return loss
 
-    def fit_kl_p_to_q(self, *args, **kwargs):
-        raise NotImplementedError('fit_kl_p_to_q is outside the B200 hot path of this round (SURVEY section 8f-2)')
+    def fit_kl_p_to_q(self, x_train: torch.Tensor, x_val: torch.Tensor, neg_log_prob_target: callable,
+                      n_epochs: int = 500, lr: float = 0.05, batch_size: int = 1024, show_progress: bool = False,
+                      keep_best_weights: bool = True, early_stopping: bool = False, early_stopping_threshold: int = 50,
+                      time_limit_seconds: float = None, reset_optimizer: bool = True):
+        """Fit by minimising KL(p || q) on samples of p with known (negative) log density (flows.py:96-197): batches in
+        the given order, validation loss summed over the validation batches, best weights by validation loss."""
+        lp_train = -neg_log_prob_target(x_train).detach()
+        lp_val = -neg_log_prob_target(x_val).detach()
+        if len(list(self.parameters())) == 0:
+            return
+        self.train()
+        t0 = time.time()
+        if self._optimizer is None or reset_optimizer:
+            self._optimizer = torch.optim.AdamW(self.parameters(), lr=lr)
+        val_loss, best_val_loss, best_epoch = None, float('inf'), 0
+        best_weights = deepcopy(self.state_dict())
+        for epoch in (pbar := tqdm(range(n_epochs), desc='Fitting NF', disable=not show_progress)):
+            if time_limit_seconds is not None and time.time() - t0 >= time_limit_seconds:
+                print('Training time limit exceeded')
+                break
+            for s0 in range(0, len(x_train), batch_size):
+                self._optimizer.zero_grad()
+                loss = self._loss_kl_p_to_q(x_train[s0:s0 + batch_size], lp_train[s0:s0 + batch_size])
+                loss.backward()
+                self._optimizer.step()
+                if show_progress:
+                    pbar.set_postfix_str(f'Training loss (batch): {float(loss):.4f}')
+            with torch.no_grad():
+                val_loss = 0.0
+                for s0 in range(0, len(x_val), batch_size):
+                    val_loss += float(self._loss_kl_p_to_q(x_val[s0:s0 + batch_size], lp_val[s0:s0 + batch_size],
+                                                           use_regularization=False))
+            if val_loss < best_val_loss:
+                best_val_loss, best_epoch = val_loss, epoch
+            if keep_best_weights and best_epoch == epoch:
+                best_weights = deepcopy(self.state_dict())
+            if early_stopping and epoch - best_epoch > early_stopping_threshold:
+                break
+        if keep_best_weights:
+            self.load_state_dict(best_weights)
+        self.eval()
+
+    def _variational_loss(self, target_log_prob: callable, n_samples: int, use_regularization: bool = True,
+                          check_for_divergences: bool = False):
+        """-mean(log p(x) + flow_log_prob) over x ~ flow, where flow_log_prob is what sample(return_log_prob=True)
+        returns (flows.py:457-493, incl. the reference's sign convention)."""
+        flow_x, flow_log_prob = self.sample(n_samples, return_log_prob=True)
+        target_value = target_log_prob(flow_x)
+        loss = -torch.mean(target_value + flow_log_prob)
+        if use_regularization:
+            loss = loss + self.regularization()
+        diverged = False
+        if check_for_divergences:
+            diverged = bool((~torch.isfinite(loss)) | (flow_x.abs().max() > 1e8) | (flow_log_prob.abs().max() > 1e6)
+                            | (~torch.isfinite(flow_x)).any() | (~torch.isfinite(flow_log_prob)).any())
+        return loss, flow_log_prob, target_value, diverged
+
+    def variational_fit(self, target_log_prob: callable, n_epochs: int = 500, lr: float = 0.05, n_samples: int = 1,
+                        early_stopping: bool = False, early_stopping_threshold: int = 50,
+                        keep_best_weights: bool = True, show_progress: bool = False,
+                        check_for_divergences: bool = False, time_limit_seconds: Union[float, int] = None,
+                        reset_optimizer: bool = True):
+        """Stochastic variational inference (flows.py:495-603): one reparameterised sample batch per epoch, divergent
+        epochs are skipped, non-finite parameters revert to the initial weights, best weights by training loss.
+        Gradients flow through the sampling direction: coupling layers (incl. the inverse spline) and
+        one-pass MADE layers (IAF) are fused; the sequential MADE direction (MAF sampling) has no fused backward."""
+        t0 = time.time()
+        if len(list(self.parameters())) == 0:
+            return
+        self.train()
+        if self._optimizer is None or reset_optimizer:
+            self._optimizer = torch.optim.AdamW(self.parameters(), lr=lr)
+        best_loss, best_epoch, n_divergences, reverted = float('inf'), 0, 0, False
+        initial_weights = deepcopy(self.state_dict())
+        best_weights = deepcopy(self.state_dict())
+        for epoch in (pbar := tqdm(range(n_epochs), desc='Fitting with SVI', disable=not show_progress)):
+            if time_limit_seconds is not None and time.time() - t0 >= time_limit_seconds:
+                print('Training time limit exceeded')
+                break
+            if check_for_divergences and not all(bool(torch.isfinite(p).all()) for p in self.parameters()):
+                print('Flow training diverged')
+                print('Reverting to initial weights')
+                reverted = True
+                break
+            self._optimizer.zero_grad()
+            loss_value = float('nan')
+            try:
+                loss, flow_lp, target_lp, diverged = self._variational_loss(target_log_prob, n_samples, True, True)
+                if not diverged:
+                    loss.backward()
+                    self._optimizer.step()
+                    loss_value = float(loss.detach())
+                    if loss_value < best_loss:
+                        best_loss, best_epoch = loss_value, epoch
+                        if keep_best_weights:
+                            best_weights = deepcopy(self.state_dict())
+            except ValueError:
+                diverged = True
+            n_divergences += int(diverged)
+            if show_progress:
+                pbar.set_postfix_str(f'Loss: {loss_value:.4f} [best: {best_loss:.4f} @ {best_epoch}], '
+                                     f'divergences: {n_divergences}')
+            if early_stopping and epoch - best_epoch > early_stopping_threshold:
+                break
+        if reverted:
+            self.load_state_dict(initial_weights)
+        elif keep_best_weights:
+            self.load_state_dict(best_weights)
+        self.eval()
 
 
 class Flow(BaseFlow):
