@@ -115,6 +115,21 @@ class CouplingBijection(AutoregressiveBijection):
                                leafs=[seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias],
                                n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, owner=self)]
 
+    #: composite path only: run the conditioner's library GEMMs on the tensor cores in TF32 for spline layers (the same
+    #: precision the fused tcgen05 kernel uses; affine / shift layers always stay in fp32)
+    composite_tf32: bool = True
+
+    def _conditioner_gemms(self, xa, context):
+        use_tf32 = self.composite_tf32 and isinstance(self.transformer, RationalQuadratic) and xa.is_cuda
+        if not use_tf32:
+            return self.conditioner_transform(xa, context=context)
+        previous = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return self.conditioner_transform(xa, context=context)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = previous
+
     def _composite(self, x: torch.Tensor, context, direction: str):
         """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""
         batch_shape = get_batch_shape(x, self.event_shape)
@@ -123,7 +138,7 @@ class CouplingBijection(AutoregressiveBijection):
         if isinstance(self.coupling, HalfSplit):
             ds = self.n_dim // 2
             xa, xb = xf[..., :ds], xf[..., ds:]
-            h = self.conditioner_transform(xa, context=context).view(*batch_shape, *self.transformer.parameter_shape)
+            h = self._conditioner_gemms(xa, context).view(*batch_shape, *self.transformer.parameter_shape)
             yb, log_det = fn(xb.contiguous(), h)
             out = torch.cat([xa, yb.reshape(*batch_shape, -1)], dim=-1)
         else:
