@@ -188,8 +188,6 @@ def run_ours(args):
         total_ms = ev[0].elapsed_time(ev[3 * args.steps])
         lp_ms = [ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)]
         s_ms = [ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]
-        sampler.stop_flag = True
-        sampler.join(timeout=3)
         del xs
         # opt-in 'fast' arithmetic mode (SFU exponentials for the spline knots), reported beside the default
         import torchflows_b200
@@ -260,6 +258,8 @@ def run_ours(args):
         t1.record(stream)
         sync_all()
         e2e_ms = t0.elapsed_time(t1) / e2e_steps
+        sampler.stop_flag = True           # clocks were sampled across the device-resident, fast-mode and e2e regions
+        sampler.join(timeout=3)
 
     # max over ranks
     times = torch.tensor([total_ms, e2e_ms, fast_ms], device=dev, dtype=torch.float64)
@@ -278,6 +278,13 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
     achieved = by_lp * B / (lp_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of the log_prob launch from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        if args.workload in tr and not args.rows:
+            traffic = tr[args.workload]['log_prob_launch_dram_bytes']
+    except Exception:
+        pass
 
     line = {
         'metric': 'log_prob+sample samples/s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
@@ -288,7 +295,7 @@ def run_ours(args):
                    'l2': f'inputs larger than L2 ({B * D * 4 >> 20} MiB per tensor)', 'precision_mode': 'default (SFU after bin search)'},
         'log_prob_samples_per_s': world * B / (lp_avg_ms * 1e-3), 'sample_samples_per_s': world * B / (s_avg_ms * 1e-3),
         'roofline': {'bound': 'hbm', 'kernel': 'b2f::flow_kernel (log_prob launch)', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
                      'peak_source': peak_src, 'algorithmic_bytes_per_row': by_lp, 'launch_ms': lp_avg_ms,
                      'sample_launch': {'achieved': by_s * B / (s_avg_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_row': by_s,
                                        'launch_ms': s_avg_ms}},
