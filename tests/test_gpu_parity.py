@@ -219,8 +219,8 @@ def test_context_presets_vs_golden(golden, dev, idx):
     close(lp, c['log_prob'], 'log_prob', LP_TOL, LP_TOL)
     close(xr, c['xr'], 'xr', za * 4, 1e-4)
     close(ldr, c['ld_r'], 'ld_r', 2 * LP_TOL, 2 * LP_TOL)
-    if c['preset'] in ('IAF', 'InverseAutoregressiveRQNSF'):
-        return           # density direction is the sequential one: no fused backward yet
+    if c['preset'] == 'InverseAutoregressiveRQNSF':
+        return           # spline + sequential density direction: fused gradient only for the exact log-det flag
     ne = len(c['event_shape'])
     xg = x.reshape(-1, *c['event_shape']).clone().requires_grad_(True)
     loss = flow._base_batch_loss((xg, torch.ones(len(xg), device=dev), ctx.reshape(-1, *c['context_shape'])))

@@ -204,7 +204,7 @@ def test_sampling_direction_gradients_vs_oracle_autograd(dev):
     from torchflows_b200 import Flow
     import torchflows_b200.architectures as arch
     for preset, D in (('RealNVP', 8), ('NICE', 6), ('CouplingRQNSF', 8), ('IAF', 6), ('CouplingRQNSF', 32),
-                      ('CouplingRQNSF', 3), ('RealNVP', 3), ('CouplingRQNSF', 5)):
+                      ('CouplingRQNSF', 3), ('RealNVP', 3), ('CouplingRQNSF', 5), ('MAF', 6), ('MAF', 33)):
         torch.manual_seed(5)
         flow = Flow(getattr(arch, preset)(D)).eval()
         sd = {k: v.clone().requires_grad_(v.is_floating_point() and ('weight' in k or 'bias' in k or 'value' in k))
@@ -252,5 +252,68 @@ def test_variational_fit_and_kl_fit(dev):
     flow = Flow(MAF(3)).to(dev)
     x = torch.randn(2000, 3) * sigma + mu.cpu()
     flow.fit_kl_p_to_q(x[:1500], x[1500:], lambda t: -target_log_prob(t.to(dev)).cpu(), n_epochs=5, lr=0.01)
+    torch.manual_seed(2)
+    flow = Flow(MAF(3)).to(dev)                 # MAF samples through the sequential direction: fused backward as well
+    flow.variational_fit(target_log_prob, n_epochs=400, lr=0.05, n_samples=256, check_for_divergences=True)
+    with torch.no_grad():
+        s = flow.sample(20000)
+    assert (s.mean(0) - mu).abs().max().item() < 0.25 and (s.std(0) - sigma).abs().max().item() < 0.25
+
+
+def test_sequential_direction_gradients(dev):
+    """Backward of the D-step sequential direction (IAF density, MAF / MA-RQNSF sampling) against torch autograd through
+    the CPU oracle's D-pass loop.  For the spline the fused gradient exists for the exact log-determinant
+    (sequential_log_det_reference_quirk = False); the oracle side builds that quantity from its own pieces."""
+    from oracle.flow_oracle import OracleFlow
+    from torchflows_b200 import Flow
+    import torchflows_b200.architectures as arch
+
+    def oracle_with_grads(preset, D, flow):
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and ('weight' in k or 'bias' in k or 'value' in k))
+              for k, v in flow.state_dict().items()}
+        o = OracleFlow(preset, (D,), {})
+        o.sd = sd
+        return o, sd
+
+    def compare(flow, sd, tol, what):
+        n = 0
+        for k, p in flow.named_parameters():
+            if p.grad is None or sd[k].grad is None or sd[k].grad.norm() == 0:
+                continue
+            assert rel(p.grad, sd[k].grad) < tol, (what, k, rel(p.grad, sd[k].grad))
+            n += 1
+        assert n >= 6, what
+
+    # IAF density = sequential direction in log_prob (what Flow.fit differentiates)
+    for D in (6, 17):
+        torch.manual_seed(3)
+        flow = Flow(arch.IAF(D)).eval()
+        o, sd = oracle_with_grads('IAF', D, flow)
+        x = torch.randn(50, D)
+        o.batch_loss(x).backward()
+        flow = flow.to(dev)
+        xg = x.to(dev).requires_grad_(True)
+        flow._base_batch_loss((xg, torch.ones(50, device=dev))).backward()
+        compare(flow, sd, 2e-4, f'IAF({D}) density')
+    # MA-RQNSF sampling with the exact log-det: x from the sequential inverse, log_det = -forward log-det at x
+    torch.manual_seed(4)
+    D = 5
+    flow = Flow(arch.MaskedAutoregressiveRQNSF(D)).eval()
+    for layer in flow.bijection.layers:
+        if hasattr(layer, 'sequential_log_det_reference_quirk'):
+            layer.sequential_log_det_reference_quirk = False
+    o, sd = oracle_with_grads('MaskedAutoregressiveRQNSF', D, flow)
+    noise = torch.randn(40, D)
+    xo, _ = o.inverse(noise)
+    _, ld_f = o.forward(xo)
+    (xo.pow(2).sum(-1).mean() + (o.base_log_prob(noise) - ld_f).mean()).backward()
+    flow = flow.to(dev)
+    x, lp = flow._sample_from_base(noise.to(dev), return_log_prob=True)
+    (x.pow(2).sum(-1).mean() + lp.mean()).backward()
+    assert rel(x, xo) < 1e-4
+    compare(flow, sd, 1e-2, 'MA-RQNSF sampling, exact log-det')
+    # and the default (reference quirk) refuses loudly instead of returning a wrong gradient
+    flow_q = Flow(arch.MaskedAutoregressiveRQNSF(D)).to(dev)
+    xq, lpq = flow_q._sample_from_base(noise.to(dev), return_log_prob=True)
     with pytest.raises(NotImplementedError):
-        Flow(MAF(3)).to(dev).variational_fit(target_log_prob, n_epochs=1)      # sequential direction: no fused backward
+        lpq.mean().backward()

@@ -213,9 +213,12 @@ class FlowFunction(torch.autograd.Function):
         cfg = ctx.cfg
         x2 = ctx.saved_tensors[0]
         ops = cfg.ops
-        if any(op.kind == N.OP_MADE_SEQ for op in ops):
-            raise NotImplementedError('backward through the sequential direction of a masked autoregressive layer '
-                                      '(IAF density / MAF sampling gradients) is not part of the fused hot path yet')
+        for op in ops:
+            if op.kind == N.OP_MADE_SEQ and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV) and not (op.flags & N.FLAG_SEQ_LOGDET_EXACT):
+                raise NotImplementedError(
+                    'gradients through the sequential direction of a spline MADE layer are implemented for the exact '
+                    'log-determinant only: set layer.sequential_log_det_reference_quirk = False (the reference returns '
+                    'the log-det of its last iteration, SURVEY Appendix B.3)')
         if cfg.flags & N.FLOW_LOGP_OF_INPUT:
             raise NotImplementedError('the fused LOGP_OF_INPUT variant is inference-only; with gradients Flow.sample '
                                       'evaluates the base density separately')
@@ -227,9 +230,9 @@ class FlowFunction(torch.autograd.Function):
             if op.kind == N.OP_ELEMENTWISE:
                 if op.leafs[0].requires_grad:
                     g[0] = torch.zeros_like(kp[0])
-            elif op.kind in (N.OP_COUPLING, N.OP_MADE):
+            elif op.kind in (N.OP_COUPLING, N.OP_MADE, N.OP_MADE_SEQ):
                 if any(t.requires_grad for t in op.leafs):
-                    g = [torch.zeros_like(t) for t in kp[:4]]
+                    g = [torch.zeros_like(t) for t in kp[:4]] + [None] * (len(kp) - 4)
             grads.append(g)
         B, D = x2.shape
         arr = N.make_ops(op_dicts(ops, grads))
@@ -248,14 +251,14 @@ class FlowFunction(torch.autograd.Function):
         for op, g in zip(ops, grads):
             if op.kind == N.OP_ELEMENTWISE:
                 leaf_grads.append(None if g[0] is None else g[0].reshape(op.leafs[0].shape))
-            elif op.kind in (N.OP_COUPLING, N.OP_MADE):
+            elif op.kind in (N.OP_COUPLING, N.OP_MADE, N.OP_MADE_SEQ):
                 if g[0] is None:
                     leaf_grads.extend([None] * 4)
                     continue
                 P = params_per_element(op.tkind, op.n_bins)
                 n_elem = op.leafs[2].shape[0] // P
                 gW1, gb1, gW2, gb2 = g[0], g[1], from_tile_layout(g[2], n_elem, P), g[3]
-                if op.kind == N.OP_MADE:
+                if op.kind in (N.OP_MADE, N.OP_MADE_SEQ):
                     gW1, gW2 = gW1 * op.consts[0], gW2 * op.consts[1]
                 leaf_grads.extend([gW1, gb1, gW2, gb2])
         return (gx if need_gx else None, None, *leaf_grads)

@@ -126,6 +126,77 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
     }
 }
 
+// Backward of the D-step sequential direction x_i = T(z_i; h_i(x_0..x_{i-1})) (layers_base.py:213-223).  A thread owns
+// a sample.  With act_j = tanh(pre_j(x)) recomputed from the complete x, walk i = D-1..0:
+//   dL/dx_i (total) = upstream + sum_j W1m[j][i] * dpre_j      (hidden units that read x_i are final: fin_j > i)
+//   (dL/dz_i, dL/dh_i) = transformer backward at (z_i, h_i);   dact_j += sum_p dh_i[p] * W2m[i][j][p]
+// and dact_j becomes dpre_j = dact_j (1 - act_j^2) once every output that reads unit j has been processed (i + 1 ==
+// fin_j).  Weight gradients of the output layer use the same per-warp staged product as the one-pass layers.
+template <int TK, int MODE>
+__device__ __forceinline__ void sequential_pass_backward(const BTile& b, const BwdOp& op, const float* __restrict__ z_saved) {
+    constexpr int P = TInfo<TK>::P, PP = TInfo<TK>::PP;
+    const Tile& t = b.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % t.G, slot = warp / t.G;
+    if (slot != 0) return;
+    const int m = g * 32 + lane, H = op.f.H, D = t.D;
+    float* act = t.hid + m * t.HS;
+    float* dact = b.dhid + m * t.HS;
+    const float* hid_g = t.hid + (g * 32) * t.HS;
+    float* xr = t.xt + m * t.XS;
+    float* gr = b.gt + m * t.XS;
+    float* dhs = b.dhs + warp * 32 * PP;
+    const bool live = m < b.rows;
+    const float GLm = b.GL[m];
+    const bool want_w = op.g2 != nullptr;
+    for (int j = 0; j < H; ++j) {
+        const float* w = op.f.p0 + (size_t)j * D;
+        float a = __ldg(op.f.p1 + j);
+        for (int k = 0; k < D; ++k) a = fmaf(__ldg(w + k), xr[t.col(k)], a);
+        act[j] = tanhf(a);
+        dact[j] = 0.0f;
+    }
+    for (int i = D - 1; i >= 0; --i) {
+        for (int j = 0; j < H; ++j)
+            if (__ldg(op.f.p4 + j) == i + 1) dact[j] *= (1.0f - act[j] * act[j]);
+        const int c = t.col(i);
+        float gx = gr[c];
+        for (int j = 0; j < H; ++j) gx = fmaf(__ldg(op.f.p0 + (size_t)j * D + i), dact[j], gx);
+        const float* w2e = op.f.p2 + (size_t)i * H * PP;
+        float acc[PP], dh[PP];
+        element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)i * P, act, H);
+        const float zi = live ? __ldg(z_saved + (size_t)m * D + c) : 0.0f;
+        float dv;
+        transformer_backward_element<TK, MODE, P, PP>(zi, acc, op.f.boundary, gx, GLm, dv, dh);
+        gr[c] = dv;
+        for (int j = 0; j < H; ++j) {
+            float sacc = 0.0f;
+#pragma unroll
+            for (int p = 0; p < P; ++p) sacc = fmaf(dh[p], __ldg(w2e + j * PP + p), sacc);
+            dact[j] += sacc;
+        }
+        if (want_w) {
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < PP; ++p) dhs[lane * PP + p] = dh[p];
+            __syncwarp();
+            for (int idx = lane; idx < H * PP; idx += 32) {
+                const int j = idx / PP, p = idx - j * PP;
+                if (p < P) {
+                    float sacc = 0.0f;
+                    for (int mm = 0; mm < 32; ++mm) sacc = fmaf(dhs[mm * PP + p], hid_g[mm * t.HS + j], sacc);
+                    atomicAdd(op.g2 + ((size_t)i * H + j) * PP + p, sacc);
+                }
+            }
+            if (lane < P) {
+                float sacc = 0.0f;
+                for (int mm = 0; mm < 32; ++mm) sacc += dhs[mm * PP + lane];
+                atomicAdd(op.g3 + (size_t)i * P + lane, sacc);
+            }
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void run_transform_backward(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
     switch (op.f.tkind) {
@@ -135,6 +206,30 @@ __device__ __forceinline__ void run_transform_backward(const BTile& b, const Bwd
         case B2F_T_AFFINE_INV: transform_pass_backward<B2F_T_AFFINE_INV, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_RQ_FWD: transform_pass_backward<B2F_T_RQ_FWD, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_RQ_INV: transform_pass_backward<B2F_T_RQ_INV, MODE>(b, op, t0, n_tgt); break;
+        default: break;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void run_sequential_backward(const BTile& b, const BwdOp& op, const float* z_saved) {
+    switch (op.f.tkind) {
+        case B2F_T_SHIFT_ADD: sequential_pass_backward<B2F_T_SHIFT_ADD, MODE>(b, op, z_saved); break;
+        case B2F_T_SHIFT_SUB: sequential_pass_backward<B2F_T_SHIFT_SUB, MODE>(b, op, z_saved); break;
+        case B2F_T_AFFINE_FWD: sequential_pass_backward<B2F_T_AFFINE_FWD, MODE>(b, op, z_saved); break;
+        case B2F_T_AFFINE_INV: sequential_pass_backward<B2F_T_AFFINE_INV, MODE>(b, op, z_saved); break;
+        case B2F_T_RQ_INV: sequential_pass_backward<B2F_T_RQ_INV, MODE>(b, op, z_saved); break;
+        default: break;
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void run_sequential_forward(const Tile& t, const DevOp& op) {
+    switch (op.tkind) {
+        case B2F_T_SHIFT_ADD: sequential_pass<B2F_T_SHIFT_ADD, MODE>(t, op); break;
+        case B2F_T_SHIFT_SUB: sequential_pass<B2F_T_SHIFT_SUB, MODE>(t, op); break;
+        case B2F_T_AFFINE_FWD: sequential_pass<B2F_T_AFFINE_FWD, MODE>(t, op); break;
+        case B2F_T_AFFINE_INV: sequential_pass<B2F_T_AFFINE_INV, MODE>(t, op); break;
+        case B2F_T_RQ_INV: sequential_pass<B2F_T_RQ_INV, MODE>(t, op); break;
         default: break;
     }
 }
@@ -164,7 +259,7 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
     b.gt = t.xt + TM * XS;
     t.hid = b.gt + TM * XS;
     b.dhid = t.hid + TM * HS;
-    t.act = nullptr;
+    t.act = b.dhid;                        // scratch of the sequential forward recompute (dhid is idle in phase A)
     t.ldp = b.dhid + TM * HS;              // [WPG][TM] (written by the forward recompute, unused)
     b.GL = t.ldp + A.WPG * TM;             // [TM]
     float* ea = b.GL + TM;                 // [3*D]
@@ -193,6 +288,12 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         float* save = A.ws + op.ws_off + row0 * D;
         for (int m = warp; m < rows; m += NW)
             for (int j = lane; j < D; j += 32) save[(size_t)m * D + j] = t.xt[m * XS + j];   // physical layout
+        if (op.f.kind == B2F_OP_MADE_SEQ) {
+            __syncthreads();
+            run_sequential_forward<MODE>(t, op.f);
+            __syncthreads();
+            continue;
+        }
         const bool coupling = op.f.kind == B2F_OP_COUPLING;
         const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0;
         hidden_layer<true>(t, op.f, n_src);
@@ -256,8 +357,33 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
             __syncthreads();
             continue;
         }
-        // conditioner layer: reload its input, recompute hidden activations
         const float* saved = A.ws + op.ws_off + row0 * D;
+        if (op.f.kind == B2F_OP_MADE_SEQ) {
+            // xt holds this layer's OUTPUT x (later layers were un-done); its input z is in the workspace
+            run_sequential_backward<MODE>(b, op, saved);
+            __syncthreads();
+            const int H = op.f.H;
+            if (op.g0) {
+                for (int idx = tid; idx < H * D; idx += NT) {
+                    const int j = idx / D, k = idx - j * D;
+                    const int c = t.col(k);
+                    float sacc = 0.0f;
+                    for (int m = 0; m < TM; ++m) sacc = fmaf(b.dhid[m * HS + j], t.xt[m * XS + c], sacc);
+                    atomicAdd(op.g0 + idx, sacc);
+                }
+                for (int j = tid; j < H; j += NT) {
+                    float sacc = 0.0f;
+                    for (int m = 0; m < TM; ++m) sacc += b.dhid[m * HS + j];
+                    atomicAdd(op.g1 + j, sacc);
+                }
+            }
+            __syncthreads();
+            for (int m = warp; m < TM; m += NW)
+                for (int j = lane; j < D; j += 32) t.xt[m * XS + j] = (m < rows) ? saved[(size_t)m * D + j] : 0.0f;
+            __syncthreads();
+            continue;
+        }
+        // conditioner layer: reload its input, recompute hidden activations
         for (int m = warp; m < TM; m += NW)
             for (int j = lane; j < D; j += 32) t.xt[m * XS + j] = (m < rows) ? saved[(size_t)m * D + j] : 0.0f;
         for (int i = tid; i < TM * HS; i += NT) b.dhid[i] = 0.0f;
@@ -315,7 +441,7 @@ using namespace b2f;
 extern "C" int64_t b2f_flow_backward_workspace(const b2f_op_t* ops, int32_t n_ops, int64_t B, int32_t D) {
     int64_t n = 0;
     for (int i = 0; i < n_ops; ++i)
-        if (ops[i].kind == B2F_OP_COUPLING || ops[i].kind == B2F_OP_MADE) ++n;
+        if (ops[i].kind == B2F_OP_COUPLING || ops[i].kind == B2F_OP_MADE || ops[i].kind == B2F_OP_MADE_SEQ) ++n;
     return n * B * (int64_t)D * (int64_t)sizeof(float);
 }
 
@@ -360,8 +486,25 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
                 Hmax = std::max(Hmax, o.n_hidden);
                 break;
             }
-            case B2F_OP_MADE_SEQ:
-                return fail(B2F_ERR_UNSUPPORTED, "op %d: backward through the sequential direction is not fused", i);
+            case B2F_OP_MADE_SEQ: {
+                if (!o.p[0] || !o.p[1] || !o.p[2] || !o.p[3] || !o.p[4] || o.n_hidden <= 0)
+                    return fail(B2F_ERR_INVALID, "op %d: conditioner parameters missing", i);
+                const bool rq = o.tkind == B2F_T_RQ_INV || o.tkind == B2F_T_RQ_FWD;
+                if (o.tkind == B2F_T_RQ_FWD) return fail(B2F_ERR_UNSUPPORTED, "op %d: sequential forward spline", i);
+                if (rq && (o.n_bins != 8 || !(o.flags & B2F_FLAG_SEQ_LOGDET_EXACT)))
+                    return fail(B2F_ERR_UNSUPPORTED,
+                                "op %d: the backward of a sequential spline layer needs B2F_FLAG_SEQ_LOGDET_EXACT (the "
+                                "reference's last-iteration log-det has no fused gradient) and n_bins == 8", i);
+                const bool any_g = o.g[0] || o.g[1] || o.g[2] || o.g[3];
+                if (any_g && !(o.g[0] && o.g[1] && o.g[2] && o.g[3]))
+                    return fail(B2F_ERR_INVALID, "op %d: give all four gradient buffers or none", i);
+                if (!workspace) return fail(B2F_ERR_INVALID, "b2f_flow_backward: workspace missing");
+                d.f.p4 = (const int*)o.p[4];
+                d.ws_off = off;
+                off += B * (long long)D;
+                Hmax = std::max(Hmax, o.n_hidden);
+                break;
+            }
             default: return fail(B2F_ERR_INVALID, "op %d: unknown kind %d", i, o.kind);
         }
     }

@@ -134,6 +134,45 @@ __device__ __forceinline__ void transform_pass(const Tile& t, const DevOp& op, i
     }
 }
 
+// D-step sequential direction of a masked autoregressive layer (layers_base.py:213-223) at the cost of ONE
+// conditioner pass: hidden pre-activations are updated incrementally (rank-1 update per finished dimension)
+// and only the P parameters of dimension i are evaluated at step i.  A thread owns a sample for all D steps.
+template <int TK, int MODE>
+__device__ __forceinline__ void sequential_pass(const Tile& t, const DevOp& op) {
+    constexpr int P = TInfo<TK>::P, PP = TInfo<TK>::PP;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % t.G, slot = warp / t.G;
+    if (slot != 0) return;
+    const int m = g * 32 + lane, H = op.H, D = t.D;
+    float* pre = t.hid + m * t.HS;
+    float* act = t.act + m * t.HS;
+    float* xr = t.xt + m * t.XS;
+    for (int j = 0; j < H; ++j) { pre[j] = __ldg(op.p1 + j); act[j] = 0.0f; }
+    const bool quirk = (TK == B2F_T_RQ_INV || TK == B2F_T_RQ_FWD) && !(op.flags & B2F_FLAG_SEQ_LOGDET_EXACT);
+    float ldsum = 0.0f;
+    for (int i = 0; i < D; ++i) {
+        // hidden units whose inputs x_0..x_{i-1} are now all final
+        for (int j = 0; j < H; ++j)
+            if (__ldg(op.p4 + j) == i) act[j] = tanhf(pre[j]);
+        float acc[PP];
+        element_params<P, PP>(acc, op.p2 + (size_t)i * H * PP, op.p3 + (size_t)i * P, act, H);
+        const int c = t.col(i);
+        float out, ld;
+        transform_element<TK, MODE, PP>(xr[c], acc, op.boundary, out, ld);
+        if (quirk && i < D - 1) {
+            // The reference returns the log-det of its LAST full pass, in which dimension i < D-1 is fed the
+            // already inverted value (layers_base.py:218-223): reproduce that term.
+            float out2;
+            transform_element<TK, MODE, PP>(out, acc, op.boundary, out2, ld);
+        }
+        xr[c] = out;
+        ldsum += ld;
+        const float* w1c = op.p0 + i;    // column i of the (masked) first layer
+        for (int j = 0; j < H; ++j) pre[j] = fmaf(__ldg(w1c + (size_t)j * D), out, pre[j]);
+    }
+    t.ldp[m] = ldsum;
+}
+
 // ElementwiseAffine / ActNorm: global parameters value:(D,2) broadcast over the batch (layers_base.py:300-303).
 // stage: ea[j] = alpha_j, ea[D+j] = beta_j, ea[2D+j] = log alpha_j;  apply: z = a*x + b  or  z = (x - b)/a.
 __device__ __forceinline__ void elementwise_stage(float* ea, const DevOp& op, int D) {
