@@ -161,8 +161,8 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
         b_hi = round_tf32(bias)
         M[:Dh, :P, kb] = b_hi
         M[:Dh, :P, kb + 1] = round_tf32(bias - b_hi)
-        chunks = M.reshape(n_chunks, epc * cpe, K2)
-        w2c = torch.cat([umma_canonical(c) for c in chunks])
+        # every chunk [N2 x K2] into canonical order in one go: (chunk, row/8, k/4, row%8, k%4)
+        w2c = M.reshape(n_chunks, (epc * cpe) // 8, 8, K2 // 4, 4).permute(0, 1, 3, 2, 4).contiguous().reshape(-1)
     out = (w1c, w2c)
     cache[key] = (ver, out)
     return out

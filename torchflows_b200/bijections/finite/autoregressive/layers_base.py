@@ -22,6 +22,35 @@ from torchflows_b200.bijections.finite.autoregressive.transformers.spline.ration
 from torchflows_b200.utils import flatten_event, get_batch_shape, unflatten_event
 
 
+class _TF32Linear(torch.autograd.Function):
+    """y = x @ W^T + b as library GEMMs on the tensor cores (TF32) in BOTH directions.  torch's global
+    ``allow_tf32`` switch is read when a GEMM executes, so a plain ``F.linear`` under a scoped switch would run its
+    backward GEMMs in fp32 SIMT; this Function scopes the switch around its own forward and backward."""
+
+    @staticmethod
+    def _scoped(fn):
+        previous = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            return fn()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = previous
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return _TF32Linear._scoped(lambda: torch.addmm(bias, x, weight.t()))
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = _TF32Linear._scoped(lambda: g @ weight) if ctx.needs_input_grad[0] else None
+        gw = _TF32Linear._scoped(lambda: g.t() @ x) if ctx.needs_input_grad[1] else None
+        gb = g.sum(dim=0) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
 def _fits_fused_kernel(n_dim: int, n_hidden: int) -> bool:
     """Mirror of the shared-memory budget of csrc/b2f_flow.cu at its smallest tile (32 samples): the sample tile
     [32][D|1] plus the hidden activations [32][H|1] (twice for the backward kernel's gradient tile) must fit in
@@ -120,15 +149,20 @@ class CouplingBijection(AutoregressiveBijection):
     composite_tf32: bool = True
 
     def _conditioner_gemms(self, xa, context):
-        use_tf32 = self.composite_tf32 and isinstance(self.transformer, RationalQuadratic) and xa.is_cuda
+        ct = self.conditioner_transform
+        use_tf32 = (self.composite_tf32 and isinstance(self.transformer, RationalQuadratic) and xa.is_cuda
+                    and context is None and type(ct) is FeedForward and ct.is_plain)
         if not use_tf32:
-            return self.conditioner_transform(xa, context=context)
-        previous = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            return self.conditioner_transform(xa, context=context)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = previous
+            return ct(xa, context=context)
+        a = xa.reshape(-1, xa.shape[-1])
+        for module in ct.sequential:
+            if isinstance(module, nn.Linear):
+                a = _TF32Linear.apply(a, module.weight, module.bias)
+            elif isinstance(module, nn.Unflatten):
+                continue
+            else:
+                a = module(a)
+        return a.reshape(*xa.shape[:-1], -1)
 
     def _composite(self, x: torch.Tensor, context, direction: str):
         """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""

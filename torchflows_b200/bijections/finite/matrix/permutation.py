@@ -47,6 +47,12 @@ class ReversePermutationMatrix(PermutationMatrix):
             return None          # very wide events: plain index flip (InvertibleMatrix.forward / inverse)
         return [prog.LoweredOp(kind=N.OP_FLIP, owner=self)]
 
+    def project_flat(self, x_flat: torch.Tensor, context_flat: torch.Tensor = None) -> torch.Tensor:
+        return torch.flip(x_flat, dims=(-1,))       # same map as indexing with the reversed permutation, cheap backward
+
+    def solve_flat(self, b_flat: torch.Tensor, context: torch.Tensor = None) -> torch.Tensor:
+        return torch.flip(b_flat, dims=(-1,))
+
     def forward(self, x, context=None):
         return self._run_fused(x, 'forward') if self.lower('forward') is not None else super().forward(x, context)
 
