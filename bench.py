@@ -50,6 +50,39 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        # NVML in-process (nvidia_ml_py): forking nvidia-smi out of a process with a CUDA context stalls the launching
+        # thread for milliseconds, which is the length of a whole step here.  nvidia-smi is only the fallback.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(',')[self.index])
+                except Exception:
+                    idx = self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return self._run_smi()
+        bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        while not self.stop_flag:
+            try:
+                row = [str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(sm_max),
+                       str(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0), 'Not Active', 'Not Active', 'Not Active', 'Not Active']
+                mask = int(get_reasons(h))
+                for bit, col in bits:
+                    if mask & bit:
+                        row[col] = 'Active'
+                self.rows.append(row)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def _run_smi(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',

@@ -39,9 +39,12 @@ def build_product(force=False, verbose_ptxas=False):
     os.makedirs(os.path.dirname(PRODUCT_SO), exist_ok=True)
     objs = []
     procs = []
+    headers = [d for d in deps if not d.endswith('.cu')]
     for cu in cus:
         obj = os.path.join(os.path.dirname(PRODUCT_SO), os.path.basename(cu)[:-3] + '.o')
         objs.append(obj)
+        if not force and not verbose_ptxas and not _newer(obj, [cu] + headers):
+            continue                      # this translation unit is up to date
         cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
                '-Xcompiler', '-fPIC', '-I', os.path.join(ROOT, 'include'), '-c', cu, '-o', obj]
         if verbose_ptxas:

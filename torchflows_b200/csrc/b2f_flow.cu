@@ -201,6 +201,9 @@ namespace b2f {
 int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                        const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                        void* stream);   // b2f_flow_tc.cu
+int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
+                         const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
+                         void* stream);  // b2f_flow_rows.cu
 }
 
 using namespace b2f;
@@ -213,9 +216,18 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
     if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: %d ops > B2F_MAX_OPS", n_ops);
     if (B == 0) return B2F_OK;
     {
-        // CouplingRQNSF-shaped programs go to the tcgen05 kernel; everything else to the generic kernel below
-        const int rc = try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream);
-        if (rc != 0) return rc == 1 ? B2F_OK : rc;
+        // Spline programs (23 parameters per element: the output layer is a real GEMM) go to the tcgen05 kernel first,
+        // affine / shift programs and anything with a sequential layer to the row-per-thread kernel first; what neither
+        // takes runs on the generic kernel below.
+        bool has_rq = false;
+        for (int i = 0; i < n_ops; ++i)
+            if (ops[i].kind >= B2F_OP_COUPLING && (ops[i].tkind == B2F_T_RQ_FWD || ops[i].tkind == B2F_T_RQ_INV)) has_rq = true;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const bool tc = has_rq ? attempt == 0 : attempt == 1;
+            const int rc = tc ? try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream)
+                              : try_launch_flow_rows(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream);
+            if (rc != 0) return rc == 1 ? B2F_OK : rc;
+        }
     }
     FlowArgs A;
     memset(&A, 0, sizeof(A));

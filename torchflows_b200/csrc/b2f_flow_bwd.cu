@@ -49,6 +49,7 @@ struct BTile {
     Tile t;
     float* gt;    // [TM][XS] gradient w.r.t. the current activations
     float* dhid;  // [TM][HS] gradient w.r.t. hidden activations, then pre-activations
+    float* dhp;   // [WPG][TM][HS] per-slot partial sums of dhid (a warp owns its (slot, 32 samples) slice: no atomics)
     float* GL;    // [TM]     dL/dlog_det of each sample (constant through the layers)
     float* dhs;   // [NW][32][PPmax] per-warp staging of dL/dh for the weight-gradient product
     int rows;
@@ -87,7 +88,15 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
     float* dhs = b.dhs + warp * 32 * PP;
     const float GLm = b.GL[m];
     const bool want_w = op.g2 != nullptr;
-    for (int e = slot; e < n_tgt; e += t.WPG) {
+    float* dhp_m = b.dhp + ((size_t)slot * t.TM + m) * t.HS;
+    for (int j = 0; j < H; ++j) dhp_m[j] = 0.0f;
+    // every CTA walks the elements in its own rotation so that concurrent CTAs add into different weight gradients
+    const int n_it = (n_tgt + t.WPG - 1) / t.WPG;
+    const int rot = (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)n_it);
+    for (int it = 0; it < n_it; ++it) {
+        int ii = it + rot; if (ii >= n_it) ii -= n_it;
+        const int e = slot + ii * t.WPG;
+        if (e >= n_tgt) continue;
         const float* w2e = op.f.p2 + (size_t)e * H * PP;
         float acc[PP], dh[PP];
         element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)e * P, hid_m, H);
@@ -101,7 +110,7 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
             float s = 0.0f;
 #pragma unroll
             for (int p = 0; p < P; ++p) s = fmaf(dh[p], __ldg(w2e + j * PP + p), s);
-            atomicAdd(b.dhid + m * t.HS + j, s);
+            dhp_m[j] += s;
         }
         if (want_w) {
             // dL/dW2[e][j][p] += sum_m dh[m][p] * hid[m][j];  dL/db2[e][p] += sum_m dh[m][p]   (m over this warp)
@@ -264,6 +273,7 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
     b.GL = t.ldp + A.WPG * TM;             // [TM]
     float* ea = b.GL + TM;                 // [3*D]
     b.dhs = ea + 3 * D;                    // [NW][32][24]
+    b.dhp = b.dhs + NW * 32 * 24;          // [WPG][TM][HS]
     const long long row0 = (long long)blockIdx.x * TM;
     const int rows = (int)min((long long)TM, A.B - row0);
     b.rows = rows;
@@ -386,7 +396,6 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         // conditioner layer: reload its input, recompute hidden activations
         for (int m = warp; m < TM; m += NW)
             for (int j = lane; j < D; j += 32) t.xt[m * XS + j] = (m < rows) ? saved[(size_t)m * D + j] : 0.0f;
-        for (int i = tid; i < TM * HS; i += NT) b.dhid[i] = 0.0f;
         __syncthreads();
         const bool coupling = op.f.kind == B2F_OP_COUPLING;
         const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0, H = op.f.H;
@@ -398,7 +407,9 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         for (int idx = tid; idx < (H << t.logTM); idx += NT) {
             const int m = idx & (TM - 1), j = idx >> t.logTM;
             const float a = t.hid[m * HS + j];
-            b.dhid[m * HS + j] *= (1.0f - a * a);
+            float d = 0.0f;
+            for (int sl = 0; sl < A.WPG; ++sl) d += b.dhp[((size_t)sl * TM + m) * HS + j];
+            b.dhid[m * HS + j] = d * (1.0f - a * a);
         }
         __syncthreads();
         if (op.g0) {
@@ -517,8 +528,8 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     if (const char* e = getenv("B2F_BWD_NT")) NT = atoi(e);
     auto smem_bytes = [&](int tm, int nt) {
         const int wpg = (nt / 32) / (tm / 32);
-        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + 2 * (size_t)tm * A.HS + (size_t)wpg * tm + tm + 3 * D +
-                                        (size_t)(nt / 32) * 32 * 24 + 4);
+        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + (2 + (size_t)wpg) * tm * A.HS + (size_t)wpg * tm + tm +
+                                        3 * D + (size_t)(nt / 32) * 32 * 24 + 4);
     };
     while (TM > 32 && smem_bytes(TM, NT) > 200 * 1024) TM >>= 1;
     if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 256 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
