@@ -18,7 +18,12 @@
 //     barrier at all: layers, the D-step sequential inverse of a masked autoregressive layer (layers_base.py:213-223)
 //     and the base log-density run back to back, warps drift freely and hide each other's latency;
 //   * the tile row stride XS is a multiple of 4 floats with XS/4 odd, so a thread reads/writes 4 consecutive columns
-//     of its row with one conflict-free 16-byte shared-memory access.
+//     of its row with one conflict-free 16-byte shared-memory access;
+//   * ReversePermutationMatrix (matrix/permutation.py:19-37) never moves data: a FLIP only toggles how logical columns
+//     map to physical ones, and that mapping is folded into the WEIGHT staging (the staged images are indexed by
+//     physical column), so every inner loop walks physical columns upwards with constant offsets;
+//   * a run of elementwise layers (ElementwiseAffine / ActNorm) is one affine map per column that the next conditioner
+//     layer, or the epilogue, applies to the values it loads anyway.
 // HBM traffic is the algorithmic minimum (x read once, z / log-density written once, weights from L1/L2).
 #include <stdlib.h>
 #include <string.h>
@@ -43,75 +48,78 @@ struct RowsArgs {
     const float* base_log_scale;
 };
 
-// 4 consecutive LOGICAL columns k0..k0+3 of a row (k0 % 4 == 0, D % 4 == 0); a flipped tile stores logical column j at
-// physical column D-1-j, so the same 16 bytes are read in reverse order
-__device__ __forceinline__ void load4(const float* xr, int k0, int flip, int D, float (&v)[4]) {
-    if (!flip) {
-        const float4 q = *reinterpret_cast<const float4*>(xr + k0);
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-        const float4 q = *reinterpret_cast<const float4*>(xr + (D - 4 - k0));
-        v[0] = q.w; v[1] = q.z; v[2] = q.y; v[3] = q.x;
+// 4 consecutive PHYSICAL columns c0..c0+3 of a row (c0 % 4 == 0)
+__device__ __forceinline__ void ld4(const float* xr, int c0, float (&v)[4]) {
+    const float4 q = *reinterpret_cast<const float4*>(xr + c0);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+__device__ __forceinline__ void st4(float* xr, int c0, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(xr + c0) = make_float4(v[0], v[1], v[2], v[3]);
+}
+// z = A_c * x + B_c with the coefficients of a pending elementwise run (er[0..D) = A, er[D..2D) = B, physical columns)
+__device__ __forceinline__ void apply_run(const float* er, int D, int c0, float (&v)[4]) {
+    float a[4], b[4];
+    ld4(er, c0, a);
+    ld4(er + D, c0, b);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = fmaf(a[u], v[u], b[u]);
+}
+
+// tanh for the hidden layer.  MODE 0: libm-grade tanhf.  MODE >= 1: 1 - 2/(exp(2x)+1) on the SFU (ex2.approx, rcp.approx):
+// ABSOLUTE error <= ~2e-7, i.e. the size of one rounding of an activation near 1 -- the activations only feed dot products
+// with O(1) weights, so this is rounding-level noise for the transformer parameters (no bin decisions on this path).
+template <int MODE> __device__ __forceinline__ float rows_tanh(float x) {
+    if constexpr (MODE == 0) return tanhf(x);
+    else {
+        const float e = exp2f(fminf(x, 44.0f) * 2.885390081777927f);      // exp(2x), clamped below fp32 overflow
+        return 1.0f - __fdividef(2.0f, e + 1.0f);
     }
 }
-__device__ __forceinline__ void store4(float* xr, int k0, int flip, int D, const float (&v)[4]) {
-    if (!flip) *reinterpret_cast<float4*>(xr + k0) = make_float4(v[0], v[1], v[2], v[3]);
-    else *reinterpret_cast<float4*>(xr + (D - 4 - k0)) = make_float4(v[3], v[2], v[1], v[0]);
-}
 
-// An elementwise run (one affine map per column, coefficients er[0..D) and er[D..2D) indexed by the LOGICAL column at the
-// time the run was reached) that has not been applied yet; `rev` = an odd number of FLIP ops happened since, so today's
-// logical column k takes the coefficients of column D-1-k -- which is exactly what load4's flip does.
-struct PendingRun {
-    const float* er;
-    int rev;
-};
-__device__ __forceinline__ void pending_coeffs(const PendingRun& pr, int k0, int D, float (&a)[4], float (&b)[4]) {
-    load4(pr.er, k0, pr.rev, D, a);
-    load4(pr.er + D, k0, pr.rev, D, b);
-}
-
-// Shared-memory image of one conditioner layer's weights, zero-padded from H to HP = 4*HP4 hidden units so that every
-// inner loop has a compile-time trip count and every weight access is one broadcast 16-byte load at a constant offset:
-//   w1  [n_src/4][HP][4]   w1[(k/4)*HP*4 + j*4 + k%4] = W1[j][k]          (one-pass layers)
-//   w1c [D][HP]            w1c[i*HP + j]              = W1[j][i]          (sequential layers: rank-1 update of step i)
+// Shared-memory image of one conditioner layer's weights, indexed by PHYSICAL column and zero-padded from H to HP = 4*HP4
+// hidden units, so that every inner loop has a compile-time trip count and every weight access is one broadcast 16-byte
+// load at a constant offset.  With f = tile currently flipped, physical source column ps0 + kp holds logical source
+// k = f ? n_src-1-kp : kp and physical target column pt0 + ep holds logical target e = f ? n_tgt-1-ep : ep.
+//   w1  [n_src/4][HP][4]   w1[(kp/4)*HP*4 + j*4 + kp%4] = W1[j][k(kp)]        (one-pass layers)
+//   w1c [D][HP]            w1c[c*HP + j]                = W1[j][i(c)]         (sequential layers: rank-1 update of step i)
 //   b1  [HP]
-//   w2  [n_tgt*P][HP]      w2[(e*P + p)*HP + j]       = W2tile[e][j][p] for j < H,  b2[e][p] for j == H (HP > H: the
-//                          kernel keeps a constant 1 in hidden slot H, so the bias costs no extra load)
+//   w2  [n_tgt*P][HP]      w2[(ep*P + p)*HP + j]        = W2tile[e(ep)][j][p] for j < H,  b2[e][p] for j == H  (HP > H:
+//                          the kernel keeps a constant 1 in hidden slot H, so the bias costs no extra load)
 template <int HP>
 struct RowsWeights {
     const float *w1, *b1, *w2;
 };
 
 template <int HP, int P>
-__device__ __forceinline__ RowsWeights<HP> stage_weights(float* wbuf, const DevOp& op, int n_src, int n_tgt, bool seq) {
+__device__ __forceinline__ RowsWeights<HP> stage_weights(float* wbuf, const DevOp& op, int n_src, int n_tgt, bool seq, int f) {
     const int H = op.H, tid = threadIdx.x;
     float* w1 = wbuf;
     float* b1 = w1 + n_src * HP;
     float* w2 = b1 + HP;
     if (!seq) {
         for (int d = tid; d < n_src * HP; d += kRowsThreads) {
-            const int k4 = d / (HP * 4), rem = d - k4 * (HP * 4), j = rem >> 2, k = 4 * k4 + (rem & 3);
+            const int k4 = d / (HP * 4), rem = d - k4 * (HP * 4), j = rem >> 2, kp = 4 * k4 + (rem & 3);
+            const int k = f ? n_src - 1 - kp : kp;
             w1[d] = (j < H) ? __ldg(op.p0 + (size_t)j * n_src + k) : 0.0f;
         }
     } else {
         for (int d = tid; d < n_src * HP; d += kRowsThreads) {
-            const int i = d / HP, j = d - i * HP;
+            const int c = d / HP, j = d - c * HP, i = f ? n_src - 1 - c : c;
             w1[d] = (j < H) ? __ldg(op.p0 + (size_t)j * n_src + i) : 0.0f;
         }
     }
     if (tid < HP) b1[tid] = (tid < H) ? __ldg(op.p1 + tid) : 0.0f;
     for (int d = tid; d < n_tgt * P * HP; d += kRowsThreads) {
-        const int ep = d / HP, j = d - ep * HP, e = ep / P, p = ep - e * P;
-        w2[d] = (j < H) ? __ldg(op.p2 + ((size_t)e * H + j) * P + p) : (j == H ? __ldg(op.p3 + ep) : 0.0f);
+        const int q = d / HP, j = d - q * HP, ep = q / P, p = q - ep * P;
+        const int e = f ? n_tgt - 1 - ep : ep;
+        w2[d] = (j < H) ? __ldg(op.p2 + ((size_t)e * H + j) * P + p) : (j == H ? __ldg(op.p3 + e * P + p) : 0.0f);
     }
     return RowsWeights<HP>{w1, b1, w2};
 }
 
 // acc[r][p] = sum_j W2[e][p][j] * hid[r][j]  with the bias in slot H   (transforms.py:297-300, last Linear)
 template <int P, int HP, int R>
-__device__ __forceinline__ void row_params(float (&acc)[R][P], const RowsWeights<HP>& W, int e, const float (&hid)[R][HP]) {
-    const float4* w2 = reinterpret_cast<const float4*>(W.w2) + (size_t)e * P * (HP / 4);
+__device__ __forceinline__ void row_params(float (&acc)[R][P], const float4* __restrict__ w2e, const float (&hid)[R][HP]) {
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         float a[R];
@@ -119,7 +127,7 @@ __device__ __forceinline__ void row_params(float (&acc)[R][P], const RowsWeights
         for (int r = 0; r < R; ++r) a[r] = 0.0f;
 #pragma unroll
         for (int j4 = 0; j4 < HP / 4; ++j4) {
-            const float4 w = w2[p * (HP / 4) + j4];
+            const float4 w = w2e[p * (HP / 4) + j4];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 a[r] = fmaf(w.x, hid[r][4 * j4 + 0], a[r]);
@@ -133,10 +141,11 @@ __device__ __forceinline__ void row_params(float (&acc)[R][P], const RowsWeights
     }
 }
 
-// one-pass conditioner layer (coupling, or masked autoregressive in its parallel direction)
+// one-pass conditioner layer (coupling, or masked autoregressive in its parallel direction); sources are the physical
+// columns [ps0, ps0+n_src), targets [pt0, pt0+n_tgt)
 template <int TK, int MODE, int HP, int R>
-__device__ __forceinline__ void rows_pass(float* x0, int XS, int D, int flip, const DevOp& op,
-                                          const RowsWeights<HP>& W, int n_src, int t0, const PendingRun& pr, float (&ld)[R]) {
+__device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp& op, const RowsWeights<HP>& W, int ps0,
+                                          int n_src, int pt0, int n_tgt, const float* er, float (&ld)[R]) {
     constexpr int P = TInfo<TK>::P;
     const int H = op.H;
     float hid[R][HP];
@@ -148,18 +157,14 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, int flip, co
     }
     // hid[r][j] = tanh(b1[j] + sum_k W1[j][k] x[r][k])                 (transforms.py:295-296 / :259-262)
     const float4* w1 = reinterpret_cast<const float4*>(W.w1);
-    for (int k0 = 0; k0 < n_src; k0 += 4, w1 += HP) {
+    for (int c0 = ps0; c0 < ps0 + n_src; c0 += 4, w1 += HP) {
         float xv[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) load4(x0 + r * 32 * XS, k0, flip, D, xv[r]);
-        if (pr.er) {   // pending elementwise run: apply it to the source columns on the way in and write them back
-            float a[4], b[4];
-            pending_coeffs(pr, k0, D, a, b);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[r][u] = fmaf(a[u], xv[r][u], b[u]);
-                store4(x0 + r * 32 * XS, k0, flip, D, xv[r]);
+        for (int r = 0; r < R; ++r) {
+            ld4(x0 + r * 32 * XS, c0, xv[r]);
+            if (er) {      // pending elementwise run: apply it to the source columns on the way in and write them back
+                apply_run(er, D, c0, xv[r]);
+                st4(x0 + r * 32 * XS, c0, xv[r]);
             }
         }
 #pragma unroll
@@ -177,26 +182,21 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, int flip, co
 #pragma unroll
     for (int j = 0; j < HP; ++j) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) hid[r][j] = (j == H) ? 1.0f : tanhf(hid[r][j]);   // slot H carries the bias; padded
-    }                                                                                  // units: tanh(0) = 0 times zero weights
-    const int n_tgt = D - t0;
-    const bool ew_targets = pr.er != nullptr && t0 >= n_src;    // coupling: the targets were not touched by the loop above
-    for (int e0 = 0; e0 < n_tgt; e0 += 4) {
+        for (int r = 0; r < R; ++r) hid[r][j] = (j == H) ? 1.0f : rows_tanh<MODE>(hid[r][j]);   // slot H carries the bias;
+    }                                                                    // padded units: tanh(0) = 0 times zero weights
+    const bool ew_targets = er != nullptr && pt0 != ps0;     // coupling: the loop above did not touch the targets
+    const float4* w2 = reinterpret_cast<const float4*>(W.w2);
+    for (int c0 = pt0; c0 < pt0 + n_tgt; c0 += 4, w2 += 4 * P * (HP / 4)) {
         float xv[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) load4(x0 + r * 32 * XS, t0 + e0, flip, D, xv[r]);
-        if (ew_targets) {
-            float a[4], b[4];
-            pending_coeffs(pr, t0 + e0, D, a, b);
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[r][u] = fmaf(a[u], xv[r][u], b[u]);
+        for (int r = 0; r < R; ++r) {
+            ld4(x0 + r * 32 * XS, c0, xv[r]);
+            if (ew_targets) apply_run(er, D, c0, xv[r]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float acc[R][P];
-            row_params<P, HP, R>(acc, W, e0 + u, hid);
+            row_params<P, HP, R>(acc, w2 + u * P * (HP / 4), hid);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float out, l;
@@ -206,16 +206,17 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, int flip, co
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) store4(x0 + r * 32 * XS, t0 + e0, flip, D, xv[r]);
+        for (int r = 0; r < R; ++r) st4(x0 + r * 32 * XS, c0, xv[r]);
     }
 }
 
 // D-step sequential direction of a masked autoregressive layer (layers_base.py:213-223) at the cost of ONE conditioner
 // pass: the hidden pre-activations get a rank-1 update per finished dimension and only the P parameters of dimension i
 // are evaluated at step i.  Everything of a sample is in its thread's registers: no barrier in the D-step loop.
-template <int TK, int MODE, int HP, int R>
-__device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, int flip, const DevOp& op,
-                                                const RowsWeights<HP>& W, const PendingRun& pr, float (&ld)[R]) {
+// REV: the tile is flipped, logical step i lives at physical column D-1-i, so physical columns are walked downwards.
+template <int TK, int MODE, int HP, int R, bool REV>
+__device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const DevOp& op, const RowsWeights<HP>& W,
+                                                const float* er, float (&ld)[R]) {
     constexpr int P = TInfo<TK>::P;
     const int H = op.H;
     float pre[R][HP], act[R][HP];
@@ -228,30 +229,28 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, int fl
         for (int r = 0; r < R; ++r) { pre[r][j] = b; act[r][j] = (j == H) ? 1.0f : 0.0f; }   // slot H carries the bias
     }
     const float4* w1c = reinterpret_cast<const float4*>(W.w1);
-    for (int i0 = 0; i0 < D; i0 += 4) {
+    const float4* w2 = reinterpret_cast<const float4*>(W.w2);
+    for (int q = 0; q < D; q += 4) {
+        const int c0 = REV ? D - 4 - q : q;
         float xv[R][4];
 #pragma unroll
-        for (int r = 0; r < R; ++r) load4(x0 + r * 32 * XS, i0, flip, D, xv[r]);
-        if (pr.er) {
-            float a[4], b[4];
-            pending_coeffs(pr, i0, D, a, b);
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) xv[r][u] = fmaf(a[u], xv[r][u], b[u]);
+        for (int r = 0; r < R; ++r) {
+            ld4(x0 + r * 32 * XS, c0, xv[r]);
+            if (er) apply_run(er, D, c0, xv[r]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u;
+        for (int uu = 0; uu < 4; ++uu) {
+            const int u = REV ? 3 - uu : uu;          // compile-time after unrolling
+            const int c = c0 + u, i = q + uu;         // physical column, logical step
             // hidden units whose inputs x_0..x_{i-1} are now all final
 #pragma unroll
             for (int j = 0; j < HP; ++j)
                 if (fin[j] == i) {
 #pragma unroll
-                    for (int r = 0; r < R; ++r) act[r][j] = tanhf(pre[r][j]);
+                    for (int r = 0; r < R; ++r) act[r][j] = rows_tanh<MODE>(pre[r][j]);
                 }
             float acc[R][P];
-            row_params<P, HP, R>(acc, W, i, act);
+            row_params<P, HP, R>(acc, w2 + (size_t)c * P * (HP / 4), act);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float out, l;
@@ -261,7 +260,7 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, int fl
             }
 #pragma unroll
             for (int j4 = 0; j4 < HP / 4; ++j4) {
-                const float4 w = w1c[i * (HP / 4) + j4];          // column i of the (masked) first layer
+                const float4 w = w1c[c * (HP / 4) + j4];          // column i of the (masked) first layer
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
                     pre[r][4 * j4 + 0] = fmaf(w.x, xv[r][u], pre[r][4 * j4 + 0]);
@@ -272,31 +271,33 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, int fl
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) store4(x0 + r * 32 * XS, i0, flip, D, xv[r]);
+        for (int r = 0; r < R; ++r) st4(x0 + r * 32 * XS, c0, xv[r]);
     }
 }
 
 template <int TK, int MODE, int HP, int R>
 __device__ __forceinline__ void rows_layer_tk(float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
-                                              const PendingRun& pr, float (&ld)[R]) {
+                                              const float* er, float (&ld)[R]) {
     const bool seq = op.kind == B2F_OP_MADE_SEQ;
     const bool coupling = op.kind == B2F_OP_COUPLING;
-    const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0;
+    const int n_src = coupling ? D / 2 : D, n_tgt = coupling ? D - D / 2 : D;      // HalfSplit: first D//2 logical columns
+    const int ps0 = flip ? D - n_src : 0, pt0 = (flip || !coupling) ? 0 : D - n_tgt;
     __syncthreads();                        // every warp is done with the previous layer's weights
-    const RowsWeights<HP> W = stage_weights<HP, TInfo<TK>::P>(wbuf, op, n_src, D - t0, seq);
+    const RowsWeights<HP> W = stage_weights<HP, TInfo<TK>::P>(wbuf, op, n_src, n_tgt, seq, flip);
     __syncthreads();
-    if (seq) rows_sequential<TK, MODE, HP, R>(x0, XS, D, flip, op, W, pr, ld);
-    else rows_pass<TK, MODE, HP, R>(x0, XS, D, flip, op, W, n_src, t0, pr, ld);
+    if (!seq) rows_pass<TK, MODE, HP, R>(x0, XS, D, op, W, ps0, n_src, pt0, n_tgt, er, ld);
+    else if (flip) rows_sequential<TK, MODE, HP, R, true>(x0, XS, D, op, W, er, ld);
+    else rows_sequential<TK, MODE, HP, R, false>(x0, XS, D, op, W, er, ld);
 }
 
 template <int MODE, int HP, int R>
 __device__ __forceinline__ void rows_layer(float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
-                                           const PendingRun& pr, float (&ld)[R]) {
+                                           const float* er, float (&ld)[R]) {
     switch (op.tkind) {
-        case B2F_T_SHIFT_ADD: rows_layer_tk<B2F_T_SHIFT_ADD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, pr, ld); break;
-        case B2F_T_SHIFT_SUB: rows_layer_tk<B2F_T_SHIFT_SUB, MODE, HP, R>(wbuf, x0, XS, D, flip, op, pr, ld); break;
-        case B2F_T_AFFINE_FWD: rows_layer_tk<B2F_T_AFFINE_FWD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, pr, ld); break;
-        case B2F_T_AFFINE_INV: rows_layer_tk<B2F_T_AFFINE_INV, MODE, HP, R>(wbuf, x0, XS, D, flip, op, pr, ld); break;
+        case B2F_T_SHIFT_ADD: rows_layer_tk<B2F_T_SHIFT_ADD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
+        case B2F_T_SHIFT_SUB: rows_layer_tk<B2F_T_SHIFT_SUB, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
+        case B2F_T_AFFINE_FWD: rows_layer_tk<B2F_T_AFFINE_FWD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
+        case B2F_T_AFFINE_INV: rows_layer_tk<B2F_T_AFFINE_INV, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
         default: break;
     }
 }
@@ -308,8 +309,8 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int D = A.D, XS = A.XS, D4 = D >> 2;
     float* xw = smem + (size_t)warp * TMW * XS;          // this warp's [32*R][XS] rows
-    float* ea = smem + (size_t)NW * TMW * XS;            // [n_runs][2][D]  A_j, B_j of every elementwise run
-    float* gb = ea + (size_t)A.n_runs * 2 * D;           // [2][D]          base loc_j, 1/scale_j
+    float* ea = smem + (size_t)NW * TMW * XS;            // [n_runs][2][D]  A_c, B_c of every elementwise run (physical c)
+    float* gb = ea + (size_t)A.n_runs * 2 * D;           // [2][D]          base loc_c, 1/scale_c             (physical c)
     float* red = gb + 2 * D;                             // [2][NW]         CTA-uniform constants (partials per warp)
     float* wbuf = red + 2 * NW;                          // staged weights of the current conditioner layer
 
@@ -332,16 +333,20 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
-    // ---- batch-independent part: every run of consecutive elementwise layers is one affine map per column -----------
+    // ---- batch-independent part: every run of consecutive elementwise layers is one affine map per column, stored by
+    //      the PHYSICAL column it applies to (the flip state at the run is known from the program) -----------------------
+    int final_flip = 0;
     {
         float lsum = 0.0f, gsum = 0.0f;
-        int run = 0;
+        int run = 0, f = 0;
         for (int oi = 0; oi < A.n_ops; ++oi) {
+            if (A.ops[oi].kind == B2F_OP_FLIP) { f ^= 1; continue; }
             if (A.ops[oi].kind != B2F_OP_ELEMENTWISE) continue;
             int n_run = 1;
             while (oi + n_run < A.n_ops && A.ops[oi + n_run].kind == B2F_OP_ELEMENTWISE) ++n_run;
             float* er = ea + (size_t)run * 2 * D;
-            for (int j = tid; j < D; j += kRowsThreads) {
+            for (int c = tid; c < D; c += kRowsThreads) {
+                const int j = f ? D - 1 - c : c;
                 float Aj = 1.0f, Bj = 0.0f;
                 for (int r = 0; r < n_run; ++r) {
                     const DevOp& o = A.ops[oi + r];
@@ -351,16 +356,19 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
                     if (o.tkind == B2F_T_AFFINE_FWD) { Aj *= a; Bj = fmaf(a, Bj, b); lsum += la; }
                     else { const float ia = 1.0f / a; Aj *= ia; Bj = (Bj - b) * ia; lsum -= la; }
                 }
-                er[j] = Aj; er[D + j] = Bj;
+                er[c] = Aj; er[D + c] = Bj;
             }
             oi += n_run - 1;
             ++run;
         }
+        final_flip = f;
         if (A.log_prob) {
-            for (int j = tid; j < D; j += kRowsThreads) {
+            const int gf = (A.flags & B2F_FLOW_LOGP_OF_INPUT) ? 0 : final_flip;      // orientation when the density is taken
+            for (int c = tid; c < D; c += kRowsThreads) {
+                const int j = gf ? D - 1 - c : c;
                 const float lsc = A.base_log_scale ? __ldg(A.base_log_scale + j) : 0.0f;
-                gb[j] = A.base_loc ? __ldg(A.base_loc + j) : 0.0f;
-                gb[D + j] = expf(-lsc);
+                gb[c] = A.base_loc ? __ldg(A.base_loc + j) : 0.0f;
+                gb[D + c] = expf(-lsc);
                 gsum += 0.91893853320467274178f + lsc;
             }
         }
@@ -379,8 +387,7 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
 #pragma unroll
     for (int r = 0; r < R; ++r) { ld[r] = 0.0f; lp[r] = 0.0f; }
     const bool want_lp = A.log_prob != nullptr;
-    int flip = 0;
-    PendingRun pr{nullptr, 0};      // elementwise run that has been reached but not applied yet: the next conditioner layer
+    const float* er = nullptr;      // elementwise run that has been reached but not applied yet: the next conditioner layer
                                     // (or the epilogue) applies it on the fly to the values it loads anyway
     // DiagonalGaussian.log_prob (gaussian.py:46-54) of the thread's rows as they stand (after the pending run, if any)
     auto base_logp = [&]() {
@@ -388,18 +395,17 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
 #pragma unroll
         for (int r = 0; r < R; ++r) s[r] = 0.0f;
         for (int c0 = 0; c0 < D; c0 += 4) {
-            float loc[4], isc[4], a[4], b[4];
-            load4(gb, c0, 0, D, loc);
-            load4(gb + D, c0, 0, D, isc);
-            if (pr.er) pending_coeffs(pr, c0, D, a, b);
+            float loc[4], isc[4];
+            ld4(gb, c0, loc);
+            ld4(gb + D, c0, isc);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 float xv[4];
-                load4(x0 + r * 32 * XS, c0, flip, D, xv);
+                ld4(x0 + r * 32 * XS, c0, xv);
+                if (er) apply_run(er, D, c0, xv);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float v = pr.er ? fmaf(a[u], xv[u], b[u]) : xv[u];
-                    const float t = (v - loc[u]) * isc[u];
+                    const float t = (xv[u] - loc[u]) * isc[u];
                     s[r] = fmaf(0.5f * t, t, s[r]);
                 }
             }
@@ -410,33 +416,29 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
     if (want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp();
 
     // ---- the layers ------------------------------------------------------------------------------------------------
-    int run = 0;
+    int run = 0, flip = 0;
     for (int oi = 0; oi < A.n_ops; ++oi) {
         const DevOp& op = A.ops[oi];
-        if (op.kind == B2F_OP_FLIP) { flip ^= 1; pr.rev ^= 1; continue; }
+        if (op.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (op.kind == B2F_OP_ELEMENTWISE) {
             while (oi + 1 < A.n_ops && A.ops[oi + 1].kind == B2F_OP_ELEMENTWISE) ++oi;
-            if (pr.er) {                            // two runs separated only by FLIPs (no preset does this): apply the first
+            if (er) {                               // two runs separated only by FLIPs (no preset does this): apply the first
                 for (int c0 = 0; c0 < D; c0 += 4) {
-                    float a[4], b[4];
-                    pending_coeffs(pr, c0, D, a, b);
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
                         float xv[4];
-                        load4(x0 + r * 32 * XS, c0, flip, D, xv);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) xv[u] = fmaf(a[u], xv[u], b[u]);
-                        store4(x0 + r * 32 * XS, c0, flip, D, xv);
+                        ld4(x0 + r * 32 * XS, c0, xv);
+                        apply_run(er, D, c0, xv);
+                        st4(x0 + r * 32 * XS, c0, xv);
                     }
                 }
             }
-            pr.er = ea + (size_t)run * 2 * D;       // every run is followed by a conditioner layer or the epilogue
-            pr.rev = 0;
+            er = ea + (size_t)run * 2 * D;
             ++run;
             continue;
         }
-        rows_layer<MODE, HP, R>(wbuf, x0, XS, D, flip, op, pr, ld);
-        pr.er = nullptr;
+        rows_layer<MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld);
+        er = nullptr;
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
@@ -456,15 +458,12 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
         int m = 0, c4 = lane;
         while (c4 >= D4) { c4 -= D4; ++m; }
         for (int idx = lane; m < rows; idx += 32) {
+            // logical columns 4*c4 .. 4*c4+3 of the output row
+            const int c0 = flip ? D - 4 - 4 * c4 : 4 * c4;
             float v[4];
-            load4(xw + m * XS, 4 * c4, flip, D, v);
-            if (pr.er) {
-                float a[4], b[4];
-                pending_coeffs(pr, 4 * c4, D, a, b);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = fmaf(a[u], v[u], b[u]);
-            }
-            __stcs(dst + idx, make_float4(v[0], v[1], v[2], v[3]));
+            ld4(xw + m * XS, c0, v);
+            if (er) apply_run(er, D, c0, v);
+            __stcs(dst + idx, flip ? make_float4(v[3], v[2], v[1], v[0]) : make_float4(v[0], v[1], v[2], v[3]));
             c4 += 32;
             while (c4 >= D4) { c4 -= D4; ++m; }
         }
