@@ -33,6 +33,11 @@ WORKLOADS = {
 }
 
 
+# the kernel each workload's log_prob launch dispatches to (b2f_flow_apply: csrc/b2f_flow.cu)
+KERNELS = {'q256': 'b2f::flow_tc_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_rows_kernel',
+           'm128': 'b2f::flow_rows_kernel'}
+
+
 def algorithmic_bytes(D):
     """SURVEY 8d, whole-flow kernels: log_prob reads x (4D) and writes one float; sample-from-given-z reads z and
     writes x (8D)."""
@@ -327,7 +332,7 @@ def run_ours(args):
                    'weights': 'random init (seed 0), ActNorm data-initialised (state T)', 'rows_per_gpu': B,
                    'l2': f'inputs larger than L2 ({B * D * 4 >> 20} MiB per tensor)', 'precision_mode': 'default (SFU after bin search)'},
         'log_prob_samples_per_s': world * B / (lp_avg_ms * 1e-3), 'sample_samples_per_s': world * B / (s_avg_ms * 1e-3),
-        'roofline': {'bound': 'hbm', 'kernel': 'b2f::flow_kernel (log_prob launch)', 'achieved': achieved,
+        'roofline': {'bound': 'hbm', 'kernel': KERNELS[args.workload] + ' (log_prob launch)', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
                      'peak_source': peak_src, 'algorithmic_bytes_per_row': by_lp, 'launch_ms': lp_avg_ms,
                      'sample_launch': {'achieved': by_s * B / (s_avg_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_row': by_s,

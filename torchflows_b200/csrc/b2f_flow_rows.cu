@@ -38,7 +38,8 @@ constexpr int kRowsThreads = 128;     // four warps; between the per-layer weigh
 
 struct RowsArgs {
     DevOp ops[B2F_MAX_OPS];
-    int n_ops, D, XS, flags, n_runs, wbuf_floats;
+    int n_ops, D, XS, flags, n_runs, tiles_per_warp;
+    int woff[B2F_MAX_OPS];      // float offset of each conditioner layer's staged weights in the weight area
     long long B;
     const float* x;
     float* y;
@@ -90,8 +91,13 @@ struct RowsWeights {
     const float *w1, *b1, *w2;
 };
 
+template <int HP>
+__device__ __forceinline__ RowsWeights<HP> weights_view(const float* wbuf, int n_src) {
+    return RowsWeights<HP>{wbuf, wbuf + n_src * HP, wbuf + n_src * HP + HP};
+}
+
 template <int HP, int P>
-__device__ __forceinline__ RowsWeights<HP> stage_weights(float* wbuf, const DevOp& op, int n_src, int n_tgt, bool seq, int f) {
+__device__ __forceinline__ void stage_weights(float* wbuf, const DevOp& op, int n_src, int n_tgt, bool seq, int f) {
     const int H = op.H, tid = threadIdx.x;
     float* w1 = wbuf;
     float* b1 = w1 + n_src * HP;
@@ -114,7 +120,6 @@ __device__ __forceinline__ RowsWeights<HP> stage_weights(float* wbuf, const DevO
         const int e = f ? n_tgt - 1 - ep : ep;
         w2[d] = (j < H) ? __ldg(op.p2 + ((size_t)e * H + j) * P + p) : (j == H ? __ldg(op.p3 + e * P + p) : 0.0f);
     }
-    return RowsWeights<HP>{w1, b1, w2};
 }
 
 // acc[r][p] = sum_j W2[e][p][j] * hid[r][j]  with the bias in slot H   (transforms.py:297-300, last Linear)
@@ -276,22 +281,20 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const 
 }
 
 template <int TK, int MODE, int HP, int R>
-__device__ __forceinline__ void rows_layer_tk(float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
+__device__ __forceinline__ void rows_layer_tk(const float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
                                               const float* er, float (&ld)[R]) {
     const bool seq = op.kind == B2F_OP_MADE_SEQ;
     const bool coupling = op.kind == B2F_OP_COUPLING;
     const int n_src = coupling ? D / 2 : D, n_tgt = coupling ? D - D / 2 : D;      // HalfSplit: first D//2 logical columns
     const int ps0 = flip ? D - n_src : 0, pt0 = (flip || !coupling) ? 0 : D - n_tgt;
-    __syncthreads();                        // every warp is done with the previous layer's weights
-    const RowsWeights<HP> W = stage_weights<HP, TInfo<TK>::P>(wbuf, op, n_src, n_tgt, seq, flip);
-    __syncthreads();
+    const RowsWeights<HP> W = weights_view<HP>(wbuf, n_src);
     if (!seq) rows_pass<TK, MODE, HP, R>(x0, XS, D, op, W, ps0, n_src, pt0, n_tgt, er, ld);
     else if (flip) rows_sequential<TK, MODE, HP, R, true>(x0, XS, D, op, W, er, ld);
     else rows_sequential<TK, MODE, HP, R, false>(x0, XS, D, op, W, er, ld);
 }
 
 template <int MODE, int HP, int R>
-__device__ __forceinline__ void rows_layer(float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
+__device__ __forceinline__ void rows_layer(const float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
                                            const float* er, float (&ld)[R]) {
     switch (op.tkind) {
         case B2F_T_SHIFT_ADD: rows_layer_tk<B2F_T_SHIFT_ADD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
@@ -313,25 +316,6 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
     float* gb = ea + (size_t)A.n_runs * 2 * D;           // [2][D]          base loc_c, 1/scale_c             (physical c)
     float* red = gb + 2 * D;                             // [2][NW]         CTA-uniform constants (partials per warp)
     float* wbuf = red + 2 * NW;                          // staged weights of the current conditioner layer
-
-    // ---- this warp's rows: asynchronous 16-byte copies global -> shared (rows beyond B are zero-filled); they are in
-    //      flight while the batch-independent constants below are computed ---------------------------------------------
-    const long long wrow0 = ((long long)blockIdx.x * NW + warp) * TMW;
-    const int rows = (int)max(0LL, min((long long)TMW, A.B - wrow0));
-    {
-        const float4* src = reinterpret_cast<const float4*>(A.x + wrow0 * D);
-        int m = 0, c4 = lane;
-        while (c4 >= D4) { c4 -= D4; ++m; }
-        for (int idx = lane; m < TMW; idx += 32) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(xw + m * XS + 4 * c4);
-            const int nbytes = (m < rows) ? 16 : 0;                     // src-size 0: the 16 bytes are zero-filled
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (m < rows ? idx : 0)), "r"(nbytes)
-                         : "memory");
-            c4 += 32;
-            while (c4 >= D4) { c4 -= D4; ++m; }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
 
     // ---- batch-independent part: every run of consecutive elementwise layers is one affine map per column, stored by
     //      the PHYSICAL column it applies to (the flip state at the run is known from the program) -----------------------
@@ -376,17 +360,51 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
         gsum = warp_sum(gsum);
         if (lane == 0) { red[warp] = lsum; red[NW + warp] = gsum; }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();   // staged constants + tile visible
+    // ---- the weights of EVERY conditioner layer, staged once per CTA (physical-column images, see RowsWeights) ---------
+    {
+        int f = 0;
+        for (int oi = 0; oi < A.n_ops; ++oi) {
+            const DevOp& op = A.ops[oi];
+            if (op.kind == B2F_OP_FLIP) { f ^= 1; continue; }
+            if (op.kind == B2F_OP_ELEMENTWISE) continue;
+            const bool coupling = op.kind == B2F_OP_COUPLING, seq = op.kind == B2F_OP_MADE_SEQ;
+            const int n_src = coupling ? D / 2 : D, n_tgt = coupling ? D - D / 2 : D;
+            if (op.tkind == B2F_T_SHIFT_ADD || op.tkind == B2F_T_SHIFT_SUB) stage_weights<HP, 1>(wbuf + A.woff[oi], op, n_src, n_tgt, seq, f);
+            else stage_weights<HP, 2>(wbuf + A.woff[oi], op, n_src, n_tgt, seq, f);
+        }
+    }
+    __syncthreads();   // the only CTA barrier: staged constants and weights visible; from here on warps run independently
     float ldc = 0.0f, gconst = 0.0f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) { ldc += red[w]; gconst += red[NW + w]; }
-
+    const bool want_lp = A.log_prob != nullptr;
     float* x0 = xw + lane * XS;                          // row r of this thread: x0 + r*32*XS
+
+  for (int tt = 0; tt < A.tiles_per_warp; ++tt) {
+    // ---- this warp's next 32*R rows: asynchronous 16-byte copies global -> shared (rows beyond B are zero-filled) -------
+    const long long wrow0 = (((long long)blockIdx.x * NW + warp) * A.tiles_per_warp + tt) * TMW;
+    const int rows = (int)max(0LL, min((long long)TMW, A.B - wrow0));
+    if (rows == 0) break;
+    __syncwarp();      // every lane is done with the previous tile
+    {
+        const float4* src = reinterpret_cast<const float4*>(A.x + wrow0 * D);
+        int m = 0, c4 = lane;
+        while (c4 >= D4) { c4 -= D4; ++m; }
+        for (int idx = lane; m < TMW; idx += 32) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(xw + m * XS + 4 * c4);
+            const int nbytes = (m < rows) ? 16 : 0;                     // src-size 0: the 16 bytes are zero-filled
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + (m < rows ? idx : 0)), "r"(nbytes)
+                         : "memory");
+            c4 += 32;
+            while (c4 >= D4) { c4 -= D4; ++m; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();      // the other lanes' copies are visible
     float ld[R], lp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) { ld[r] = 0.0f; lp[r] = 0.0f; }
-    const bool want_lp = A.log_prob != nullptr;
     const float* er = nullptr;      // elementwise run that has been reached but not applied yet: the next conditioner layer
                                     // (or the epilogue) applies it on the fly to the values it loads anyway
     // DiagonalGaussian.log_prob (gaussian.py:46-54) of the thread's rows as they stand (after the pending run, if any)
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
             ++run;
             continue;
         }
-        rows_layer<MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld);
+        rows_layer<MODE, HP, R>(wbuf + A.woff[oi], x0, XS, D, flip, op, er, ld);
         er = nullptr;
     }
 
@@ -468,6 +486,7 @@ __global__ void __launch_bounds__(kRowsThreads) flow_rows_kernel(const __grid_co
             while (c4 >= D4) { c4 -= D4; ++m; }
         }
     }
+  }   // tiles of this warp
 }
 
 template <int MODE, int HP4>
@@ -538,16 +557,31 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
     if (hp4 > 8) return 0;
     int XS = D + 4;
     if (((XS >> 2) & 1) == 0) XS += 4;     // XS/4 odd: conflict-free 16-byte row accesses across a warp
-    // staged weights of the largest layer: w1 [n_src][HP] + b1 [HP] + w2 [n_tgt*P][HP], P <= 2, n_src, n_tgt <= D
-    const size_t wbuf = (size_t)D * HP + HP + (size_t)2 * D * HP;
-    const size_t fixed = sizeof(float) * ((size_t)n_runs * 2 * D + 2 * D + 8 + wbuf);
-    auto smem_bytes = [&](int r) { return sizeof(float) * (size_t)(kRowsThreads / 32) * 32 * r * XS + fixed; };
+    // staged weights of every conditioner layer: w1 [n_src][HP] + b1 [HP] + w2 [n_tgt*P][HP]
+    size_t wtotal = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        const b2f_op_t& o = ops[i];
+        if (o.kind != B2F_OP_COUPLING && o.kind != B2F_OP_MADE && o.kind != B2F_OP_MADE_SEQ) continue;
+        const int n_src = o.kind == B2F_OP_COUPLING ? D / 2 : D, n_tgt = o.kind == B2F_OP_COUPLING ? D - D / 2 : D;
+        const int P = (o.tkind == B2F_T_SHIFT_ADD || o.tkind == B2F_T_SHIFT_SUB) ? 1 : 2;
+        A.woff[i] = (int)wtotal;
+        wtotal += (size_t)n_src * HP + HP + (size_t)n_tgt * P * HP;
+    }
     const int R = 1;
-    const size_t smem = smem_bytes(R);
+    const size_t smem = sizeof(float) * ((size_t)(kRowsThreads / 32) * 32 * R * XS + (size_t)n_runs * 2 * D + 2 * D + 8 + wtotal);
     if (smem > 110 * 1024) return 0;
-    A.n_ops = n_ops; A.D = D; A.XS = XS; A.B = B; A.flags = flags; A.n_runs = n_runs; A.wbuf_floats = (int)wbuf;
+    A.n_ops = n_ops; A.D = D; A.XS = XS; A.B = B; A.flags = flags; A.n_runs = n_runs;
     A.x = x; A.y = y; A.log_det = log_det; A.log_prob = log_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
-    const long long rows_per_cta = (long long)(kRowsThreads / 32) * 32 * R;
+    // a warp walks tiles_per_warp consecutive 32-row tiles (the per-CTA weight staging is amortised over them) while the
+    // grid stays several waves deep, so that the hardware CTA scheduler still balances the SMs
+    int sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long long warp_tiles = (B + 32 * R - 1) / (32 * R);
+    long long tpw = warp_tiles / ((long long)sms * 16 * 3);          // ~16 resident warps per SM, >= 3 waves
+    tpw = std::max(1LL, std::min(8LL, tpw));
+    if (const char* e = getenv("B2F_ROWS_TPW")) { const int t = atoi(e); if (t >= 1 && t <= 64) tpw = t; }
+    A.tiles_per_warp = (int)tpw;
+    const long long rows_per_cta = (long long)(kRowsThreads / 32) * 32 * R * tpw;
     const long long grid = (B + rows_per_cta - 1) / rows_per_cta;
     if (grid > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: batch too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
