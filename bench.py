@@ -53,27 +53,35 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
-
-    def run(self):
-        # NVML in-process (nvidia_ml_py): forking nvidia-smi out of a process with a CUDA context stalls the launching
-        # thread for milliseconds, which is the length of a whole step here.  nvidia-smi is only the fallback.
+        # NVML in-process (nvidia_ml_py), imported and initialised HERE, on the caller's thread and before the timed
+        # region: importing the module holds the GIL for tens of milliseconds, and forking nvidia-smi out of a process
+        # with a CUDA context stalls the launching thread just as long -- both are whole steps at this scale.
+        self.nvml = None
         try:
             import pynvml
             pynvml.nvmlInit()
             visible = os.environ.get('CUDA_VISIBLE_DEVICES')
-            idx = self.index
+            idx = index
             if visible:
                 try:
-                    idx = int(visible.split(',')[self.index])
+                    idx = int(visible.split(',')[index])
                 except Exception:
-                    idx = self.index
+                    idx = index
             h = pynvml.nvmlDeviceGetHandleByIndex(idx)
             sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
                 pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            get_reasons(h)
+            self.nvml = (pynvml, h, sm_max, get_reasons)
         except Exception:
+            self.nvml = None
+
+    def run(self):
+        if self.nvml is None:
             return self._run_smi()
+        pynvml, h, sm_max, get_reasons = self.nvml
         bits = ((0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6))       # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+        period = float(os.environ.get('B2F_CLOCK_PERIOD', '0.05'))
         while not self.stop_flag:
             try:
                 row = [str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(sm_max),
@@ -85,7 +93,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append(row)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(period)
 
     def _run_smi(self):
         while not self.stop_flag:
@@ -210,10 +218,13 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     with torch.no_grad():
         for _ in range(args.warmup):
-            step()
+            lp, xs = step()        # bound like in the timed loop: the allocator ends warm-up holding both output buffers
         sync_all()
         sampler = ClockSampler(local_rank)
         sampler.start()
+        import gc
+        gc.collect()
+        gc.disable()           # a collector pause on the launching thread is a bubble on the GPU at ~1 ms per step
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
         ev[0].record(stream)
         for i in range(args.steps):
@@ -253,11 +264,22 @@ def run_ours(args):
         h2d_stream = torch.cuda.Stream(device=dev)
         d2h_stream = torch.cuda.Stream(device=dev)
 
+        import collections
+        in_flight = collections.deque()      # (device tensors, main-stream event, d2h-stream event) of the last two steps
+
         def e2e_step():
             # Chunked and interleaved: while the kernels of chunk i run, chunk i+1 of x is on its way up (H2D) and the
-            # samples of chunk i-1 are on their way down (D2H) -- the two PCIe directions are used at the same time.
+            # samples of chunk i-1 are on their way down (D2H) -- the two PCIe directions are used at the same time, also
+            # across step boundaries.  The device tensors of a step stay referenced until the step after the next one
+            # starts (ordered by events), so the caching allocator sees the same allocation pattern every step: no
+            # cudaMalloc and no cross-stream reuse hazards inside the timed region.
+            if len(in_flight) == 2:
+                old, ev_main, ev_d2h = in_flight.popleft()
+                h2d_stream.wait_event(ev_main)          # its staging blocks are no longer read by kernels
+                stream.wait_event(ev_d2h)               # its output blocks have been copied out
+                del old
             chunks = list(range(0, B, rows_c))
-            staged = {}
+            staged, keep = {}, []
 
             def stage(s):
                 with torch.cuda.stream(h2d_stream):
@@ -273,7 +295,6 @@ def run_ours(args):
                 xc, e = staged.pop(s)
                 stream.wait_event(e)
                 lpc = flow.log_prob(xc)                                   # public API, device chunk
-                xc.record_stream(stream)
                 n = min(rows_c, B - s)
                 xsc = flow.sample(n, no_grad=True)                        # draws z on the device, inverse pass
                 done = torch.cuda.Event()
@@ -282,20 +303,26 @@ def run_ours(args):
                     d2h_stream.wait_event(done)
                     lp_host[s:s + n].copy_(lpc, non_blocking=True)
                     xs_host[s:s + n].copy_(xsc, non_blocking=True)
-                    lpc.record_stream(d2h_stream)
-                    xsc.record_stream(d2h_stream)
-            stream.wait_stream(d2h_stream)
+                keep.append((xc, lpc, xsc))
+            ev_main, ev_d2h = torch.cuda.Event(), torch.cuda.Event()
+            ev_main.record(stream)
+            ev_d2h.record(d2h_stream)
+            in_flight.append((keep, ev_main, ev_d2h))
 
-        e2e_step()
+        for _ in range(3):
+            e2e_step()
+        stream.wait_stream(d2h_stream)
         sync_all()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record(stream)
         for _ in range(e2e_steps):
             e2e_step()
+        stream.wait_stream(d2h_stream)         # the last step's results are in host memory
         t1.record(stream)
         sync_all()
         e2e_ms = t0.elapsed_time(t1) / e2e_steps
+        gc.enable()
         sampler.stop_flag = True           # clocks were sampled across the device-resident, fast-mode and e2e regions
         sampler.join(timeout=3)
 

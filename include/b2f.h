@@ -139,6 +139,15 @@ int b2f_debug_umma_gemm(const float *A, const float *B, float *C, int32_t N, int
 const char *b2f_last_error(void);
 int32_t b2f_abi_version(void);
 
+/* Diagnostics: which kernel the calling thread's last successful b2f_flow_apply launched (the dispatch is by program
+ * shape, see DESIGN.md "Kernels"): the generic FP32 kernel (csrc/b2f_flow.cu), the tcgen05 kernel (csrc/b2f_flow_tc.cu)
+ * or the row-per-thread kernel (csrc/b2f_flow_rows.cu).  No reference counterpart. */
+#define B2F_KERNEL_NONE 0
+#define B2F_KERNEL_GENERIC 1
+#define B2F_KERNEL_TC 2
+#define B2F_KERNEL_ROWS 3
+int32_t b2f_last_flow_kernel(void);
+
 #ifdef __cplusplus
 }
 #endif

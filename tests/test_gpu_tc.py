@@ -66,12 +66,18 @@ def test_tensor_core_flow_matches_generic_kernel_and_oracle(preset, D, B):
     g = torch.Generator().manual_seed(B)
     x, z = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
     os.environ.pop('B2F_DISABLE_TC', None)
-    tc = _lp_and_sample(flow, x.to(dev), z.to(dev))
-    os.environ['B2F_DISABLE_TC'] = '1'
+    os.environ['B2F_DISABLE_ROWS'] = '1'       # affine / shift presets would otherwise take the row-per-thread kernel
     try:
+        from torchflows_b200 import _native as N_
+        tc = _lp_and_sample(flow, x.to(dev), z.to(dev))
+        if preset not in ('MAF', 'IAF', 'MaskedAutoregressiveRQNSF'):      # their sampling pass is sequential: generic
+            assert N_.last_flow_kernel() == N_.KERNEL_TC
+        os.environ['B2F_DISABLE_TC'] = '1'
         gen = _lp_and_sample(flow, x.to(dev), z.to(dev))
+        assert N_.last_flow_kernel() == N_.KERNEL_GENERIC
     finally:
         os.environ.pop('B2F_DISABLE_TC', None)
+        os.environ.pop('B2F_DISABLE_ROWS', None)
     names = ('log_prob', 'z', 'log_det', 'sample', 'sample log_prob')
     for a, b, n in zip(tc, gen, names):
         a, b = a.double().cpu(), b.double().cpu()

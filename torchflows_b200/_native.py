@@ -20,6 +20,7 @@ FLAG_TC_FLIPPED = 4
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 FLOW_MODE_FAST_KNOTS = 4
+KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS = range(4)
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
                 T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}
@@ -49,6 +50,7 @@ def lib():
         vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
         L.b2f_last_error.restype = ctypes.c_char_p
         L.b2f_abi_version.restype = i32
+        L.b2f_last_flow_kernel.restype = i32
         L.b2f_params_per_element.argtypes = [i32, i32]
         L.b2f_padded_params.argtypes = [i32]
         L.b2f_flow_apply.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
@@ -141,6 +143,11 @@ def transformer_backward(tkind, x2, h, h_row_stride, gout, gld, n_bins=8, bounda
         check(lib().b2f_transformer_backward(tkind, ptr(x2), ptr(h), ptr(gout), ptr(gld), ptr(gx), ptr(gh), n_rows, E,
                                              h_row_stride, n_bins, boundary, flags, stream_ptr(x2.device)))
     return gx, gh
+
+
+def last_flow_kernel() -> int:
+    """Which kernel this thread's last flow_apply launched (KERNEL_GENERIC / KERNEL_TC / KERNEL_ROWS)."""
+    return int(lib().b2f_last_flow_kernel())
 
 
 def column_stats(x2: torch.Tensor):

@@ -9,6 +9,7 @@
 namespace b2f {
 
 char* last_error_buffer();   // thread-local, defined in b2f_api.cu
+int& last_flow_kernel();     // thread-local, which kernel b2f_flow_apply launched last (B2F_KERNEL_*)
 
 inline int fail(int code, const char* fmt, ...) {
     va_list ap;

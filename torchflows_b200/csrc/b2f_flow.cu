@@ -226,6 +226,7 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
             const bool tc = has_rq ? attempt == 0 : attempt == 1;
             const int rc = tc ? try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream)
                               : try_launch_flow_rows(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream);
+            if (rc == 1) last_flow_kernel() = tc ? B2F_KERNEL_TC : B2F_KERNEL_ROWS;
             if (rc != 0) return rc == 1 ? B2F_OK : rc;
         }
     }
@@ -291,5 +292,6 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+    last_flow_kernel() = B2F_KERNEL_GENERIC;
     return check_launch("b2f_flow_apply");
 }

@@ -52,7 +52,7 @@ struct BTile {
     float* dhp;   // [WPG][TM][HS] per-slot partial sums of dhid (a warp owns its (slot, 32 samples) slice: no atomics)
     float* GL;    // [TM]     dL/dlog_det of each sample (constant through the layers)
     float* dhs;   // [NW][32][PPmax] per-warp staging of dL/dh for the weight-gradient product
-    int rows;
+    int rows, rotate;
 };
 
 template <int TK, int MODE, int P, int PP>
@@ -92,7 +92,7 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
     for (int j = 0; j < H; ++j) dhp_m[j] = 0.0f;
     // every CTA walks the elements in its own rotation so that concurrent CTAs add into different weight gradients
     const int n_it = (n_tgt + t.WPG - 1) / t.WPG;
-    const int rot = (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)n_it);
+    const int rot = b.rotate ? (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)n_it) : 0;
     for (int it = 0; it < n_it; ++it) {
         int ii = it + rot; if (ii >= n_it) ii -= n_it;
         const int e = slot + ii * t.WPG;
@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
     const long long row0 = (long long)blockIdx.x * TM;
     const int rows = (int)min((long long)TM, A.B - row0);
     b.rows = rows;
+    b.rotate = A.flags & 0x100;
 
     for (int m = warp; m < TM; m += NW) {
         float* dst = t.xt + m * XS;
@@ -520,6 +521,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
         }
     }
     A.n_ops = n_ops; A.D = D; A.B = B; A.flags = flags;
+    if (getenv("B2F_BWD_ROT")) A.flags |= 0x100;
     A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     A.gx = gx; A.ws = (float*)workspace;
     A.XS = D | 1; A.HS = Hmax | 1;
