@@ -52,7 +52,7 @@ struct BTile {
     float* dhp;   // [WPG][TM][HS] per-slot partial sums of dhid (a warp owns its (slot, 32 samples) slice: no atomics)
     float* GL;    // [TM]     dL/dlog_det of each sample (constant through the layers)
     float* dhs;   // [NW][32][PPmax] per-warp staging of dL/dh for the weight-gradient product
-    int rows, rotate;
+    int rows, precise;
 };
 
 template <int TK, int MODE, int P, int PP>
@@ -90,13 +90,7 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
     const bool want_w = op.g2 != nullptr;
     float* dhp_m = b.dhp + ((size_t)slot * t.TM + m) * t.HS;
     for (int j = 0; j < H; ++j) dhp_m[j] = 0.0f;
-    // every CTA walks the elements in its own rotation so that concurrent CTAs add into different weight gradients
-    const int n_it = (n_tgt + t.WPG - 1) / t.WPG;
-    const int rot = b.rotate ? (int)((blockIdx.x * 2654435761u >> 8) % (unsigned)n_it) : 0;
-    for (int it = 0; it < n_it; ++it) {
-        int ii = it + rot; if (ii >= n_it) ii -= n_it;
-        const int e = slot + ii * t.WPG;
-        if (e >= n_tgt) continue;
+    for (int e = slot; e < n_tgt; e += t.WPG) {
         const float* w2e = op.f.p2 + (size_t)e * H * PP;
         float acc[PP], dh[PP];
         element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)e * P, hid_m, H);
@@ -133,6 +127,162 @@ __device__ __forceinline__ void transform_pass_backward(const BTile& b, const Bw
             }
         }
     }
+}
+
+// ---- the same layer with its two batch-sized contractions on the tensor cores (spline layers, default arithmetic) ------
+// Per warp (32 samples) and target element e, with dh[row][p] the transformer's parameter gradient (P = 23, padded 24):
+//   dL/dW2[e][j][p] = sum_row hid[row][j] * dh[row][p]   (+ a constant-1 hidden row H for dL/db2[e][p])
+//   dL/dhid[row][j] = sum_p   dh[row][p]  * W2[e][j][p]
+// are [H+1 x 32] x [32 x 24] and [32 x 24] x [24 x H] products: mma.sync.m16n8k8 TF32 with fp32 accumulation, as the
+// 3xTF32 split  a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (a_hi = the operand's upper 19 bits, which is what the tensor
+// core reads from an fp32 register anyway; a_lo = a - a_hi, exact) -- fp32-faithful to ~2^-21, so the gradients keep the
+// accuracy of the FFMA path above (`precise` mode and H > 31 still take that path).  dh goes through the per-warp staging
+// buffer dhs[32][24] to reach the fragment layouts; the hid fragments are loaded once per layer; the dL/dhid accumulators
+// live in registers across all elements of the warp.
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x); }       // hardware ignores the low 13 bits
+__device__ __forceinline__ uint32_t tf32_lo(float x) {
+    return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+__device__ __forceinline__ void mma3_tf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                          uint32_t bh1, uint32_t bl0, uint32_t bl1);
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void mma3_tf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                          uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+    mma_tf32(d, al, bh0, bh1);
+    mma_tf32(d, ah, bl0, bl1);
+    mma_tf32(d, ah, bh0, bh1);
+}
+
+// MT = ceil((H+1)/16) row tiles of dL/dW2^T, NT2 = ceil(H/8) column tiles of dL/dhid
+template <int TK, int MODE, int MT, int NT2>
+__device__ __forceinline__ void transform_pass_backward_mma(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
+    constexpr int P = TInfo<TK>::P, PP = TInfo<TK>::PP;
+    static_assert(PP == 24, "spline layers only");
+    const Tile& t = b.t;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = warp % t.G, slot = warp / t.G;
+    const int m = g * 32 + lane, H = op.f.H;
+    const int gq = lane >> 2, tq = lane & 3;
+    const float* hid_m = t.hid + m * t.HS;
+    const float* hid_g = t.hid + (g * 32) * t.HS;
+    float* dhs = b.dhs + warp * 32 * PP;
+    const float GLm = b.GL[m];
+    const bool want_w = op.g2 != nullptr;
+
+    // A fragments of dL/dW2^T = hid^T (rows j, columns = the warp's 32 samples), row H = 1 (bias), rows > H = 0
+    float a1[MT][4][4];
+    {
+        auto hv = [&](int row, int j) { return j < H ? hid_g[row * t.HS + j] : (j == H ? 1.0f : 0.0f); };
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                a1[mt][ks][0] = hv(8 * ks + tq, 16 * mt + gq);
+                a1[mt][ks][1] = hv(8 * ks + tq, 16 * mt + gq + 8);
+                a1[mt][ks][2] = hv(8 * ks + tq + 4, 16 * mt + gq);
+                a1[mt][ks][3] = hv(8 * ks + tq + 4, 16 * mt + gq + 8);
+            }
+    }
+    float acc2[2][NT2][4];        // dL/dhid of the warp's 32 samples, summed over this warp's elements
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc2[mt][nt][i] = 0.0f;
+
+    for (int e = slot; e < n_tgt; e += t.WPG) {
+        const float* w2e = op.f.p2 + (size_t)e * H * PP;
+        {
+            float acc[PP], dh[PP];
+            element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)e * P, hid_m, H);
+            const int c = t.col(t0 + e);
+            float dv;
+            transformer_backward_element<TK, MODE, P, PP>(t.xt[m * t.XS + c], acc, op.f.boundary, b.gt[m * t.XS + c], GLm,
+                                                          dv, dh);
+            b.gt[m * t.XS + c] = dv;
+            __syncwarp();
+            float4* drow = reinterpret_cast<float4*>(dhs + lane * PP);
+#pragma unroll
+            for (int q = 0; q < PP / 4; ++q) drow[q] = make_float4(dh[4 * q], dh[4 * q + 1], dh[4 * q + 2], dh[4 * q + 3]);
+            __syncwarp();
+        }
+        // dL/dhid += dh [32 x 24] * W2[e]^T [24 x H]
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+            uint32_t a2h[2][4], a2l[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* r0 = dhs + (16 * mt + gq) * PP + 8 * ks + tq;
+                const float v[4] = {r0[0], r0[8 * PP], r0[4], r0[8 * PP + 4]};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a2h[mt][i] = tf32_hi(v[i]); a2l[mt][i] = tf32_lo(v[i]); }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT2; ++nt) {
+                const int j = 8 * nt + gq;
+                const float* wj = w2e + j * PP + 8 * ks + tq;
+                const float w0 = j < H ? __ldg(wj) : 0.0f, w1 = j < H ? __ldg(wj + 4) : 0.0f;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    mma3_tf32(acc2[mt][nt], a2h[mt], a2l[mt], tf32_hi(w0), tf32_hi(w1), tf32_lo(w0), tf32_lo(w1));
+            }
+        }
+        if (want_w) {
+            // dL/dW2[e]^T (+ bias row) = hid^T [H+1 x 32] * dh [32 x 24]
+            float acc1[MT][3][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc1[mt][nt][i] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt) {
+                    const float* r0 = dhs + (8 * ks + tq) * PP + 8 * nt + gq;
+                    const float d0 = r0[0], d1 = r0[4 * PP];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint32_t ah[4], al[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { ah[i] = tf32_hi(a1[mt][ks][i]); al[i] = tf32_lo(a1[mt][ks][i]); }
+                        mma3_tf32(acc1[mt][nt], ah, al, tf32_hi(d0), tf32_hi(d1), tf32_lo(d0), tf32_lo(d1));
+                    }
+                }
+            float* g2e = op.g2 + (size_t)e * H * PP;
+            float* g3e = op.g3 + (size_t)e * P;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = 16 * mt + gq + ((i & 2) ? 8 : 0), p = 8 * nt + 2 * tq + (i & 1);
+                        if (p < P) {
+                            if (j < H) atomicAdd(g2e + j * PP + p, acc1[mt][nt][i]);
+                            else if (j == H) atomicAdd(g3e + p, acc1[mt][nt][i]);
+                        }
+                    }
+        }
+    }
+    // this warp's partial of dL/dhid: (slot, sample, j) has exactly one owner lane, no atomics
+    float* dhp = b.dhp + ((size_t)slot * t.TM + g * 32) * t.HS;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT2; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = 16 * mt + gq + ((i & 2) ? 8 : 0), j = 8 * nt + 2 * tq + (i & 1);
+                if (j < H) dhp[row * t.HS + j] = acc2[mt][nt][i];
+            }
 }
 
 // Backward of the D-step sequential direction x_i = T(z_i; h_i(x_0..x_{i-1})) (layers_base.py:213-223).  A thread owns
@@ -206,6 +356,16 @@ __device__ __forceinline__ void sequential_pass_backward(const BTile& b, const B
     }
 }
 
+template <int TK, int MODE>
+__device__ __forceinline__ void transform_pass_backward_rq(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
+    const int H = op.f.H;
+    if (b.precise || H > 31) transform_pass_backward<TK, MODE>(b, op, t0, n_tgt);
+    else if (H <= 7) transform_pass_backward_mma<TK, MODE, 1, 1>(b, op, t0, n_tgt);
+    else if (H <= 15) transform_pass_backward_mma<TK, MODE, 1, 2>(b, op, t0, n_tgt);
+    else if (H <= 23) transform_pass_backward_mma<TK, MODE, 2, 3>(b, op, t0, n_tgt);
+    else transform_pass_backward_mma<TK, MODE, 2, 4>(b, op, t0, n_tgt);
+}
+
 template <int MODE>
 __device__ __forceinline__ void run_transform_backward(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
     switch (op.f.tkind) {
@@ -213,8 +373,8 @@ __device__ __forceinline__ void run_transform_backward(const BTile& b, const Bwd
         case B2F_T_SHIFT_SUB: transform_pass_backward<B2F_T_SHIFT_SUB, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_AFFINE_FWD: transform_pass_backward<B2F_T_AFFINE_FWD, MODE>(b, op, t0, n_tgt); break;
         case B2F_T_AFFINE_INV: transform_pass_backward<B2F_T_AFFINE_INV, MODE>(b, op, t0, n_tgt); break;
-        case B2F_T_RQ_FWD: transform_pass_backward<B2F_T_RQ_FWD, MODE>(b, op, t0, n_tgt); break;
-        case B2F_T_RQ_INV: transform_pass_backward<B2F_T_RQ_INV, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_RQ_FWD: transform_pass_backward_rq<B2F_T_RQ_FWD, MODE>(b, op, t0, n_tgt); break;
+        case B2F_T_RQ_INV: transform_pass_backward_rq<B2F_T_RQ_INV, MODE>(b, op, t0, n_tgt); break;
         default: break;
     }
 }
@@ -272,12 +432,12 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
     t.ldp = b.dhid + TM * HS;              // [WPG][TM] (written by the forward recompute, unused)
     b.GL = t.ldp + A.WPG * TM;             // [TM]
     float* ea = b.GL + TM;                 // [3*D]
-    b.dhs = ea + 3 * D;                    // [NW][32][24]
+    b.dhs = ea + ((3 * D + 3) & ~3);       // [NW][32][24], 16-byte aligned
     b.dhp = b.dhs + NW * 32 * 24;          // [WPG][TM][HS]
     const long long row0 = (long long)blockIdx.x * TM;
     const int rows = (int)min((long long)TM, A.B - row0);
     b.rows = rows;
-    b.rotate = A.flags & 0x100;
+    b.precise = A.flags & B2F_FLOW_MODE_PRECISE;
 
     for (int m = warp; m < TM; m += NW) {
         float* dst = t.xt + m * XS;
@@ -521,7 +681,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
         }
     }
     A.n_ops = n_ops; A.D = D; A.B = B; A.flags = flags;
-    if (getenv("B2F_BWD_ROT")) A.flags |= 0x100;
+    if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
     A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     A.gx = gx; A.ws = (float*)workspace;
     A.XS = D | 1; A.HS = Hmax | 1;
@@ -531,7 +691,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     auto smem_bytes = [&](int tm, int nt) {
         const int wpg = (nt / 32) / (tm / 32);
         return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + (2 + (size_t)wpg) * tm * A.HS + (size_t)wpg * tm + tm +
-                                        3 * D + (size_t)(nt / 32) * 32 * 24 + 4);
+                                        ((3 * D + 3) & ~3) + (size_t)(nt / 32) * 32 * 24 + 4);
     };
     while (TM > 32 && smem_bytes(TM, NT) > 200 * 1024) TM >>= 1;
     if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 256 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
