@@ -419,6 +419,11 @@ __device__ __forceinline__ void run_transform_forward(const Tile& t, const DevOp
 template <int MODE>
 __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constant__ BwdArgs A) {
     extern __shared__ __align__(16) float smem[];
+    long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
+    if ((A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+    }
     BTile b;
     Tile& t = b.t;
     t.D = A.D; t.TM = A.TM; t.logTM = A.logTM; t.XS = A.XS; t.HS = A.HS; t.WPG = A.WPG; t.G = A.G; t.flip = 0;
@@ -602,6 +607,12 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         for (int m = warp; m < rows; m += NW)
             for (int j = lane; j < D; j += 32) A.gx[(row0 + m) * D + j] = b.gt[m * XS + t.col(j)];
     }
+    if ((A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        const long long c1 = clock64();
+        printf("[bwd dbg] block %d: %lld cycles, %llu ns, start at %llu ns\n", blockIdx.x, c1 - dbg_c0, t1 - dbg_t0, dbg_t0);
+    }
 }
 
 static int ilog2b(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
@@ -682,6 +693,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     }
     A.n_ops = n_ops; A.D = D; A.B = B; A.flags = flags;
     if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
+    if (getenv("B2F_BWD_DEBUG_CLOCK")) A.flags |= 0x200;
     A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     A.gx = gx; A.ws = (float*)workspace;
     A.XS = D | 1; A.HS = Hmax | 1;
