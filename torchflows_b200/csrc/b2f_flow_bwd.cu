@@ -33,7 +33,7 @@ struct BwdOp {
 
 struct BwdArgs {
     BwdOp ops[B2F_MAX_OPS];
-    int n_ops, D, TM, logTM, XS, HS, WPG, G, flags;
+    int n_ops, D, TM, logTM, XS, HS, WPG, G, flags, wst_stride;
     long long B;
     const float* x;
     const float* gy;
@@ -52,7 +52,8 @@ struct BTile {
     float* dhp;   // [WPG][TM][HS] per-slot partial sums of dhid (a warp owns its (slot, 32 samples) slice: no atomics)
     float* GL;    // [TM]     dL/dlog_det of each sample (constant through the layers)
     float* dhs;   // [NW][32][PPmax] per-warp staging of dL/dh for the weight-gradient product
-    int rows, precise;
+    float* wst;   // [NW][2][wst_stride] per-warp double buffer of one element's output-layer weights (spline layers)
+    int rows, precise, wst_stride;
 };
 
 template <int TK, int MODE, int P, int PP>
@@ -196,11 +197,32 @@ __device__ __forceinline__ void transform_pass_backward_mma(const BTile& b, cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc2[mt][nt][i] = 0.0f;
 
-    for (int e = slot; e < n_tgt; e += t.WPG) {
-        const float* w2e = op.f.p2 + (size_t)e * H * PP;
+    // W2[e] (H x 24 floats) + b2[e] of the NEXT element travel global -> shared (cp.async) behind the current element's
+    // math: with 8 warps per SM every weight load from L2 would otherwise be an exposed round trip (the j-loop of the
+    // output layer alone is H dependent ones)
+    float* wbuf[2] = {b.wst + (size_t)(2 * warp) * b.wst_stride, b.wst + (size_t)(2 * warp + 1) * b.wst_stride};
+    auto stage = [&](int e, float* dst) {
+        const float4* src = reinterpret_cast<const float4*>(op.f.p2 + (size_t)e * H * PP);
+        for (int q = lane; q < H * (PP / 4); q += 32) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + q) : "memory");
+        }
+        if (lane < P) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + H * PP + lane);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(op.f.p3 + (size_t)e * P + lane) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if (slot < n_tgt) stage(slot, wbuf[0]);
+    for (int e = slot; e < n_tgt; e += t.WPG, cur ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                  // this element's weights have landed; everyone is done with the other buffer
+        const float* w2e = wbuf[cur];
+        if (e + t.WPG < n_tgt) stage(e + t.WPG, wbuf[cur ^ 1]);
         {
             float acc[PP], dh[PP];
-            element_params<P, PP>(acc, w2e, op.f.p3 + (size_t)e * P, hid_m, H);
+            element_params<P, PP, false>(acc, w2e, w2e + H * PP, hid_m, H);
             const int c = t.col(t0 + e);
             float dv;
             transformer_backward_element<TK, MODE, P, PP>(t.xt[m * t.XS + c], acc, op.f.boundary, b.gt[m * t.XS + c], GLm,
@@ -227,7 +249,7 @@ __device__ __forceinline__ void transform_pass_backward_mma(const BTile& b, cons
             for (int nt = 0; nt < NT2; ++nt) {
                 const int j = 8 * nt + gq;
                 const float* wj = w2e + j * PP + 8 * ks + tq;
-                const float w0 = j < H ? __ldg(wj) : 0.0f, w1 = j < H ? __ldg(wj + 4) : 0.0f;
+                const float w0 = j < H ? wj[0] : 0.0f, w1 = j < H ? wj[4] : 0.0f;
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt)
                     mma3_tf32(acc2[mt][nt], a2h[mt], a2l[mt], tf32_hi(w0), tf32_hi(w1), tf32_lo(w0), tf32_lo(w1));
@@ -359,7 +381,7 @@ __device__ __forceinline__ void sequential_pass_backward(const BTile& b, const B
 template <int TK, int MODE>
 __device__ __forceinline__ void transform_pass_backward_rq(const BTile& b, const BwdOp& op, int t0, int n_tgt) {
     const int H = op.f.H;
-    if (b.precise || H > 31) transform_pass_backward<TK, MODE>(b, op, t0, n_tgt);
+    if (b.precise || H > 31 || b.wst_stride == 0) transform_pass_backward<TK, MODE>(b, op, t0, n_tgt);
     else if (H <= 7) transform_pass_backward_mma<TK, MODE, 1, 1>(b, op, t0, n_tgt);
     else if (H <= 15) transform_pass_backward_mma<TK, MODE, 1, 2>(b, op, t0, n_tgt);
     else if (H <= 23) transform_pass_backward_mma<TK, MODE, 2, 3>(b, op, t0, n_tgt);
@@ -417,7 +439,7 @@ __device__ __forceinline__ void run_transform_forward(const Tile& t, const DevOp
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constant__ BwdArgs A) {
+__global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constant__ BwdArgs A) {
     extern __shared__ __align__(16) float smem[];
     long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
     if ((A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0) {
@@ -439,6 +461,8 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
     float* ea = b.GL + TM;                 // [3*D]
     b.dhs = ea + ((3 * D + 3) & ~3);       // [NW][32][24], 16-byte aligned
     b.dhp = b.dhs + NW * 32 * 24;          // [WPG][TM][HS]
+    b.wst = b.dhp + ((A.WPG * TM * HS + 3) & ~3);
+    b.wst_stride = A.wst_stride;
     const long long row0 = (long long)blockIdx.x * TM;
     const int rows = (int)min((long long)TM, A.B - row0);
     b.rows = rows;
@@ -478,6 +502,9 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         __syncthreads();
     }
 
+    long long dbg_cA = 0, dbg_cT = 0, dbg_cH = 0, dbg_cR = 0;
+    const bool dbg = (A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0;
+    if (dbg) dbg_cA = clock64();
     // ---- gradient seed: dL/dz = gy + glp * d base_logp / dz ;  dL/dlog_det = gld + glp ------------------
     for (int m = warp; m < TM; m += NW) {
         const bool live = m < rows;
@@ -565,10 +592,14 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         __syncthreads();
         const bool coupling = op.f.kind == B2F_OP_COUPLING;
         const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0, H = op.f.H;
+        long long c_a = 0, c_b = 0, c_c = 0;
+        if (dbg) c_a = clock64();
         hidden_layer<true>(t, op.f, n_src);
         __syncthreads();
+        if (dbg) c_b = clock64();
         run_transform_backward<MODE>(b, op, t0, D - t0);
         __syncthreads();
+        if (dbg) { c_c = clock64(); dbg_cH += c_b - c_a; dbg_cT += c_c - c_b; dbg_cR -= c_c; }
         // tanh': dpre = dhid * (1 - hid^2)
         for (int idx = tid; idx < (H << t.logTM); idx += NT) {
             const int m = idx & (TM - 1), j = idx >> t.logTM;
@@ -611,7 +642,8 @@ __global__ void __launch_bounds__(256) flow_backward_kernel(const __grid_constan
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         const long long c1 = clock64();
-        printf("[bwd dbg] block %d: %lld cycles, %llu ns, start at %llu ns\n", blockIdx.x, c1 - dbg_c0, t1 - dbg_t0, dbg_t0);
+        printf("[bwd dbg] block %d: %lld cycles, %llu ns, start at %llu ns; phase A %lld, hidden recompute (B) %lld, transform backward %lld\n",
+               blockIdx.x, c1 - dbg_c0, t1 - dbg_t0, dbg_t0, dbg_cA - dbg_c0, dbg_cH, dbg_cT);
     }
 }
 
@@ -692,21 +724,36 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
         }
     }
     A.n_ops = n_ops; A.D = D; A.B = B; A.flags = flags;
-    if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
-    if (getenv("B2F_BWD_DEBUG_CLOCK")) A.flags |= 0x200;
     A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     A.gx = gx; A.ws = (float*)workspace;
     A.XS = D | 1; A.HS = Hmax | 1;
-    int TM = 64, NT = 256;
+    if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
+    if (getenv("B2F_BWD_DEBUG_CLOCK")) A.flags |= 0x200;
+    // spline one-pass layers: per-warp double buffer for one element's output-layer weights (tensor-core path)
+    int Hrq = 0;
+    bool rq_aligned = true;
+    for (int i = 0; i < n_ops; ++i) {
+        const b2f_op_t& o = ops[i];
+        if ((o.kind == B2F_OP_COUPLING || o.kind == B2F_OP_MADE) && (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV) &&
+            o.n_hidden <= 31) {
+            Hrq = std::max(Hrq, o.n_hidden);
+            if (reinterpret_cast<uintptr_t>(o.p[2]) & 15) rq_aligned = false;
+        }
+    }
+    A.wst_stride = (Hrq > 0 && rq_aligned && !(A.flags & B2F_FLOW_MODE_PRECISE)) ? ((Hrq * 24 + 24 + 3) & ~3) : 0;
+    // spline programs: 12 warps on one 32-row tile (the kernel is latency-bound: measured 10.4 ms against 11.6 ms for
+    // 8 warps on 64 rows, CouplingRQNSF-256, 131072 rows); everything else: 8 warps on 64 rows
+    int TM = A.wst_stride ? 32 : 64, NT = A.wst_stride ? 384 : 256;
     if (const char* e = getenv("B2F_BWD_TM")) TM = atoi(e);
     if (const char* e = getenv("B2F_BWD_NT")) NT = atoi(e);
     auto smem_bytes = [&](int tm, int nt) {
         const int wpg = (nt / 32) / (tm / 32);
-        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + (2 + (size_t)wpg) * tm * A.HS + (size_t)wpg * tm + tm +
-                                        ((3 * D + 3) & ~3) + (size_t)(nt / 32) * 32 * 24 + 4);
+        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + 2 * (size_t)tm * A.HS + (((size_t)wpg * tm * A.HS + 3) & ~3) +
+                                        (size_t)wpg * tm + tm + ((3 * D + 3) & ~3) + (size_t)(nt / 32) * 32 * 24 +
+                                        (size_t)(nt / 32) * 2 * A.wst_stride + 4);
     };
     while (TM > 32 && smem_bytes(TM, NT) > 200 * 1024) TM >>= 1;
-    if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 256 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
+    if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 384 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
         return fail(B2F_ERR_INVALID, "b2f_flow_backward: bad tile shape TM=%d NT=%d", TM, NT);
     const size_t smem = smem_bytes(TM, NT);
     if (smem > 227 * 1024) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: D=%d H=%d does not fit shared memory", D, Hmax);

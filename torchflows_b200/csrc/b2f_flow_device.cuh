@@ -25,18 +25,22 @@ template <> struct TInfo<B2F_T_RQ_INV> { static constexpr int P = 23, PP = 24; }
 
 // transformer parameters of one element from the hidden activations of this thread's sample:
 // acc[p] = b2[e*P+p] + sum_j W2tile[e][j][p] * hid[j]          (transforms.py:297-300, last Linear)
-template <int P, int PP>
+template <int P, int PP, bool GLOBAL = true>
 __device__ __forceinline__ void element_params(float (&acc)[PP], const float* __restrict__ w2e,
                                                const float* __restrict__ b2e, const float* hid_m, int H) {
+    // GLOBAL: the weights are read through the read-only path (ld.global.nc); otherwise they sit in shared memory
+    auto ld1 = [](const float* q) { if constexpr (GLOBAL) return __ldg(q); else return *q; };
+    auto ld2 = [](const float2* q) { if constexpr (GLOBAL) return __ldg(q); else return *q; };
+    auto ld4 = [](const float4* q) { if constexpr (GLOBAL) return __ldg(q); else return *q; };
 #pragma unroll
-    for (int p = 0; p < PP; ++p) acc[p] = (p < P) ? __ldg(b2e + p) : 0.0f;
+    for (int p = 0; p < PP; ++p) acc[p] = (p < P) ? ld1(b2e + p) : 0.0f;
     if constexpr (PP % 4 == 0) {
         const float4* w = reinterpret_cast<const float4*>(w2e);
         for (int j = 0; j < H; ++j) {
             const float hj = hid_m[j];
 #pragma unroll
             for (int c = 0; c < PP / 4; ++c) {
-                const float4 wv = __ldg(w + j * (PP / 4) + c);
+                const float4 wv = ld4(w + j * (PP / 4) + c);
                 acc[4 * c + 0] = fmaf(wv.x, hj, acc[4 * c + 0]);
                 acc[4 * c + 1] = fmaf(wv.y, hj, acc[4 * c + 1]);
                 acc[4 * c + 2] = fmaf(wv.z, hj, acc[4 * c + 2]);
@@ -47,12 +51,12 @@ __device__ __forceinline__ void element_params(float (&acc)[PP], const float* __
         const float2* w = reinterpret_cast<const float2*>(w2e);
         for (int j = 0; j < H; ++j) {
             const float hj = hid_m[j];
-            const float2 wv = __ldg(w + j);
+            const float2 wv = ld2(w + j);
             acc[0] = fmaf(wv.x, hj, acc[0]);
             acc[1] = fmaf(wv.y, hj, acc[1]);
         }
     } else {
-        for (int j = 0; j < H; ++j) acc[0] = fmaf(__ldg(w2e + j), hid_m[j], acc[0]);
+        for (int j = 0; j < H; ++j) acc[0] = fmaf(ld1(w2e + j), hid_m[j], acc[0]);
     }
 }
 
