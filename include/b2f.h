@@ -99,6 +99,18 @@ int b2f_flow_apply(const b2f_op_t *ops, int32_t n_ops, const float *x, float *y,
                    const float *base_loc, const float *base_log_scale, int64_t B, int32_t D, int32_t flags,
                    void *stream);
 
+/* b2f_flow_apply for a training step: additionally writes, for every COUPLING / MADE / MADE_SEQ op in order, the
+ * activations as they ENTER that layer into `workspace` ([layer][B][D] floats, b2f_flow_backward_workspace() bytes) --
+ * exactly what b2f_flow_backward would otherwise recompute.  *saved = 1 if the kernel that took the program wrote them
+ * (today: the tensor-core kernel), 0 if not (the call is then identical to b2f_flow_apply and `workspace` is untouched).
+ * With *saved == 1 call b2f_flow_backward with B2F_FLOW_WS_FILLED, the same workspace and x = the OUTPUT y of this call.
+ * Replaces the activations torch autograd keeps alive for backward (flows.py:199-224). */
+int b2f_flow_apply_saving(const b2f_op_t *ops, int32_t n_ops, const float *x, float *y, float *log_det, float *log_prob,
+                          const float *base_loc, const float *base_log_scale, void *workspace, int32_t *saved, int64_t B,
+                          int32_t D, int32_t flags, void *stream);
+#define B2F_FLOW_WS_FILLED 8 /* b2f_flow_backward: `workspace` already holds the layer inputs (b2f_flow_apply_saving) and
+                                `x` is the forward OUTPUT; the forward recompute is skipped */
+
 /* Backward of b2f_flow_apply in the density direction: given the saved input x and upstream gradients
  * gy:(B,D) (nullable), glog_det:(B) (nullable), glog_prob:(B) (nullable), recomputes the forward per tile and
  * produces gx:(B,D) (nullable) and accumulates parameter gradients into ops[i].g[].  Replaces autograd

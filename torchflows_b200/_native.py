@@ -20,6 +20,7 @@ FLAG_TC_FLIPPED = 4
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 FLOW_MODE_FAST_KNOTS = 4
+FLOW_WS_FILLED = 8
 KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS = range(4)
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
@@ -54,6 +55,8 @@ def lib():
         L.b2f_params_per_element.argtypes = [i32, i32]
         L.b2f_padded_params.argtypes = [i32]
         L.b2f_flow_apply.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+        L.b2f_flow_apply_saving.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, vp, ctypes.POINTER(i32), i64,
+                                            i32, i32, vp]
         L.b2f_flow_backward.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
         L.b2f_flow_backward_workspace.argtypes = [ctypes.POINTER(Op), i32, i64, i32]
         L.b2f_flow_backward_workspace.restype = i64
@@ -105,8 +108,10 @@ def make_ops(ops: Sequence[dict]):
 
 
 def flow_apply(ops: Sequence[dict], x: torch.Tensor, want_y=True, want_log_det=True, want_log_prob=False,
-               base_loc=None, base_log_scale=None, flags=0):
-    """x: (B, D) CUDA fp32 contiguous.  Returns (y | None, log_det | None, log_prob | None)."""
+               base_loc=None, base_log_scale=None, flags=0, save_layer_inputs=False):
+    """x: (B, D) CUDA fp32 contiguous.  Returns (y | None, log_det | None, log_prob | None); with save_layer_inputs a fourth
+    item: the workspace holding every conditioner layer's input for flow_backward (None if the kernel that ran cannot
+    save them -- b2f_flow_apply_saving)."""
     x = require_cuda_f32(x, 'flow input')
     B, D = x.shape
     y = torch.empty_like(x) if want_y else None
@@ -114,9 +119,17 @@ def flow_apply(ops: Sequence[dict], x: torch.Tensor, want_y=True, want_log_det=T
     lp = torch.empty(B, device=x.device, dtype=torch.float32) if want_log_prob else None
     arr = make_ops(ops)
     with torch.cuda.device(x.device):
-        check(lib().b2f_flow_apply(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
-                                   ptr(base_log_scale), B, D, flags, stream_ptr(x.device)))
-    return y, ld, lp
+        if not save_layer_inputs:
+            check(lib().b2f_flow_apply(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
+                                       ptr(base_log_scale), B, D, flags, stream_ptr(x.device)))
+            return y, ld, lp
+        ws_bytes = int(lib().b2f_flow_backward_workspace(arr, len(ops), B, D))
+        ws = torch.empty(max(ws_bytes, 4) // 4, device=x.device, dtype=torch.float32)
+        saved = ctypes.c_int32(0)
+        check(lib().b2f_flow_apply_saving(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
+                                          ptr(base_log_scale), ptr(ws), ctypes.byref(saved), B, D, flags,
+                                          stream_ptr(x.device)))
+    return y, ld, lp, (ws if saved.value else None)
 
 
 def transformer_apply(tkind, x2: torch.Tensor, h: torch.Tensor, h_row_stride: int, n_bins=8, boundary=50.0,

@@ -199,10 +199,13 @@ class FlowFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2, cfg: _Cfg, *leafs):
-        y, ld, lp = N.flow_apply(op_dicts(cfg.ops, D=x2.shape[1]), x2, True, True, cfg.want_log_prob, cfg.base_loc,
-                                 cfg.base_log_scale, cfg.flags)
+        # the forward kernel keeps every conditioner layer's input for the backward kernel when it can (tensor-core
+        # kernel): the backward pass then starts from the output y and skips its own forward recompute
+        y, ld, lp, ws = N.flow_apply(op_dicts(cfg.ops, D=x2.shape[1]), x2, True, True, cfg.want_log_prob, cfg.base_loc,
+                                     cfg.base_log_scale, cfg.flags, save_layer_inputs=not (cfg.flags & N.FLOW_LOGP_OF_INPUT))
         ctx.cfg = cfg
-        ctx.save_for_backward(x2, *leafs)
+        ctx.ws = ws
+        ctx.save_for_backward(x2 if ws is None else y, *leafs)
         if lp is None:
             lp = x2.new_empty(0)
             ctx.mark_non_differentiable(lp)
@@ -236,8 +239,12 @@ class FlowFunction(torch.autograd.Function):
             grads.append(g)
         B, D = x2.shape
         arr = N.make_ops(op_dicts(ops, grads))
-        ws_bytes = N.lib().b2f_flow_backward_workspace(arr, len(ops), B, D)
-        ws = torch.empty(max(int(ws_bytes), 4) // 4, device=dev, dtype=torch.float32)
+        flags = cfg.flags
+        if ctx.ws is not None:
+            ws, flags = ctx.ws, flags | N.FLOW_WS_FILLED       # x2 is the forward output here
+        else:
+            ws_bytes = N.lib().b2f_flow_backward_workspace(arr, len(ops), B, D)
+            ws = torch.empty(max(int(ws_bytes), 4) // 4, device=dev, dtype=torch.float32)
         need_gx = ctx.needs_input_grad[0]
         gx = torch.empty_like(x2)
 
@@ -247,7 +254,7 @@ class FlowFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             N.check(N.lib().b2f_flow_backward(arr, len(ops), N.ptr(x2), N.ptr(c(gy)), N.ptr(c(gld)), N.ptr(glp_),
                                               N.ptr(cfg.base_loc), N.ptr(cfg.base_log_scale), N.ptr(gx), N.ptr(ws),
-                                              B, D, cfg.flags, N.stream_ptr(dev)))
+                                              B, D, flags, N.stream_ptr(dev)))
         for op, g in zip(ops, grads):
             if op.kind == N.OP_ELEMENTWISE:
                 leaf_grads.append(None if g[0] is None else g[0].reshape(op.leafs[0].shape))

@@ -200,7 +200,7 @@ static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 namespace b2f {
 int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                        const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
-                       void* stream);   // b2f_flow_tc.cu
+                       void* stream, float* ws);   // b2f_flow_tc.cu (ws: optional save area for the layer inputs)
 int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                          const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                          void* stream);  // b2f_flow_rows.cu
@@ -208,9 +208,9 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
 
 using namespace b2f;
 
-extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
-                              float* log_prob, const float* base_loc, const float* base_log_scale, int64_t B,
-                              int32_t D, int32_t flags, void* stream) {
+static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
+                           float* log_prob, const float* base_loc, const float* base_log_scale, int64_t B,
+                           int32_t D, int32_t flags, void* stream, float* ws, int32_t* saved) {
     if (B == 0 && n_ops >= 0 && D > 0) return B2F_OK;      // empty batch: nothing to do (pointers may be null)
     if (!ops || n_ops < 0 || !x || D <= 0 || B < 0) return fail(B2F_ERR_INVALID, "b2f_flow_apply: bad arguments");
     if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: %d ops > B2F_MAX_OPS", n_ops);
@@ -224,9 +224,10 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
             if (ops[i].kind >= B2F_OP_COUPLING && (ops[i].tkind == B2F_T_RQ_FWD || ops[i].tkind == B2F_T_RQ_INV)) has_rq = true;
         for (int attempt = 0; attempt < 2; ++attempt) {
             const bool tc = has_rq ? attempt == 0 : attempt == 1;
-            const int rc = tc ? try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream)
+            const int rc = tc ? try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream, ws)
                               : try_launch_flow_rows(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream);
             if (rc == 1) last_flow_kernel() = tc ? B2F_KERNEL_TC : B2F_KERNEL_ROWS;
+            if (rc == 1 && tc && ws && saved) *saved = 1;
             if (rc != 0) return rc == 1 ? B2F_OK : rc;
         }
     }
@@ -294,4 +295,19 @@ extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x
     kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
     last_flow_kernel() = B2F_KERNEL_GENERIC;
     return check_launch("b2f_flow_apply");
+}
+
+extern "C" int b2f_flow_apply(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
+                              float* log_prob, const float* base_loc, const float* base_log_scale, int64_t B,
+                              int32_t D, int32_t flags, void* stream) {
+    return flow_apply_impl(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream, nullptr, nullptr);
+}
+
+extern "C" int b2f_flow_apply_saving(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det,
+                                     float* log_prob, const float* base_loc, const float* base_log_scale, void* workspace,
+                                     int32_t* saved, int64_t B, int32_t D, int32_t flags, void* stream) {
+    if (!saved) return fail(B2F_ERR_INVALID, "b2f_flow_apply_saving: saved is null");
+    *saved = 0;
+    return flow_apply_impl(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream,
+                           (float*)workspace, saved);
 }

@@ -475,6 +475,12 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
     __syncthreads();
 
     // ---- phase A: forward recompute, saving the input of every conditioner layer ---------------------
+    // (skipped when the forward pass already saved them, B2F_FLOW_WS_FILLED: the tile loaded above is then the flow's
+    //  OUTPUT and only the flip state has to be brought to the end of the program)
+    if (A.flags & B2F_FLOW_WS_FILLED) {
+        for (int oi = 0; oi < A.n_ops; ++oi)
+            if (A.ops[oi].f.kind == B2F_OP_FLIP) t.flip ^= 1;
+    } else
     for (int oi = 0; oi < A.n_ops; ++oi) {
         const BwdOp& op = A.ops[oi];
         if (op.f.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
@@ -727,6 +733,12 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     A.x = x; A.gy = gy; A.gld = glog_det; A.glp = glog_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     A.gx = gx; A.ws = (float*)workspace;
     A.XS = D | 1; A.HS = Hmax | 1;
+    if (flags & B2F_FLOW_WS_FILLED) {
+        int nflip = 0;
+        for (int i = 0; i < n_ops; ++i) nflip += ops[i].kind == B2F_OP_FLIP;
+        if (nflip & 1) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: B2F_FLOW_WS_FILLED needs an even number of FLIP ops");
+        if (!workspace) return fail(B2F_ERR_INVALID, "b2f_flow_backward: B2F_FLOW_WS_FILLED without a workspace");
+    }
     if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
     if (getenv("B2F_BWD_DEBUG_CLOCK")) A.flags |= 0x200;
     // spline one-pass layers: per-warp double buffer for one element's output-layer weights (tensor-core path)

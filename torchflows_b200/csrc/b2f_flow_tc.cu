@@ -63,6 +63,7 @@ struct TcOp {
     const float* b1;            // COUPLING: (32) padded
     const float* w1c;           // canonical [32 x Ds]
     const float* w2c;           // n_chunks x canonical [192 x K2]
+    long long ws_off;           // float offset of this layer's saved input in TcArgs::ws
 };
 
 struct TcArgs {
@@ -75,6 +76,7 @@ struct TcArgs {
     float* log_prob;
     const float* base_loc;
     const float* base_log_scale;
+    float* ws;                  // optional: the tile as it enters every conditioner layer is saved here (training)
 };
 
 struct TcSmem {
@@ -382,6 +384,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const __grid_con
                     continue;
                 }
                 // ---------------- coupling layer ----------------
+                if (A.ws) {      // training: keep this layer's input for b2f_flow_backward (physical column order)
+                    const int m = rg * 8 + r8;
+                    if (m < rows) {
+                        float4* dst = reinterpret_cast<float4*>(A.ws + op.ws_off + (row0 + m) * D);
+                        for (int kc = kq; kc < D / 4; kc += 4)
+                            __stcs(dst + kc, *reinterpret_cast<const float4*>(xaddr(s, Dh, m, 4 * kc)));
+                    }
+                }
                 const uint32_t ph = lc & 1;
                 if (op.x3) {
                     // low parts of the source columns for the 3xTF32 split: x_lo = x - trunc_tf32(x), exact in fp32
@@ -488,13 +498,14 @@ namespace b2f {
 // generic kernel -- same library, same results up to tf32 rounding of the conditioner), < 0 on error.
 int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                        const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
-                       void* stream) {
+                       void* stream, float* ws) {
     if (getenv("B2F_DISABLE_TC")) return 0;
     if (D % 16 != 0 || D < 32 || D > 256) return 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || (y && (reinterpret_cast<uintptr_t>(y) & 15))) return 0;
     int flip = 0, n_coupling = 0, K2max = 8, K1max = D / 2, W2max = 0, any_x3 = 0;
     TcArgs A;
     memset(&A, 0, sizeof(A));
+    long long ws_next = 0;
     for (int i = 0; i < n_ops; ++i) {
         const b2f_op_t& o = ops[i];
         TcOp& t = A.ops[i];
@@ -503,6 +514,8 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
         if (o.kind != B2F_OP_COUPLING && o.kind != B2F_OP_MADE) return 0;
         t.made = o.kind == B2F_OP_MADE;
+        t.ws_off = ws_next;                 // same order and stride as b2f_flow_backward_workspace
+        ws_next += B * (long long)D;
         if (!(o.flags & B2F_FLAG_TC_OPERANDS) || !o.p[4] || !o.p[5] || !o.p[1]) return 0;
         const bool rq = o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV;
         const int Dh_ = D / 2;
@@ -535,6 +548,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
     A.n_ops = n_ops; A.D = D; A.flags = flags; A.B = B;
     A.n_tiles = (int)((B + 127) / 128);
     A.x = x; A.y = y; A.log_det = log_det; A.log_prob = log_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
+    A.ws = ws;
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
