@@ -317,3 +317,39 @@ def test_sequential_direction_gradients(dev):
     xq, lpq = flow_q._sample_from_base(noise.to(dev), return_log_prob=True)
     with pytest.raises(NotImplementedError):
         lpq.mean().backward()
+
+
+def test_backward_from_saved_layer_inputs_matches_recompute():
+    """Training forward on the tensor-core kernel saves every conditioner layer's input (b2f_flow_apply_saving) and the
+    backward kernel starts from the output (B2F_FLOW_WS_FILLED); with B2F_DISABLE_TC=1 the forward is the generic fp32
+    kernel and the backward kernel recomputes the forward itself.  Same gradients up to the tf32 rounding of the
+    tensor-core conditioner."""
+    import os
+    from torchflows_b200 import Flow, _native as N
+    from torchflows_b200.architectures import CouplingRQNSF
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    flow = Flow(CouplingRQNSF(64)).to(dev)
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            if name.endswith('.value'):
+                p.add_(0.2 * torch.randn_like(p))
+    flow.eval()
+    x = torch.randn(777, 64, device=dev)
+    grads = []
+    for disable_tc in (False, True):
+        if disable_tc:
+            os.environ['B2F_DISABLE_TC'] = '1'
+        try:
+            flow.zero_grad(set_to_none=True)
+            xx = x.clone().requires_grad_(True)
+            loss = -flow.log_prob(xx).mean()
+            assert N.last_flow_kernel() == (N.KERNEL_GENERIC if disable_tc else N.KERNEL_TC)
+            loss.backward()
+            grads.append([xx.grad.clone()] + [p.grad.clone() for p in flow.parameters() if p.grad is not None])
+        finally:
+            os.environ.pop('B2F_DISABLE_TC', None)
+    assert len(grads[0]) == len(grads[1]) > 5
+    for a, b in zip(*grads):
+        scale = b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= 5e-3 * scale + 1e-7, ((a - b).abs().max().item(), scale)
