@@ -214,10 +214,11 @@ template <int MODE> B2F_HD f2 knot_exp2(f2 t) {
     return exp_det2(t);
 }
 
-template <int NB, bool INV, int MODE, class H>
-B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel& s) {
+// Step 1 of the knots: the two softmaxes' exponentials e[] (.x widths, .y heights) and the factor g that turns them into
+// bin sizes -- everything that does not depend on the evaluation point.
+template <int NB, int MODE, class H>
+B2F_HD void rq_knot_weights(const H& h, int nb_rt, f2 (&e)[NB > 0 ? NB : kRqMaxBins], f2& g) {
     const int nb = NB > 0 ? NB : nb_rt;
-    f2 e[NB > 0 ? NB : kRqMaxBins];            // .x: widths softmax, .y: heights softmax, evaluated in lock-step
     // logits: widths u_x; heights u_x + u_y/1000 (rational_quadratic.py:75-76)
     float mx = -INFINITY, my = -INFINITY;
 #pragma unroll
@@ -236,7 +237,14 @@ B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel&
     }
     // sizes_j = 1e-3 + (1 - 1e-3*nb) * softmax_j   (rational_quadratic.py:46-47)
     const float c1 = (float)(1.0 - 1e-3 * (double)nb);   // Python double, cast once (rational_quadratic.py:47)
-    const f2 g = mk2(r_mul(c1, knot_rcp<MODE>(sum.x)), r_mul(c1, knot_rcp<MODE>(sum.y)));
+    g = mk2(r_mul(c1, knot_rcp<MODE>(sum.x)), r_mul(c1, knot_rcp<MODE>(sum.y)));
+}
+
+// Step 2: cumulative sums -> knots, and the search for the bin of v.
+template <int NB, bool INV, class H>
+B2F_HD void rq_search(float v, const H& h, int nb_rt, float lo, float hi, const f2 (&e)[NB > 0 ? NB : kRqMaxBins], f2 g,
+                      RqSel& s) {
+    const int nb = NB > 0 ? NB : nb_rt;
     const float span = r_add(hi, -lo);
     const f2 span2 = mk2(span, span), lo2 = mk2(lo, lo), minb2 = mk2(kRqMinBin, kRqMinBin);
     f2 c = mk2(0.0f, 0.0f);
@@ -258,6 +266,14 @@ B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel&
         if (take) { s.xk1 = kx; s.yk1 = ky; s.ud1 = ud; }
         prev_below = below;
     }
+}
+
+template <int NB, bool INV, int MODE, class H>
+B2F_HD void rq_select(float v, const H& h, int nb_rt, float lo, float hi, RqSel& s) {
+    f2 e[NB > 0 ? NB : kRqMaxBins];            // .x: widths softmax, .y: heights softmax, evaluated in lock-step
+    f2 g;
+    rq_knot_weights<NB, MODE>(h, nb_rt, e, g);
+    rq_search<NB, INV>(v, h, nb_rt, lo, hi, e, g, s);
 }
 
 struct RqEval {          // quantities shared by value, log-det and backward
@@ -341,6 +357,25 @@ B2F_HD void rq_apply(float v, const H& h, int nb_rt, float boundary, float& out,
     rq_select<NB, INV, MODE>(v, h, nb_rt, -boundary, boundary, s);
     if (INV) rq_eval_inv<MODE>(v, s, out, ld, e); else rq_eval_fwd<MODE>(v, s, out, ld, e);
     k = s.k;
+}
+
+// out = T(v) and, on top, the log-det of the SAME spline at the point `out` -- the term the reference's sequential
+// inverse reports for every dimension but the last (layers_base.py:218-223).  Identical arithmetic
+// to two rq_apply calls with the same parameters, but the softmax exponentials are computed once.
+template <int NB, bool INV, int MODE, class H>
+B2F_HD void rq_apply_then_logdet_at_output(float v, const H& h, int nb_rt, float boundary, float& out, float& ld_at_out) {
+    if (!(v > -boundary && v < boundary)) { out = v; ld_at_out = 0.0f; return; }     // then `out` is out of bounds too
+    f2 e[NB > 0 ? NB : kRqMaxBins];
+    f2 g;
+    rq_knot_weights<NB, MODE>(h, nb_rt, e, g);
+    RqSel s; RqEval ev;
+    float ld;
+    rq_search<NB, INV>(v, h, nb_rt, -boundary, boundary, e, g, s);
+    if (INV) rq_eval_inv<MODE>(v, s, out, ld, ev); else rq_eval_fwd<MODE>(v, s, out, ld, ev);
+    if (!(out > -boundary && out < boundary)) { ld_at_out = 0.0f; return; }
+    float out2;
+    rq_search<NB, INV>(out, h, nb_rt, -boundary, boundary, e, g, s);
+    if (INV) rq_eval_inv<MODE>(out, s, out2, ld_at_out, ev); else rq_eval_fwd<MODE>(out, s, out2, ld_at_out, ev);
 }
 
 // ---- backward of the forward-direction spline ---------------------------------------------
