@@ -134,3 +134,54 @@ def test_rows_kernel_raw_programs_through_the_c_abi():
             for a, b in zip(*outs):
                 err = ((a.double() - b.double()).abs() / (1 + b.double().abs())).max().item()
                 assert err < 2e-5, (len(prog), flags, err)
+
+
+@pytest.mark.parametrize('preset,D,B', [('MaskedAutoregressiveRQNSF', 128, 333), ('MaskedAutoregressiveRQNSF', 16, 100),
+                                        ('InverseAutoregressiveRQNSF', 24, 77), ('InverseAutoregressiveRQNSF', 64, 1000)])
+def test_rows_kernel_sequential_spline_layers(preset, D, B):
+    """The D-step sequential direction of spline MADE layers (MA-RQNSF sampling, IA-RQNSF density) on the rows kernel
+    (per-warp streaming of the per-element output-layer weights), incl. the reference's last-iteration log-det, against
+    the generic kernel and the CPU oracle."""
+    from oracle.flow_oracle import OracleFlow
+    from torchflows_b200 import Flow, _native as N
+    import torchflows_b200.architectures as arch
+    dev = torch.device('cuda:0')
+    torch.manual_seed(D + 7)
+    flow = Flow(getattr(arch, preset)(D)).eval()
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            if name.endswith('.value'):
+                p.add_(0.3 * torch.randn_like(p))
+    oracle = OracleFlow(preset, (D,), flow.state_dict())
+    flow = flow.to(dev)
+    g = torch.Generator().manual_seed(B)
+    v = (1.5 * torch.randn(B, D, generator=g)).to(dev)
+    sampling = preset == 'MaskedAutoregressiveRQNSF'
+
+    def call():
+        with torch.no_grad():
+            if sampling:
+                return flow._sample_from_base(v, no_grad=True, return_log_prob=True)
+            z, ld = flow.bijection.forward(v)
+            return z, flow.log_prob(v), ld
+    rows = call()
+    assert N.last_flow_kernel() == N.KERNEL_ROWS
+    os.environ['B2F_DISABLE_ROWS'] = '1'
+    try:
+        gen = call()
+        assert N.last_flow_kernel() == N.KERNEL_GENERIC
+    finally:
+        os.environ.pop('B2F_DISABLE_ROWS', None)
+    # two fp32 kernels with different summation orders in the hidden layer: spline VALUES agree to the spline tolerance
+    # (knot noise ~ ulp(boundary), cf. tests/test_gpu_tc.py), log-quantities to 2e-4
+    for idx, (a, b) in enumerate(zip(rows, gen)):
+        err = ((a.double() - b.double()).abs() / (1 + b.double().abs())).max().item()
+        assert err < (2e-3 if idx == 0 else 2e-4), (idx, err)
+    nb = min(B, 48)
+    if sampling:
+        xs_ref, lps_ref = oracle.sample_from_noise(v[:nb].cpu(), return_log_prob=True)
+        assert ((rows[0][:nb].double().cpu() - xs_ref.double()).abs() / (1 + xs_ref.double().abs())).max().item() < 2e-3
+        assert ((rows[1][:nb].double().cpu() - lps_ref.double()).abs() / (1 + lps_ref.double().abs())).max().item() < 2e-4
+    else:
+        lp_ref = oracle.log_prob(v[:nb].cpu()).double()
+        assert ((rows[1][:nb].double().cpu() - lp_ref).abs() / (1 + lp_ref.abs())).max().item() < 1e-4
