@@ -61,14 +61,32 @@ class Bijection(nn.Module):
         return self.batch_apply(self.inverse, batch_size, x, context, **kwargs)
 
     def sq_norm_param(self) -> torch.Tensor:
-        """Squared norm of the trainable parameters (base.py:134-144)."""
-        return sum([torch.sum(torch.square(p)) for p in self.parameters() if p.requires_grad])
+        """Squared norm of the trainable parameters (base.py:134-144); on the GPU as one fused multi-tensor reduction
+        forward and one multi-tensor scale backward instead of two tiny kernels per parameter tensor each way."""
+        params = [p for p in self.parameters() if p.requires_grad]
+        if params and all(p.is_cuda for p in params):
+            return _SqNorm.apply(*params)
+        return sum([torch.sum(torch.square(p)) for p in params])
 
     def regularization(self, *aux: Tuple[Any, ...]) -> torch.Tensor:
         return torch.tensor(0.0)
 
     def invert(self):
         self.forward, self.inverse = self.inverse, self.forward
+
+
+class _SqNorm(torch.autograd.Function):
+    """sum_i ||p_i||^2 over a list of CUDA tensors."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        ctx.save_for_backward(*params)
+        norms = torch._foreach_norm([p.detach() for p in params], 2)
+        return torch.stack(norms).square().sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(torch._foreach_mul([p.detach() for p in ctx.saved_tensors], 2.0 * g))
 
 
 def invert(bijection: Bijection) -> Bijection:
@@ -163,11 +181,21 @@ class BijectiveComposition(Bijection):
         return self._run_layers(z, context, "inverse")
 
     def regularization(self):
-        """Sum of the layers' regularization terms (base.py:234-243), accumulated on the parameters' device."""
-        terms = [layer.regularization() for layer in self.layers]
-        terms = [t for t in terms if isinstance(t, torch.Tensor)]
-        device = next((t.device for t in terms if t.is_cuda), torch.device('cpu'))
-        total = torch.zeros((), device=device)
-        for t in terms:
-            total = total + t.to(device)
-        return total
+        """Sum of the layers' regularization terms (base.py:234-243).  Terms that live on the GPU are summed there; the
+        layers' default `torch.tensor(0.0)` placeholders stay on the host (a 0-dim CPU tensor combines with a CUDA loss as
+        a scalar, so no per-layer host-to-device copy is issued)."""
+        terms = [t for t in (layer.regularization() for layer in self.layers) if isinstance(t, torch.Tensor)]
+        gpu = [t for t in terms if t.is_cuda]
+        cpu = [t for t in terms if not t.is_cuda]
+        total = None
+        for t in gpu:
+            total = t if total is None else total + t
+        if cpu:
+            host = cpu[0]
+            for t in cpu[1:]:
+                host = host + t
+            if total is None:
+                return host
+            if host.requires_grad or float(host) != 0.0:
+                total = total + host.to(total.device)
+        return total if total is not None else torch.tensor(0.0)

@@ -76,7 +76,7 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
     int XS = D + 4;
     if (((XS >> 2) & 1) == 0) XS += 4;     // XS/4 odd: conflict-free 16-byte row accesses across a warp
     const bool spline = Hrq > 0;
-    if (spline && hp4 > 4) return 0;
+    if (spline && (hp4 > 4 || (flags & B2F_FLOW_MODE_PRECISE))) return 0;      // precise splines: generic kernel
     const int NT = spline ? kRowsThreadsSpline : kRowsThreadsAffine;
     // staged weights of every conditioner layer: w1 [n_src][HP] + b1 [HP] + w2 [n_tgt*P][HP] (no w2 for spline layers)
     size_t wtotal = 0;

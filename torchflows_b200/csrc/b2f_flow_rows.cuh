@@ -286,8 +286,8 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const 
 // InverseAutoregressiveRQNSF density).  The output layer is 23 x H weights PER ELEMENT (tile layout [e][j][24] in global
 // memory): too large to stage for all D elements, so every warp streams the next element's block (H*24 + 23 floats)
 // into its own double buffer with cp.async while it works on the current element.
-template <int TK, int MODE, int HP, bool REV>
-__device__ __forceinline__ void rows_sequential_rq(float* x0, int D, const DevOp& op, const RowsWeights<HP>& W,
+template <int TK, int MODE, int HP>
+__device__ __forceinline__ void rows_sequential_rq(float* x0, int D, int rev, const DevOp& op, const RowsWeights<HP>& W,
                                                    const float* er, float* wst, int wst_stride, float& ld) {
     constexpr int P = 23, PP = 24;
     const int H = op.H, lane = threadIdx.x & 31;
@@ -320,7 +320,7 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, int D, const DevOp
     // reference's log-det quirk) and must stay inside the instruction cache; x is read and written as scalars
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
-        const int c = REV ? D - 1 - i : i, cur = i & 1;       // physical column of logical step i
+        const int c = rev ? D - 1 - i : i, cur = i & 1;       // physical column of logical step i (rev: flipped tile)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();                                 // element i's weights have landed; the other buffer is free
         if (i + 1 < D) stage(i + 1, buf[cur ^ 1]);
@@ -387,13 +387,8 @@ __device__ __forceinline__ void rows_layer(const float* wbuf, float* x0, int XS,
         static_assert(R == 1, "spline layers: one row per thread");
         if (op.tkind == B2F_T_RQ_FWD || op.tkind == B2F_T_RQ_INV) {       // sequential spline layer (host guarantees MADE_SEQ)
             const RowsWeights<HP> W = weights_view<HP>(wbuf, D);
-            if (op.tkind == B2F_T_RQ_INV) {
-                if (flip) rows_sequential_rq<B2F_T_RQ_INV, MODE, HP, true>(x0, D, op, W, er, wst, wst_stride, ld[0]);
-                else rows_sequential_rq<B2F_T_RQ_INV, MODE, HP, false>(x0, D, op, W, er, wst, wst_stride, ld[0]);
-            } else {
-                if (flip) rows_sequential_rq<B2F_T_RQ_FWD, MODE, HP, true>(x0, D, op, W, er, wst, wst_stride, ld[0]);
-                else rows_sequential_rq<B2F_T_RQ_FWD, MODE, HP, false>(x0, D, op, W, er, wst, wst_stride, ld[0]);
-            }
+            if (op.tkind == B2F_T_RQ_INV) rows_sequential_rq<B2F_T_RQ_INV, MODE, HP>(x0, D, flip, op, W, er, wst, wst_stride, ld[0]);
+            else rows_sequential_rq<B2F_T_RQ_FWD, MODE, HP>(x0, D, flip, op, W, er, wst, wst_stride, ld[0]);
             return;
         }
     }

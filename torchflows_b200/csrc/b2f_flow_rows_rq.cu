@@ -17,9 +17,8 @@ static cudaError_t launch_spline_h(int hp4, const RowsArgs& A, unsigned grid, si
 }
 
 cudaError_t launch_rows_spline(int mode, int hp4, const RowsArgs& A, unsigned grid, size_t smem, cudaStream_t st) {
-    return mode == 0 ? launch_spline_h<0>(hp4, A, grid, smem, st)
-         : mode == 1 ? launch_spline_h<1>(hp4, A, grid, smem, st)
-                     : launch_spline_h<2>(hp4, A, grid, smem, st);
+    // default and fast arithmetic; `precise` programs stay on the generic kernel (b2f_flow_rows.cu does not send them here)
+    return mode == 2 ? launch_spline_h<2>(hp4, A, grid, smem, st) : launch_spline_h<1>(hp4, A, grid, smem, st);
 }
 
 }  // namespace b2f
