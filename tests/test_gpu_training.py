@@ -259,3 +259,24 @@ def test_variational_fit_and_kl_fit(dev):
     flow.fit_kl_p_to_q(x[:1500], x[1500:], lambda t: -target_log_prob(t.to(dev)).cpu(), n_epochs=5, lr=0.01)
     # MAF samples through the sequential direction: fused backward as well
     assert any(svi_recovers_target(MAF, seed, 400) for seed in (2, 3, 4))
+
+
+@pytest.mark.parametrize('preset,D,n,bs', [('RealNVP', 3, 500, None), ('CouplingRQNSF', 16, 1024, 256), ('MAF', 8, 700, 256)])
+def test_fit_with_cuda_graph_matches_eager_fit(preset, D, n, bs):
+    """fit(cuda_graph=True): the training step replayed from a CUDA graph (full batches) mixed with eager steps (the first
+    three, and the ragged last batch of every epoch) follows the eager trajectory; validation and the best-weights
+    snapshot see the replayed updates."""
+    from torchflows_b200 import Flow
+    import torchflows_b200.architectures as arch
+    dev = torch.device('cuda:0')
+    finals = []
+    for graph in (False, True):
+        torch.manual_seed(0)
+        x = torch.randn(n, D) * 1.5 + 0.3
+        torch.manual_seed(1)
+        flow = Flow(getattr(arch, preset)(D)).to(dev)
+        flow.fit(x, n_epochs=30, batch_size=bs, lr=0.01, x_val=x[:100], cuda_graph=graph)
+        assert not flow.training
+        with torch.no_grad():
+            finals.append(flow.log_prob(x.to(dev)).mean().item())
+    assert abs(finals[0] - finals[1]) < 2e-3 * (1 + abs(finals[0])), finals

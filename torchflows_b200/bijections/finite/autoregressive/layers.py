@@ -63,7 +63,8 @@ class ActNorm(ElementwiseInverseAffine):
         scale = std.to(self.value.dtype)[:, None]
         shift = mean.to(self.value.dtype)[:, None]
         new = torch.cat([self.transformer.unconstrain_scale(scale), shift], dim=-1)
-        self.value.data = new.view(self.value.shape).to(self.value.device)
+        with torch.no_grad():      # in place (the reference rebinds .data, layers.py:68): the parameter keeps its storage, so
+            self.value.copy_(new.view(self.value.shape))      # snapshots and captured graphs keep pointing at it
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.needs_data_init():

@@ -1,4 +1,8 @@
 // Small non-kernel entry points of the C ABI.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "b2f_common.cuh"
 
 namespace b2f {
@@ -6,6 +10,20 @@ char* last_error_buffer() {
     static thread_local char buf[512] = {0};
     return buf;
 }
+int raise_smem_limit(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> limit;
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return (int)ce;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = limit[std::make_pair(dev, kernel)];
+    if (bytes <= cur) return (int)cudaSuccess;
+    ce = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) cur = bytes;
+    return (int)ce;
+}
+
 int& last_flow_kernel() {
     static thread_local int k = B2F_KERNEL_NONE;
     return k;

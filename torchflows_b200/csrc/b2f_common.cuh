@@ -25,6 +25,11 @@ inline int check_launch(const char* what) {
     return B2F_OK;
 }
 
+// Raise (never lower) a kernel's dynamic shared-memory limit.  The limit is state of the FUNCTION, not of a launch: a kernel
+// node replayed from a CUDA graph keeps the size it was captured with, so a later, smaller eager launch must not shrink
+// the limit under it.  Per device; the attribute call is skipped when the limit is already high enough.
+int raise_smem_limit(const void* kernel, size_t bytes);   // b2f_api.cu; returns a cudaError_t value
+
 inline int params_per_element(int tkind, int n_bins) {
     switch (tkind) {
         case B2F_T_SHIFT_ADD: case B2F_T_SHIFT_SUB: return 1;

@@ -290,7 +290,7 @@ static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, f
     const long long grid = (B + TM - 1) / TM;
     if (grid > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: batch too large for one launch");
     auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_kernel<0> : ((flags & B2F_FLOW_MODE_FAST_KNOTS) ? flow_kernel<2> : flow_kernel<1>);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)kern, smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
     last_flow_kernel() = B2F_KERNEL_GENERIC;

@@ -775,7 +775,7 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     // gradients of the spline knots cancel at the 1e-3 level in fp32 (tests/test_c_oracle_and_hostmath.py): always use the
     // accurate exp / log / division variants here, whatever arithmetic mode the forward pass runs in
     auto kern = flow_backward_kernel<0>;
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)kern, smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     kern<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
     return check_launch("b2f_flow_backward");

@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
 template <int MODE, int HP4, bool RQ, int NT>
 static cudaError_t launch_rows_kernel(const RowsArgs& A, unsigned grid, size_t smem, cudaStream_t st) {
     auto kern = flow_rows_kernel<MODE, HP4, 1, RQ, NT>;
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)kern, smem);
     if (ce != cudaSuccess) return ce;
     kern<<<grid, NT, smem, st>>>(A);
     return cudaSuccess;

@@ -554,7 +554,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(A.n_tiles, n_sm);
     auto kern = (flags & B2F_FLOW_MODE_PRECISE) ? flow_tc_kernel<0> : ((flags & B2F_FLOW_MODE_FAST_KNOTS) ? flow_tc_kernel<2> : flow_tc_kernel<1>);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)kern, smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute(tc): %s", cudaGetErrorString(ce));
     kern<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(A);
     const int rc = check_launch("b2f_flow_apply (tensor-core kernel)");

@@ -68,7 +68,7 @@ extern "C" int b2f_debug_umma_gemm(const float* A, const float* B, float* C, int
     if (smem > 200 * 1024) return fail(B2F_ERR_UNSUPPORTED, "b2f_debug_umma_gemm: tile too large");
     int cols = 32;
     while (cols < N) cols <<= 1;
-    cudaError_t ce = cudaFuncSetAttribute(umma_gemm_debug_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)umma_gemm_debug_kernel, smem);
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     umma_gemm_debug_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, C, N, K, cols);
     return check_launch("b2f_debug_umma_gemm");

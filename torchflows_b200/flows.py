@@ -4,6 +4,7 @@ What changes underneath: ``log_prob`` and ``sample`` of a lowerable bijection ar
 (layers + log-det + base density, csrc/b2f_flow.cu); ``fit`` trains through the hand-written backward kernel
 and, when ``torch.distributed`` is initialised, runs data-parallel: every rank takes its slice of each
 minibatch and gradients are all-reduced over NCCL (NVLink/NVSwitch) in one flat bucket per step."""
+import math
 import time
 import warnings
 from copy import deepcopy
@@ -59,11 +60,49 @@ def _allreduce_stats(s, q, n):
     return packed[:d], packed[d:2 * d], packed[2 * d]
 
 
-def _make_adamw(params, lr):
+def _make_adamw(params, lr, capturable=False):
     """The reference's optimizer: `torch.optim.AdamW(self.parameters(), lr=lr)` (flows.py:309,537).  The fused
     single-kernel variant is deliberately NOT used: with it stochastic variational inference on the affine presets stopped
-    converging in tests/test_gpu_training.py::test_variational_fit_and_kl_fit (0 of 6 initialisations against 6 of 6)."""
-    return torch.optim.AdamW(list(params), lr=lr)
+    converging in tests/test_gpu_training.py::test_variational_fit_and_kl_fit (0 of 6 initialisations against 6 of 6).
+    `capturable`: step counter on the device, so that optimizer.step() can be part of a CUDA graph."""
+    return torch.optim.AdamW(list(params), lr=lr, capturable=capturable)
+
+
+class _Snapshot(dict):
+    """A copy of a state_dict that remembers the live tensors it was taken from."""
+    sources = None
+
+
+def _touch(params):
+    """Bump the version counters of parameters that were updated inside a CUDA-graph replay (no Python ran): the kernel
+    operand layouts cached per (pointer, version) in _program.py are derived again on next use."""
+    params = [p for p in params if p.numel() > 0]
+    if params:
+        with torch.no_grad():
+            torch._foreach_add_(params, 0.0)
+
+
+class _GraphTrainStep:
+    """One training step of `BaseFlow.fit` -- loss, backward, AdamW -- captured in a CUDA graph for a fixed batch size.
+    The kernels of this package launch on the current stream through the C ABI and allocate through torch, so they are
+    captured like any torch op; operand layouts derived from the weights are recomputed inside the graph."""
+
+    def __init__(self, flow, xb, wb):
+        self.rows = len(xb)
+        self.x, self.w = xb.clone(), wb.clone()
+        opt = flow._optimizer
+        opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = flow._base_batch_loss((self.x, self.w), reduction=torch.mean, use_regularization=True)
+            self.loss.backward()
+            opt.step()
+
+    def __call__(self, xb, wb):
+        self.x.copy_(xb)
+        self.w.copy_(wb)
+        self.graph.replay()
+        return self.loss.detach()
 
 
 class BaseFlow(nn.Module):
@@ -110,12 +149,14 @@ class BaseFlow(nn.Module):
     def _snapshot_weights(self, into: dict = None) -> dict:
         """`deepcopy(self.state_dict())` of the reference's keep-best-weights logic (flows.py:246,429) without the
         per-tensor Python work: the first call clones, later calls refresh the same buffers with one fused copy."""
-        state = self.state_dict()
-        if into is None or into.keys() != state.keys():
-            return {k: v.detach().clone() for k, v in state.items()}
-        dst, src = list(into.values()), [v.detach() for v in state.values()]
+        if into is None or getattr(into, 'sources', None) is None:
+            state = self.state_dict()
+            snap = _Snapshot((k, v.detach().clone()) for k, v in state.items())
+            snap.sources = [v.detach() for v in state.values()]     # the module's own parameters and buffers
+            return snap
+        dst = list(into.values())
         if dst:
-            torch._foreach_copy_(dst, src)
+            torch._foreach_copy_(dst, into.sources)
         return into
 
     def fit(self, x_train: torch.Tensor, n_epochs: int = 500, lr: float = 0.05, batch_size: Union[int, str] = 1024,
@@ -123,11 +164,17 @@ class BaseFlow(nn.Module):
             context_train: torch.Tensor = None, x_val: torch.Tensor = None, w_val: torch.Tensor = None,
             context_val: torch.Tensor = None, keep_best_weights: bool = True, early_stopping: bool = False,
             early_stopping_threshold: int = 50, max_batch_size_mb: int = None,
-            time_limit_seconds: Union[float, int] = None, reset_optimizer: bool = True):
+            time_limit_seconds: Union[float, int] = None, reset_optimizer: bool = True, cuda_graph: bool = False):
         """Maximum-likelihood fit with the reference's semantics (flows.py:226-455): AdamW, minibatches in a fresh
         random order every epoch, best-weights snapshot, divergence rollback, optional validation / early stopping /
         adaptive batch size / time limit.  The data are moved to the flow's device once and batches are index
-        slices there (the reference collates every batch on the host through a DataLoader)."""
+        slices there (the reference collates every batch on the host through a DataLoader).
+
+        ``cuda_graph=True`` (not in the reference; single process, no context): after three ordinary steps the training
+        step (forward, backward, AdamW) is captured once per batch size in a CUDA graph and replayed, so a step costs
+        one graph launch instead of ~60 kernel launches and their Python -- for launch-bound problems such as the README
+        example.  Same arithmetic; the loss is checked for divergence after the replayed step instead of before its
+        backward pass (a diverged step is rolled back to the best weights either way)."""
         t0 = time.time()
         self.train()
         params = list(self.parameters())
@@ -173,9 +220,11 @@ class BaseFlow(nn.Module):
                 raise ValueError(f'Expected same number of validation data and validation weights, '
                                  f'but found {len(xv_dev)} and {len(wv_dev)}')
 
+        use_graph = bool(cuda_graph) and world == 1 and context_train is None and device.type == 'cuda'
         if self._optimizer is None or reset_optimizer:
-            self._optimizer = _make_adamw(self.parameters(), lr)
+            self._optimizer = _make_adamw(self.parameters(), lr, capturable=use_graph)
         trainable = [p for p in self.parameters() if p.requires_grad]
+        graph_step, eager_steps, replayed, loss = None, 0, False, None
         if world > 1:
             self.bijection._stats_reduce_fn = _allreduce_stats     # ActNorm initialises from global statistics
         gen = torch.Generator(device='cpu')
@@ -202,6 +251,30 @@ class BaseFlow(nn.Module):
                 idx = slice(start + lo, start + hi) if order is None else order[start + lo:start + hi]
                 xb, wb = x_dev[idx], w_dev[idx]
                 cb = None if c_dev is None else c_dev[idx]
+                if use_graph and eager_steps >= 3 and stop - start == min(batch_size, n_train):
+                    if graph_step is None or graph_step.rows != len(xb):
+                        # operand layouts cached for the current weights (e.g. by the validation pass) must be derived
+                        # again INSIDE the capture, or every replay would read the frozen copies
+                        _touch(trainable)
+                        # no reference to an eager step's autograd graph may survive: its AccumulateGrad nodes are bound
+                        # to the stream they were created on and would break the capture
+                        loss = graph_step = None
+                        graph_step = _GraphTrainStep(self, xb, wb)
+                    loss_value = graph_step(xb, wb).item()        # one host sync per step
+                    replayed = True
+                    if not math.isfinite(loss_value):
+                        _touch(trainable)
+                        self.load_state_dict(best_weights)
+                        warnings.warn('Flow training diverged. Reverting to previous weights.')
+                        diverged = True
+                        break
+                    total += loss_value
+                    n_batches += 1
+                    continue
+                if replayed:
+                    _touch(trainable)          # the replays updated the weights behind the operand caches' back
+                    replayed = False
+                eager_steps += 1
                 loss, loss_value = self._loss_and_backward_inputs(xb, wb, stop - start, world, cb)
                 if not torch.isfinite(loss_value):
                     self.load_state_dict(best_weights)       # roll back (flows.py:387-393)
@@ -225,6 +298,9 @@ class BaseFlow(nn.Module):
             mean_loss = total / max(n_batches, 1)
             if mean_loss < best_train_loss:
                 best_train_loss, best_train_epoch = mean_loss, epoch
+            if replayed and x_val is not None:
+                _touch(trainable)
+                replayed = False
             if x_val is not None:
                 with torch.no_grad():
                     acc = 0.0
@@ -244,6 +320,9 @@ class BaseFlow(nn.Module):
                 if epoch - ref_epoch > early_stopping_threshold:
                     break
 
+        if replayed:
+            _touch(trainable)
+        graph_step = None
         if keep_best_weights:
             self.load_state_dict(best_weights)
         self.eval()
