@@ -441,11 +441,16 @@ __device__ __forceinline__ void run_transform_forward(const Tile& t, const DevOp
 template <int MODE>
 __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constant__ BwdArgs A) {
     extern __shared__ __align__(16) float smem[];
+#ifdef B2F_BWD_CLOCK_HOOK
+    // Phase timing from inside the kernel (build with -DB2F_BWD_CLOCK_HOOK, run with B2F_BWD_DEBUG_CLOCK=1): every 512th
+    // CTA prints its cycles per phase.  ncu reports this launch at half its stand-alone duration, so this is the
+    // instrument for it; compiled out by default (the printf costs registers and stack).
     long long dbg_c0 = 0; unsigned long long dbg_t0 = 0;
     if ((A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0) {
         dbg_c0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
     }
+#endif
     BTile b;
     Tile& t = b.t;
     t.D = A.D; t.TM = A.TM; t.logTM = A.logTM; t.XS = A.XS; t.HS = A.HS; t.WPG = A.WPG; t.G = A.G; t.flip = 0;
@@ -508,9 +513,11 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         __syncthreads();
     }
 
+#ifdef B2F_BWD_CLOCK_HOOK
     long long dbg_cA = 0, dbg_cT = 0, dbg_cH = 0, dbg_cR = 0;
     const bool dbg = (A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0;
     if (dbg) dbg_cA = clock64();
+#endif
     // ---- gradient seed: dL/dz = gy + glp * d base_logp / dz ;  dL/dlog_det = gld + glp ------------------
     for (int m = warp; m < TM; m += NW) {
         const bool live = m < rows;
@@ -598,14 +605,20 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         __syncthreads();
         const bool coupling = op.f.kind == B2F_OP_COUPLING;
         const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0, H = op.f.H;
+#ifdef B2F_BWD_CLOCK_HOOK
         long long c_a = 0, c_b = 0, c_c = 0;
         if (dbg) c_a = clock64();
+#endif
         hidden_layer<true>(t, op.f, n_src);
         __syncthreads();
+#ifdef B2F_BWD_CLOCK_HOOK
         if (dbg) c_b = clock64();
+#endif
         run_transform_backward<MODE>(b, op, t0, D - t0);
         __syncthreads();
+#ifdef B2F_BWD_CLOCK_HOOK
         if (dbg) { c_c = clock64(); dbg_cH += c_b - c_a; dbg_cT += c_c - c_b; dbg_cR -= c_c; }
+#endif
         // tanh': dpre = dhid * (1 - hid^2)
         for (int idx = tid; idx < (H << t.logTM); idx += NT) {
             const int m = idx & (TM - 1), j = idx >> t.logTM;
@@ -644,6 +657,7 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         for (int m = warp; m < rows; m += NW)
             for (int j = lane; j < D; j += 32) A.gx[(row0 + m) * D + j] = b.gt[m * XS + t.col(j)];
     }
+#ifdef B2F_BWD_CLOCK_HOOK
     if ((A.flags & 0x200) && threadIdx.x == 0 && (blockIdx.x % 512) == 0) {
         unsigned long long t1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -651,6 +665,7 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         printf("[bwd dbg] block %d: %lld cycles, %llu ns, start at %llu ns; phase A %lld, hidden recompute (B) %lld, transform backward %lld\n",
                blockIdx.x, c1 - dbg_c0, t1 - dbg_t0, dbg_t0, dbg_cA - dbg_c0, dbg_cH, dbg_cT);
     }
+#endif
 }
 
 static int ilog2b(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }

@@ -7,7 +7,6 @@ minibatch and gradients are all-reduced over NCCL (NVLink/NVSwitch) in one flat 
 import math
 import time
 import warnings
-from copy import deepcopy
 from typing import Optional, Tuple, Union
 
 import torch
