@@ -222,6 +222,8 @@ class BaseFlow(nn.Module):
         use_graph = bool(cuda_graph) and world == 1 and context_train is None and device.type == 'cuda'
         if self._optimizer is None or reset_optimizer:
             self._optimizer = _make_adamw(self.parameters(), lr, capturable=use_graph)
+        elif use_graph and not all(g.get('capturable', False) for g in self._optimizer.param_groups):
+            use_graph = False        # an optimizer kept from an earlier call cannot be stepped inside a graph: stay eager
         trainable = [p for p in self.parameters() if p.requires_grad]
         graph_step, eager_steps, replayed, loss = None, 0, False, None
         if world > 1:
