@@ -222,7 +222,54 @@ __device__ __forceinline__ void transform_pass_backward_mma(const BTile& b, cons
         if (e + t.WPG < n_tgt) stage(e + t.WPG, wbuf[cur ^ 1]);
         {
             float acc[PP], dh[PP];
-            element_params<P, PP, false>(acc, w2e, w2e + H * PP, hid_m, H);
+            {
+                // transformer parameters of the warp's 32 samples: [32 x (H+1)] (hid | 1) times [(H+1) x 24] (W2[e] ; b2[e],
+                // contiguous in the staged block) on the tensor cores (3xTF32), then through the staging buffer to get
+                // from the accumulator layout to one sample per thread
+                float pacc[2][3][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) pacc[mt][nt][i] = 0.0f;
+                auto hv = [&](int row, int j) { return j < H ? hid_g[row * t.HS + j] : (j == H ? 1.0f : 0.0f); };
+#pragma unroll
+                for (int ks = 0; ks < NT2; ++ks) {               // NT2 = ceil((H+1)/8) as well
+                    uint32_t ah[2][4], al[2][4];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        const float v[4] = {hv(16 * mt + gq, 8 * ks + tq), hv(16 * mt + gq + 8, 8 * ks + tq),
+                                            hv(16 * mt + gq, 8 * ks + tq + 4), hv(16 * mt + gq + 8, 8 * ks + tq + 4)};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { ah[mt][i] = tf32_hi(v[i]); al[mt][i] = tf32_lo(v[i]); }
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt) {
+                        const int j0 = 8 * ks + tq, j1 = j0 + 4;
+                        const float w0 = j0 <= H ? w2e[j0 * PP + 8 * nt + gq] : 0.0f;
+                        const float w1 = j1 <= H ? w2e[j1 * PP + 8 * nt + gq] : 0.0f;
+#pragma unroll
+                        for (int mt = 0; mt < 2; ++mt)
+                            mma3_tf32(pacc[mt][nt], ah[mt], al[mt], tf32_hi(w0), tf32_hi(w1), tf32_lo(w0), tf32_lo(w1));
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 3; ++nt) {
+                        float* r0 = dhs + (16 * mt + gq) * PP + 8 * nt + 2 * tq;
+                        *reinterpret_cast<float2*>(r0) = make_float2(pacc[mt][nt][0], pacc[mt][nt][1]);
+                        *reinterpret_cast<float2*>(r0 + 8 * PP) = make_float2(pacc[mt][nt][2], pacc[mt][nt][3]);
+                    }
+                __syncwarp();
+                const float4* prow = reinterpret_cast<const float4*>(dhs + lane * PP);
+#pragma unroll
+                for (int q = 0; q < PP / 4; ++q) {
+                    const float4 v = prow[q];
+                    acc[4 * q] = v.x; acc[4 * q + 1] = v.y; acc[4 * q + 2] = v.z; acc[4 * q + 3] = v.w;
+                }
+            }
             const int c = t.col(t0 + e);
             float dv;
             transformer_backward_element<TK, MODE, P, PP>(t.xt[m * t.XS + c], acc, op.f.boundary, b.gt[m * t.XS + c], GLm,
