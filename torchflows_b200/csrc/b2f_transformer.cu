@@ -87,6 +87,53 @@ __global__ void __launch_bounds__(256) transformer_backward_kernel(
     gx[idx] = dv;
 }
 
+// Spline backward with dense parameters (h_row_stride == E * 23, n_bins == 8): a block's 256 elements own one contiguous
+// 256 x 23-float slab of h and of gh, so both travel through shared memory with coalesced 16-byte accesses (the
+// thread-per-element loads above touch 32 different sectors per instruction and write 4 bytes of every sector 8 times).
+template <int TK, int MODE>
+__global__ void __launch_bounds__(256) transformer_backward_staged_kernel(
+    const float* __restrict__ x, const float* __restrict__ h, const float* __restrict__ gout,
+    const float* __restrict__ glog_det, float* __restrict__ gx, float* __restrict__ gh, long long n_elem, int E,
+    float boundary) {
+    constexpr int P = 23;
+    __shared__ __align__(16) float buf[256 * P];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * 256;
+    const int n_here = (int)min(256LL, n_elem - base);
+    const int n_f = n_here * P;
+    {
+        const float4* src = reinterpret_cast<const float4*>(h + base * P);      // base * 92 bytes: a multiple of 16
+        for (int q = tid; q < (n_f >> 2); q += 256) reinterpret_cast<float4*>(buf)[q] = __ldg(src + q);
+        for (int q = (n_f & ~3) + tid; q < n_f; q += 256) buf[q] = __ldg(h + base * P + q);
+    }
+    __syncthreads();
+    if (tid < n_here) {
+        const long long idx = base + tid;
+        const long long row = idx / E;
+        float* mine = buf + tid * P;                 // stride 23 floats: conflict-free
+        float hv[P + 1], gv[P + 1];
+#pragma unroll
+        for (int i = 0; i < P; ++i) { hv[i] = mine[i]; gv[i] = 0.0f; }
+        const float v = __ldg(x + idx);
+        const float GZ = gout ? __ldg(gout + idx) : 0.0f;
+        const float GL = glog_det ? __ldg(glog_det + row) : 0.0f;
+        float dv;
+        auto hf = [&](int i) { return hv[i]; };
+        auto gf = [&](int i, float val) { gv[i] = val; };
+        if constexpr (TK == B2F_T_RQ_FWD) rq_backward_fwd<8, MODE>(v, hf, 8, boundary, GZ, GL, dv, gf);
+        else rq_backward_inv<8, MODE>(v, hf, 8, boundary, GZ, GL, dv, gf);
+        gx[idx] = dv;
+#pragma unroll
+        for (int i = 0; i < P; ++i) mine[i] = gv[i];
+    }
+    __syncthreads();
+    {
+        float4* dst = reinterpret_cast<float4*>(gh + base * P);
+        for (int q = tid; q < (n_f >> 2); q += 256) __stcs(dst + q, reinterpret_cast<const float4*>(buf)[q]);
+        for (int q = (n_f & ~3) + tid; q < n_f; q += 256) gh[base * P + q] = buf[q];
+    }
+}
+
 __global__ void __launch_bounds__(256) column_stats_kernel(const float* __restrict__ x, double* __restrict__ sum,
                                                            double* __restrict__ sumsq, long long B, int D,
                                                            long long rows_per_block) {
@@ -129,6 +176,12 @@ static int launch_bwd(const float* x, const float* h, const float* gout, const f
     const long long blocks = (n + block - 1) / block;
     if (blocks > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_backward: too many elements");
     constexpr bool rq = TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV;
+    if constexpr (rq) {
+        if (nb == 8 && hs == (int64_t)E * 23 && !((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(gh)) & 15)) {
+            transformer_backward_staged_kernel<TK, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, gout, gld, gx, gh, n, E, boundary);
+            return check_launch("b2f_transformer_backward");
+        }
+    }
     if (rq && nb == 8)
         transformer_backward_kernel<TK, 8, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, gout, gld, gx, gh, n_rows, E, hs, nb, boundary);
     else
