@@ -333,11 +333,10 @@ __device__ __forceinline__ void transform_pass_backward_mma(const BTile& b, cons
                 for (int nt = 0; nt < 3; ++nt)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
+                        // row j < H of the product is dL/dW2[e][j][:], row H is dL/db2[e][:]: one predicated reduction
                         const int j = 16 * mt + gq + ((i & 2) ? 8 : 0), p = 8 * nt + 2 * tq + (i & 1);
-                        if (p < P) {
-                            if (j < H) atomicAdd(g2e + j * PP + p, acc1[mt][nt][i]);
-                            else if (j == H) atomicAdd(g3e + p, acc1[mt][nt][i]);
-                        }
+                        float* dst = (j < H) ? g2e + j * PP + p : g3e + p;
+                        if (p < P && j <= H) atomicAdd(dst, acc1[mt][nt][i]);
                     }
         }
     }
