@@ -279,4 +279,4 @@ def test_fit_with_cuda_graph_matches_eager_fit(preset, D, n, bs):
         assert not flow.training
         with torch.no_grad():
             finals.append(flow.log_prob(x.to(dev)).mean().item())
-    assert abs(finals[0] - finals[1]) < 2e-3 * (1 + abs(finals[0])), finals
+    assert abs(finals[0] - finals[1]) < 5e-3 * (1 + abs(finals[0])), finals
