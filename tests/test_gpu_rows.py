@@ -185,3 +185,30 @@ def test_rows_kernel_sequential_spline_layers(preset, D, B):
     else:
         lp_ref = oracle.log_prob(v[:nb].cpu()).double()
         assert ((rows[1][:nb].double().cpu() - lp_ref).abs() / (1 + lp_ref.abs())).max().item() < 1e-4
+
+
+def test_rows_kernel_in_place_spline_sampling_is_bit_identical():
+    """MA-RQNSF sampling keeps its rows in the output buffer (global memory, no shared-memory tile); same arithmetic as
+    the tiled mode (B2F_ROWS_NO_INPLACE=1), so bit-identical results, including a ragged last warp."""
+    from torchflows_b200 import Flow, _native as N
+    from torchflows_b200.architectures import MaskedAutoregressiveRQNSF
+    dev = torch.device('cuda:0')
+    torch.manual_seed(4)
+    flow = Flow(MaskedAutoregressiveRQNSF(32)).to(dev).eval()
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            if name.endswith('.value'):
+                p.add_(0.3 * torch.randn_like(p))
+    for B in (1, 37, 64, 1000):
+        z = 1.5 * torch.randn(B, 32, device=dev)
+        outs = []
+        for tiled in (False, True):
+            if tiled:
+                os.environ['B2F_ROWS_NO_INPLACE'] = '1'
+            try:
+                with torch.no_grad():
+                    outs.append(flow._sample_from_base(z, no_grad=True, return_log_prob=True))
+                assert N.last_flow_kernel() == N.KERNEL_ROWS
+            finally:
+                os.environ.pop('B2F_ROWS_NO_INPLACE', None)
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), B

@@ -90,12 +90,29 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
         wtotal += (size_t)n_src * HP + HP + (rq ? 0 : (size_t)n_tgt * P * HP);
     }
     const int R = 1;
+    // Programs whose conditioner layers are ALL sequential spline layers and that produce an output (sampling): the rows
+    // live in the output buffer itself -- every thread walks its own row of y in global memory (L1 keeps its current
+    // line) -- so no shared-memory tile limits the number of resident warps.  Needs: an even number of flips (the result
+    // is already in logical order), every elementwise run followed by a layer or trailing, x and y distinct.
+    bool inplace = spline && y != nullptr && (const void*)y != (const void*)x && !getenv("B2F_ROWS_NO_INPLACE");
+    if (inplace) {
+        int nflip = 0, state = 0;      // state 0: no run pending, 1: run pending, 2: run pending and a flip seen after it
+        for (int i = 0; i < n_ops && inplace; ++i) {
+            const b2f_op_t& o = ops[i];
+            if (o.kind == B2F_OP_FLIP) { ++nflip; if (state == 1) state = 2; continue; }
+            if (o.kind == B2F_OP_ELEMENTWISE) { if (state == 2) inplace = false; state = 1; continue; }
+            if (!(o.kind == B2F_OP_MADE_SEQ && (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV))) inplace = false;
+            state = 0;
+        }
+        if (nflip & 1) inplace = false;
+    }
+    if (inplace) XS = 0;                                           // no tile
     const int rq_stride = spline ? ((Hrq * 24 + 24 + 3) & ~3) : 0;
     const size_t smem = sizeof(float) * ((size_t)(NT / 32) * 32 * R * XS + (size_t)n_runs * 2 * D + 2 * D + 8 + wtotal +
                                          (size_t)(NT / 32) * 2 * rq_stride);
     if (smem > 110 * 1024) return 0;
     A.n_ops = n_ops; A.D = D; A.XS = XS; A.B = B; A.flags = flags; A.n_runs = n_runs;
-    A.wtotal = (int)wtotal; A.rq_stride = rq_stride;
+    A.wtotal = (int)wtotal; A.rq_stride = rq_stride; A.inplace = inplace ? 1 : 0;
     A.x = x; A.y = y; A.log_det = log_det; A.log_prob = log_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
     // a warp walks tiles_per_warp consecutive 32-row tiles (the per-CTA weight staging is amortised over them) while the
     // grid stays several waves deep, so that the hardware CTA scheduler still balances the SMs

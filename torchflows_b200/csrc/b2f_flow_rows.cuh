@@ -39,6 +39,7 @@ struct RowsArgs {
     DevOp ops[B2F_MAX_OPS];
     int n_ops, D, XS, flags, n_runs, tiles_per_warp;
     int wtotal, rq_stride;      // floats of all staged weights; floats per per-warp streaming buffer (spline layers)
+    int inplace;                // spline programs with an output buffer: rows live in y (global memory), no shared tile
     int woff[B2F_MAX_OPS];      // float offset of each conditioner layer's staged weights in the weight area
     long long B;
     const float* x;
@@ -286,9 +287,13 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const 
 // InverseAutoregressiveRQNSF density).  The output layer is 23 x H weights PER ELEMENT (tile layout [e][j][24] in global
 // memory): too large to stage for all D elements, so every warp streams the next element's block (H*24 + 23 floats)
 // into its own double buffer with cp.async while it works on the current element.
+// `xin`: where this layer reads its input row from (the kernel's input x for the first layer of an in-place program,
+// otherwise x0 itself); `live`: the thread owns a real row (threads past the end of the batch still take part in the
+// warp-wide weight staging but must not touch global memory).
 template <int TK, int MODE, int HP>
-__device__ __forceinline__ void rows_sequential_rq(float* x0, int D, int rev, const DevOp& op, const RowsWeights<HP>& W,
-                                                   const float* er, float* wst, int wst_stride, float& ld) {
+__device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, bool live, int D, int rev, const DevOp& op,
+                                                   const RowsWeights<HP>& W, const float* er, float* wst, int wst_stride,
+                                                   float& ld) {
     constexpr int P = 23, PP = 24;
     const int H = op.H, lane = threadIdx.x & 31;
     float pre[HP], act[HP];
@@ -325,7 +330,7 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, int D, int rev, co
         __syncwarp();                                 // element i's weights have landed; the other buffer is free
         if (i + 1 < D) stage(i + 1, buf[cur ^ 1]);
         const float* w2e = buf[cur];
-        float v = x0[c];
+        float v = live ? xin[c] : 0.0f;
         if (er) v = fmaf(er[c], v, er[D + c]);
 #pragma unroll
         for (int j = 0; j < HP; ++j)
@@ -354,7 +359,7 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, int D, int rev, co
         } else {
             transform_element<TK, MODE, PP>(v, acc, op.boundary, out, l);
         }
-        x0[c] = out;
+        if (live) x0[c] = out;
         ld += l;
 #pragma unroll
         for (int j4 = 0; j4 < HP / 4; ++j4) {
@@ -382,13 +387,15 @@ __device__ __forceinline__ void rows_layer_tk(const float* wbuf, float* x0, int 
 
 template <int MODE, int HP, int R, bool RQ>
 __device__ __forceinline__ void rows_layer(const float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
-                                           const float* er, float (&ld)[R], float* wst, int wst_stride) {
+                                           const float* er, float (&ld)[R], float* wst, int wst_stride,
+                                           const float* xin = nullptr, bool live = true) {
     if constexpr (RQ) {
         static_assert(R == 1, "spline layers: one row per thread");
         if (op.tkind == B2F_T_RQ_FWD || op.tkind == B2F_T_RQ_INV) {       // sequential spline layer (host guarantees MADE_SEQ)
             const RowsWeights<HP> W = weights_view<HP>(wbuf, D);
-            if (op.tkind == B2F_T_RQ_INV) rows_sequential_rq<B2F_T_RQ_INV, MODE, HP>(x0, D, flip, op, W, er, wst, wst_stride, ld[0]);
-            else rows_sequential_rq<B2F_T_RQ_FWD, MODE, HP>(x0, D, flip, op, W, er, wst, wst_stride, ld[0]);
+            const float* in = xin ? xin : x0;
+            if (op.tkind == B2F_T_RQ_INV) rows_sequential_rq<B2F_T_RQ_INV, MODE, HP>(x0, in, live, D, flip, op, W, er, wst, wst_stride, ld[0]);
+            else rows_sequential_rq<B2F_T_RQ_FWD, MODE, HP>(x0, in, live, D, flip, op, W, er, wst, wst_stride, ld[0]);
             return;
         }
     }
@@ -478,6 +485,8 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
     for (int w = 0; w < NW; ++w) { ldc += red[w]; gconst += red[NW + w]; }
     const bool want_lp = A.log_prob != nullptr;
     float* x0 = xw + lane * XS;                          // row r of this thread: x0 + r*32*XS
+    bool inplace = false;
+    if constexpr (RQ) inplace = A.inplace != 0;          // rows stay in global memory (y): no tile, twice the resident warps
 
   for (int tt = 0; tt < A.tiles_per_warp; ++tt) {
     // ---- this warp's next 32*R rows: asynchronous 16-byte copies global -> shared (rows beyond B are zero-filled) -------
@@ -485,7 +494,12 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
     const int rows = (int)max(0LL, min((long long)TMW, A.B - wrow0));
     if (rows == 0) break;
     __syncwarp();      // every lane is done with the previous tile
-    {
+    const bool live = !inplace || lane < rows;
+    const float* xin = nullptr;                          // in-place mode: the first layer reads the thread's row of x
+    if (inplace) {
+        x0 = A.y + (wrow0 + (live ? lane : 0)) * D;
+        xin = A.x + (wrow0 + (live ? lane : 0)) * D;
+    } else {
         const float4* src = reinterpret_cast<const float4*>(A.x + wrow0 * D);
         int m = 0, c4 = lane;
         while (c4 >= D4) { c4 -= D4; ++m; }
@@ -507,7 +521,7 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
     const float* er = nullptr;      // elementwise run that has been reached but not applied yet: the next conditioner layer
                                     // (or the epilogue) applies it on the fly to the values it loads anyway
     // DiagonalGaussian.log_prob (gaussian.py:46-54) of the thread's rows as they stand (after the pending run, if any)
-    auto base_logp = [&]() {
+    auto base_logp = [&](const float* rowp, bool write_back) {
         float s[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) s[r] = 0.0f;
@@ -517,9 +531,10 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
             ld4(gb + D, c0, isc);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float xv[4];
-                ld4(x0 + r * 32 * XS, c0, xv);
+                float xv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (live) ld4(rowp + r * 32 * XS, c0, xv);
                 if (er) apply_run(er, D, c0, xv);
+                if (write_back && live) st4(x0 + r * 32 * XS, c0, xv);       // in-place mode: the trailing elementwise run
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float t = (xv[u] - loc[u]) * isc[u];
@@ -530,7 +545,7 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
 #pragma unroll
         for (int r = 0; r < R; ++r) lp[r] = -(s[r] + gconst);
     };
-    if (want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp();
+    if (want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp(xin ? xin : x0, false);
 
     // ---- the layers ------------------------------------------------------------------------------------------------
     int run = 0, flip = 0;
@@ -554,12 +569,22 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
             ++run;
             continue;
         }
-        rows_layer<MODE, HP, R, RQ>(wbuf + A.woff[oi], x0, XS, D, flip, op, er, ld, wst, A.rq_stride);
+        rows_layer<MODE, HP, R, RQ>(wbuf + A.woff[oi], x0, XS, D, flip, op, er, ld, wst, A.rq_stride, xin, live);
         er = nullptr;
+        xin = nullptr;                                   // later layers read what this one wrote
     }
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
-    if (want_lp && !(A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp();
+    if (inplace) {
+        // the rows are already where they belong; the host guarantees an even number of flips and at least one layer
+        if (want_lp && !(A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp(x0, er != nullptr);
+        else if (er) {
+            for (int c0 = 0; c0 < D; c0 += 4) {
+                float xv[4];
+                if (live) { ld4(x0, c0, xv); apply_run(er, D, c0, xv); st4(x0, c0, xv); }
+            }
+        }
+    } else if (want_lp && !(A.flags & B2F_FLOW_LOGP_OF_INPUT)) base_logp(x0, false);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int m = r * 32 + lane;
@@ -569,7 +594,7 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
             if (want_lp) A.log_prob[wrow0 + m] = lp[r] + l;
         }
     }
-    if (A.y) {
+    if (A.y && !inplace) {
         __syncwarp();
         float4* dst = reinterpret_cast<float4*>(A.y + wrow0 * D);
         int m = 0, c4 = lane;
