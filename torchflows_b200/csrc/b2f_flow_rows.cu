@@ -90,21 +90,27 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
         wtotal += (size_t)n_src * HP + HP + (rq ? 0 : (size_t)n_tgt * P * HP);
     }
     const int R = 1;
-    // Programs whose conditioner layers are ALL sequential spline layers and that produce an output (sampling): the rows
+    // Programs whose conditioner layers are ALL sequential (MAF / MA-RQNSF sampling) and that produce an output: the rows
     // live in the output buffer itself -- every thread walks its own row of y in global memory (L1 keeps its current
     // line) -- so no shared-memory tile limits the number of resident warps.  Needs: an even number of flips (the result
     // is already in logical order), every elementwise run followed by a layer or trailing, x and y distinct.
-    bool inplace = spline && y != nullptr && (const void*)y != (const void*)x && !getenv("B2F_ROWS_NO_INPLACE");
+    bool inplace = y != nullptr && (const void*)y != (const void*)x && !getenv("B2F_ROWS_NO_INPLACE");
     if (inplace) {
         int nflip = 0, state = 0;      // state 0: no run pending, 1: run pending, 2: run pending and a flip seen after it
         for (int i = 0; i < n_ops && inplace; ++i) {
             const b2f_op_t& o = ops[i];
             if (o.kind == B2F_OP_FLIP) { ++nflip; if (state == 1) state = 2; continue; }
             if (o.kind == B2F_OP_ELEMENTWISE) { if (state == 2) inplace = false; state = 1; continue; }
-            if (!(o.kind == B2F_OP_MADE_SEQ && (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV))) inplace = false;
+            if (o.kind != B2F_OP_MADE_SEQ) inplace = false;   // one-pass layers walk a row twice: measured slower in place
             state = 0;
         }
         if (nflip & 1) inplace = false;
+    }
+    if (inplace && !spline) {
+        // affine / shift programs: worth it only when the tile, not the register file, limits the resident warps
+        const size_t with_tile = sizeof(float) * ((size_t)(NT / 32) * 32 * XS + (size_t)n_runs * 2 * D + 2 * D + 8 + wtotal);
+        const size_t ctas = (220 * 1024) / with_tile;
+        if (ctas * (NT / 32) >= 16) inplace = false;
     }
     if (inplace) XS = 0;                                           // no tile
     const int rq_stride = spline ? ((Hrq * 24 + 24 + 3) & ~3) : 0;

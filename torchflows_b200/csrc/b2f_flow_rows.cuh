@@ -153,7 +153,10 @@ __device__ __forceinline__ void row_params(float (&acc)[R][P], const float4* __r
 // columns [ps0, ps0+n_src), targets [pt0, pt0+n_tgt)
 template <int TK, int MODE, int HP, int R>
 __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp& op, const RowsWeights<HP>& W, int ps0,
-                                          int n_src, int pt0, int n_tgt, const float* er, float (&ld)[R]) {
+                                          int n_src, int pt0, int n_tgt, const float* er, float (&ld)[R],
+                                          const float* xin, bool live) {
+    // xin / live: in-place mode (rows in global memory), see rows_sequential_rq; xin == nullptr and live == true otherwise
+    const float* sin = xin ? xin : x0;
     constexpr int P = TInfo<TK>::P;
     const int H = op.H;
     float hid[R][HP];
@@ -169,11 +172,10 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp&
         float xv[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            ld4(x0 + r * 32 * XS, c0, xv[r]);
-            if (er) {      // pending elementwise run: apply it to the source columns on the way in and write them back
-                apply_run(er, D, c0, xv[r]);
-                st4(x0 + r * 32 * XS, c0, xv[r]);
-            }
+            xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0f;
+            if (live) ld4(sin + r * 32 * XS, c0, xv[r]);
+            if (er) apply_run(er, D, c0, xv[r]);   // pending elementwise run: applied to the source columns on the way in
+            if ((er || xin) && live) st4(x0 + r * 32 * XS, c0, xv[r]);      // ... and written back (or copied x -> y)
         }
 #pragma unroll
         for (int j = 0; j < HP; ++j) {
@@ -193,12 +195,14 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp&
         for (int r = 0; r < R; ++r) hid[r][j] = (j == H) ? 1.0f : rows_tanh<MODE>(hid[r][j]);   // slot H carries the bias;
     }                                                                    // padded units: tanh(0) = 0 times zero weights
     const bool ew_targets = er != nullptr && pt0 != ps0;     // coupling: the loop above did not touch the targets
+    const float* tin = (xin && pt0 != ps0) ? xin : x0;       // ... so in-place mode still finds them in the input
     const float4* w2 = reinterpret_cast<const float4*>(W.w2);
     for (int c0 = pt0; c0 < pt0 + n_tgt; c0 += 4, w2 += 4 * P * (HP / 4)) {
         float xv[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            ld4(x0 + r * 32 * XS, c0, xv[r]);
+            xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0f;
+            if (live) ld4(tin + r * 32 * XS, c0, xv[r]);
             if (ew_targets) apply_run(er, D, c0, xv[r]);
         }
 #pragma unroll
@@ -214,7 +218,8 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp&
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) st4(x0 + r * 32 * XS, c0, xv[r]);
+        for (int r = 0; r < R; ++r)
+            if (live) st4(x0 + r * 32 * XS, c0, xv[r]);
     }
 }
 
@@ -224,7 +229,8 @@ __device__ __forceinline__ void rows_pass(float* x0, int XS, int D, const DevOp&
 // REV: the tile is flipped, logical step i lives at physical column D-1-i, so physical columns are walked downwards.
 template <int TK, int MODE, int HP, int R, bool REV>
 __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const DevOp& op, const RowsWeights<HP>& W,
-                                                const float* er, float (&ld)[R]) {
+                                                const float* er, float (&ld)[R], const float* xin, bool live) {
+    const float* sin = xin ? xin : x0;
     constexpr int P = TInfo<TK>::P;
     const int H = op.H;
     float pre[R][HP], act[R][HP];
@@ -243,7 +249,8 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const 
         float xv[R][4];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            ld4(x0 + r * 32 * XS, c0, xv[r]);
+            xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0f;
+            if (live) ld4(sin + r * 32 * XS, c0, xv[r]);
             if (er) apply_run(er, D, c0, xv[r]);
         }
 #pragma unroll
@@ -279,7 +286,8 @@ __device__ __forceinline__ void rows_sequential(float* x0, int XS, int D, const 
             }
         }
 #pragma unroll
-        for (int r = 0; r < R; ++r) st4(x0 + r * 32 * XS, c0, xv[r]);
+        for (int r = 0; r < R; ++r)
+            if (live) st4(x0 + r * 32 * XS, c0, xv[r]);
     }
 }
 
@@ -374,15 +382,15 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
 
 template <int TK, int MODE, int HP, int R>
 __device__ __forceinline__ void rows_layer_tk(const float* wbuf, float* x0, int XS, int D, int flip, const DevOp& op,
-                                              const float* er, float (&ld)[R]) {
+                                              const float* er, float (&ld)[R], const float* xin, bool live) {
     const bool seq = op.kind == B2F_OP_MADE_SEQ;
     const bool coupling = op.kind == B2F_OP_COUPLING;
     const int n_src = coupling ? D / 2 : D, n_tgt = coupling ? D - D / 2 : D;      // HalfSplit: first D//2 logical columns
     const int ps0 = flip ? D - n_src : 0, pt0 = (flip || !coupling) ? 0 : D - n_tgt;
     const RowsWeights<HP> W = weights_view<HP>(wbuf, n_src);
-    if (!seq) rows_pass<TK, MODE, HP, R>(x0, XS, D, op, W, ps0, n_src, pt0, n_tgt, er, ld);
-    else if (flip) rows_sequential<TK, MODE, HP, R, true>(x0, XS, D, op, W, er, ld);
-    else rows_sequential<TK, MODE, HP, R, false>(x0, XS, D, op, W, er, ld);
+    if (!seq) rows_pass<TK, MODE, HP, R>(x0, XS, D, op, W, ps0, n_src, pt0, n_tgt, er, ld, xin, live);
+    else if (flip) rows_sequential<TK, MODE, HP, R, true>(x0, XS, D, op, W, er, ld, xin, live);
+    else rows_sequential<TK, MODE, HP, R, false>(x0, XS, D, op, W, er, ld, xin, live);
 }
 
 template <int MODE, int HP, int R, bool RQ>
@@ -400,10 +408,10 @@ __device__ __forceinline__ void rows_layer(const float* wbuf, float* x0, int XS,
         }
     }
     switch (op.tkind) {
-        case B2F_T_SHIFT_ADD: rows_layer_tk<B2F_T_SHIFT_ADD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
-        case B2F_T_SHIFT_SUB: rows_layer_tk<B2F_T_SHIFT_SUB, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
-        case B2F_T_AFFINE_FWD: rows_layer_tk<B2F_T_AFFINE_FWD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
-        case B2F_T_AFFINE_INV: rows_layer_tk<B2F_T_AFFINE_INV, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld); break;
+        case B2F_T_SHIFT_ADD: rows_layer_tk<B2F_T_SHIFT_ADD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld, xin, live); break;
+        case B2F_T_SHIFT_SUB: rows_layer_tk<B2F_T_SHIFT_SUB, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld, xin, live); break;
+        case B2F_T_AFFINE_FWD: rows_layer_tk<B2F_T_AFFINE_FWD, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld, xin, live); break;
+        case B2F_T_AFFINE_INV: rows_layer_tk<B2F_T_AFFINE_INV, MODE, HP, R>(wbuf, x0, XS, D, flip, op, er, ld, xin, live); break;
         default: break;
     }
 }
@@ -485,8 +493,7 @@ __global__ void __launch_bounds__(NT) flow_rows_kernel(const __grid_constant__ R
     for (int w = 0; w < NW; ++w) { ldc += red[w]; gconst += red[NW + w]; }
     const bool want_lp = A.log_prob != nullptr;
     float* x0 = xw + lane * XS;                          // row r of this thread: x0 + r*32*XS
-    bool inplace = false;
-    if constexpr (RQ) inplace = A.inplace != 0;          // rows stay in global memory (y): no tile, twice the resident warps
+    const bool inplace = A.inplace != 0;                 // rows stay in global memory (y): no tile, more resident warps
 
   for (int tt = 0; tt < A.tiles_per_warp; ++tt) {
     // ---- this warp's next 32*R rows: asynchronous 16-byte copies global -> shared (rows beyond B are zero-filled) -------
