@@ -12,12 +12,19 @@
 // element) the conditioner is ~1-2 kFLOP per row -- far too small for a 128-row tensor-core tile pipeline (measured:
 // barrier round trips dominate) and dominated by shared-memory traffic and __syncthreads in the warp-per-element
 // mapping of b2f_flow.cu.  Here a THREAD owns R rows for the whole program:
-//   * the hidden activations hid[R][HB] and the transformer parameters acc[R][PP] live in registers;
-//   * every weight address is uniform over the CTA, so a weight is one broadcast 16-byte load from L1 that feeds
-//     4*R FFMAs in each of the 32 lanes;
-//   * a warp only ever touches its own 32*R rows of the shared-memory tile, so after the tile load there is no CTA
-//     barrier at all: layers, the D-step sequential inverse of a masked autoregressive layer (layers_base.py:213-223)
-//     and the base log-density run back to back, warps drift freely and hide each other's latency;
+//   * the hidden activations hid[R][HP] and the transformer parameters acc[R][P] live in registers (R = 1 is what ships:
+//     two rows per thread measured slower, occupancy beats weight reuse);
+//   * the weights of EVERY conditioner layer are staged once per CTA in shared memory, zero-padded to HP = 4*HP4 hidden
+//     units with the output bias in a constant-1 hidden slot, so every inner loop has a compile-time trip count and a
+//     weight is one broadcast 16-byte shared-memory load that feeds 4 FFMAs in each of the 32 lanes; spline layers (23 x H
+//     weights per element) stream the next element's block into a per-warp double buffer with cp.async instead;
+//   * a warp only ever touches its own 32 rows (cp.async tile load, several tiles per warp), so after the one staging
+//     barrier there is no CTA barrier at all: layers, the D-step sequential inverse of a masked autoregressive layer
+//     (layers_base.py:213-223) and the base log-density run back to back, warps drift freely and hide each other's
+//     latency;
+//   * all-sequential programs that write an output keep their rows in the output buffer itself (`inplace`: a thread walks
+//     its own row of y in global memory, L1 holds its current line): no tile, so registers, not shared memory, bound the
+//     resident warps;
 //   * the tile row stride XS is a multiple of 4 floats with XS/4 odd, so a thread reads/writes 4 consecutive columns
 //     of its row with one conflict-free 16-byte shared-memory access;
 //   * ReversePermutationMatrix (matrix/permutation.py:19-37) never moves data: a FLIP only toggles how logical columns
