@@ -114,7 +114,11 @@ def flow_apply(ops: Sequence[dict], x: torch.Tensor, want_y=True, want_log_det=T
     save them -- b2f_flow_apply_saving)."""
     x = require_cuda_f32(x, 'flow input')
     B, D = x.shape
-    y = torch.empty_like(x) if want_y else None
+    # all-sequential programs (IAF / IA-RQNSF densities) run in place in their output buffer (csrc/b2f_flow_rows.cu): give
+    # them one even when the caller only wants the log-density
+    kinds = [o['kind'] for o in ops]
+    scratch_y = (not want_y) and OP_MADE_SEQ in kinds and all(k in (OP_ELEMENTWISE, OP_FLIP, OP_MADE_SEQ) for k in kinds)
+    y = torch.empty_like(x) if (want_y or scratch_y) else None
     ld = torch.empty(B, device=x.device, dtype=torch.float32) if want_log_det else None
     lp = torch.empty(B, device=x.device, dtype=torch.float32) if want_log_prob else None
     arr = make_ops(ops)
@@ -122,14 +126,14 @@ def flow_apply(ops: Sequence[dict], x: torch.Tensor, want_y=True, want_log_det=T
         if not save_layer_inputs:
             check(lib().b2f_flow_apply(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
                                        ptr(base_log_scale), B, D, flags, stream_ptr(x.device)))
-            return y, ld, lp
+            return (y if want_y else None), ld, lp
         ws_bytes = int(lib().b2f_flow_backward_workspace(arr, len(ops), B, D))
         ws = torch.empty(max(ws_bytes, 4) // 4, device=x.device, dtype=torch.float32)
         saved = ctypes.c_int32(0)
         check(lib().b2f_flow_apply_saving(arr, len(ops), ptr(x), ptr(y), ptr(ld), ptr(lp), ptr(base_loc),
                                           ptr(base_log_scale), ptr(ws), ctypes.byref(saved), B, D, flags,
                                           stream_ptr(x.device)))
-    return y, ld, lp, (ws if saved.value else None)
+    return (y if want_y else None), ld, lp, (ws if saved.value else None)
 
 
 def transformer_apply(tkind, x2: torch.Tensor, h: torch.Tensor, h_row_stride: int, n_bins=8, boundary=50.0,
