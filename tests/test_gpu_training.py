@@ -280,3 +280,31 @@ def test_fit_with_cuda_graph_matches_eager_fit(preset, D, n, bs):
         with torch.no_grad():
             finals.append(flow.log_prob(x.to(dev)).mean().item())
     assert abs(finals[0] - finals[1]) < 5e-3 * (1 + abs(finals[0])), finals
+
+
+def test_flow_apply_saving_reports_whether_layer_inputs_were_saved():
+    """b2f_flow_apply_saving: the tensor-core kernel writes the conditioner-layer inputs (first layer's = the flow input
+    after the leading elementwise run; checked for an identity ElementwiseAffine), the other kernels report saved = 0."""
+    from torchflows_b200 import Flow, _native as N, _program as P
+    from torchflows_b200.architectures import CouplingRQNSF, RealNVP
+    dev = torch.device('cuda:0')
+    torch.manual_seed(0)
+    x = torch.randn(300, 64, device=dev)
+    for cls, expect in ((CouplingRQNSF, True), (RealNVP, False)):
+        flow = Flow(cls(64)).to(dev).eval()
+        ops = flow.bijection.fused_ops('forward')
+        with torch.no_grad():
+            y, ld, lp, ws = N.flow_apply(P.op_dicts(ops, D=64), x, True, True, False, None, None, 0, save_layer_inputs=True)
+            y2, ld2, _ = N.flow_apply(P.op_dicts(ops, D=64), x, True, True, False, None, None, 0)
+        assert (ws is not None) == expect, cls.__name__
+        assert torch.equal(y, y2) and torch.equal(ld, ld2)
+        if ws is not None:
+            n_cond = sum(1 for o in ops if o.kind in (N.OP_COUPLING, N.OP_MADE, N.OP_MADE_SEQ))
+            saved = ws[:n_cond * 300 * 64].view(n_cond, 300, 64)
+            # what enters the first coupling layer is the leading ElementwiseAffine applied to x (the flip in between only
+            # relabels columns)
+            assert ops[0].kind == N.OP_ELEMENTWISE and ops[1].kind == N.OP_FLIP
+            with torch.no_grad():
+                first_in = P.run_program([ops[0]], x)[0]
+            assert torch.allclose(saved[0], first_in, atol=1e-5)
+            assert torch.isfinite(saved).all()
