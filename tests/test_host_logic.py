@@ -176,3 +176,51 @@ def test_data_parallel_helpers_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and 'ok' in o, o
+
+
+def test_weight_snapshots_follow_in_place_updates():
+    """BaseFlow._snapshot_weights (the keep-best-weights copy of fit, flows.py:246,429): the first call clones the
+    state_dict, later calls refresh the same buffers from the live tensors; ActNorm's data-dependent initialisation is in
+    place, so the live tensors stay the ones the snapshot remembers."""
+    import torch
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import RealNVP
+    torch.manual_seed(0)
+    flow = Flow(RealNVP(4))
+    snap = flow._snapshot_weights()
+    assert set(snap.keys()) == set(flow.state_dict().keys())
+    storages = {k: v.data_ptr() for k, v in snap.items()}
+    with torch.no_grad():
+        for p in flow.parameters():
+            p.add_(1.0)
+    stale = {k: v.clone() for k, v in snap.items()}
+    snap2 = flow._snapshot_weights(snap)
+    assert snap2 is snap and all(v.data_ptr() == storages[k] for k, v in snap.items())
+    for k, v in flow.state_dict().items():
+        assert torch.equal(snap[k], v)
+        if v.is_floating_point() and v.numel() and k.endswith(('weight', 'bias', 'value')):
+            assert not torch.equal(stale[k], v)
+    flow.load_state_dict(stale)
+    for k, v in flow.state_dict().items():
+        assert torch.equal(stale[k], v)
+
+
+def test_composition_regularization_sums_layer_terms():
+    """BijectiveComposition.regularization (bijections/base.py:234-243): l2_coef * sum of squared trainable parameters of
+    the layers that ask for it, zero placeholders ignored."""
+    import torch
+    from torchflows_b200.architectures import RealNVP
+    torch.manual_seed(0)
+    bij = RealNVP(6)
+    expected = 0.0
+    n_reg = 0
+    for layer in bij.layers:
+        if getattr(layer, 'l2_regularization', False) and getattr(layer, 'l2_coef', 0.0) > 0:
+            expected = expected + layer.l2_coef * sum(float((p.detach() ** 2).sum()) for p in layer.parameters() if p.requires_grad)
+            n_reg += 1
+    total = bij.regularization()
+    assert isinstance(total, torch.Tensor) and total.dim() == 0
+    assert abs(float(total) - float(expected)) <= 1e-6 * (1 + abs(float(expected)))
+    if n_reg:
+        total.backward()
+        assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in bij.parameters())
