@@ -220,7 +220,7 @@ def test_composition_regularization_sums_layer_terms():
             n_reg += 1
     total = bij.regularization()
     assert isinstance(total, torch.Tensor) and total.dim() == 0
-    assert abs(float(total) - float(expected)) <= 1e-6 * (1 + abs(float(expected)))
+    assert abs(float(total.detach()) - float(expected)) <= 1e-6 * (1 + abs(float(expected)))
     if n_reg:
         total.backward()
         assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in bij.parameters())
