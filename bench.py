@@ -182,6 +182,29 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def transformer_kernel_roofline(torch, dev, hbm_peak):
+    """Stand-alone rational-quadratic spline transformer (b2f_transformer_apply, dense parameters): 16384 x 512 elements,
+    (23 + 2) * 4 algorithmic bytes per element, CUDA-event timing over 10 launches, operands (771 MB of h) larger than L2."""
+    from torchflows_b200 import _native as N
+    rows, E, P = 16384, 512, 23
+    x = torch.randn(rows, E, device=dev) * 2
+    h = torch.randn(rows, E * P, device=dev)
+    for _ in range(3):
+        N.transformer_apply(N.T_RQ_FWD, x, h, E * P, 8, 50.0)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        N.transformer_apply(N.T_RQ_FWD, x, h, E * P, 8, 50.0)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 10
+    achieved = rows * E * (P + 2) * 4 / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'kernel': 'b2f::transformer_kernel<RQ_FWD> (b2f_transformer_apply)', 'achieved': achieved,
+            'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'algorithmic_bytes_per_element': (P + 2) * 4,
+            'elements': rows * E, 'launch_ms': ms}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -371,6 +394,13 @@ def run_ours(args):
                            'note': "torchflows_b200.set_math_mode('fast'): opt-in, bin indices not bit-reproducible"},
         'clocks': sampler.summary(),
     }
+    if rank == 0:
+        # SURVEY 8d asks for the per-layer transformer kernel next to the whole-flow one: the stand-alone spline transformer
+        # (b2f_transformer_apply given materialised parameters) is the genuinely HBM-bound kernel of this path
+        try:
+            line['per_layer_roofline'] = transformer_kernel_roofline(torch, dev, hbm_peak)
+        except Exception as e:       # never let the side measurement take the headline down
+            line['per_layer_roofline'] = {'error': str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu:
         sd = {k: v.cpu() for k, v in flow.state_dict().items()}
         v, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, 3, 1)
