@@ -68,8 +68,8 @@ def build_oracle(force=False):
 
 def build_hostmath(force=False):
     src = os.path.join(ROOT, 'tests', 'host_math.cpp')
-    hdr = os.path.join(ROOT, 'torchflows_b200', 'csrc', 'b2f_math.cuh')
-    if force or _newer(HOSTMATH_SO, [src, hdr]):
+    hdrs = [os.path.join(ROOT, 'torchflows_b200', 'csrc', n) for n in ('b2f_math.cuh', 'b2f_rqfast.cuh')]
+    if force or _newer(HOSTMATH_SO, [src] + hdrs):
         os.makedirs(os.path.dirname(HOSTMATH_SO), exist_ok=True)
         _run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-x', 'c++', src, '-o', HOSTMATH_SO])
     return HOSTMATH_SO

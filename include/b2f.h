@@ -67,6 +67,26 @@ enum b2f_op_kind {
                                               = tf32 hi / lo parts of b2, rest zero.  Byte offset of (row, k) in an operand
                                               with K columns: (row/8)*K*32 + (k/4)*128 + (row%8)*16 + (k%4)*4 */
 #define B2F_FLAG_TC_FLIPPED 4       /* op flag: p[4] was laid out for a flipped tile (odd number of FLIP ops before) */
+#define B2F_FLAG_TCQ_OPERANDS 8     /* op flag (COUPLING, RQ, n_bins 8), set on EVERY coupling op of a program made of
+                                       ELEMENTWISE / FLIP / COUPLING ops: the program is laid out for the second-generation
+                                       spline kernel (csrc/b2f_flow_tcq.cu; layout produced by torchflows_b200/_tcq.py):
+                                       p[4] = layer blob (fp32 words, 16-byte aligned), with Dh = D/2, K2 = roundup(H+2, 8):
+                                         [0,8)  int32 header: magic 'BTCQ', physical source half (0|1), 1 if the source half must be
+                                                materialised (src affine below), H, K2, Dh/2 chunks, Dh, 0
+                                         W1c    canonical [32 x Dh] tf32, columns in PHYSICAL order of the source half
+                                         b1     32 floats (zero padded)
+                                         W2c    Dh/2 chunks, each canonical [48 x K2]: row = 24*(element in chunk) + folded column
+                                                (csrc/b2f_rqfast.cuh: log2e*u_x | log2e/1000*u_y | differences of padded derivative
+                                                logits), elements in PHYSICAL order of the target half; K columns H, H+1 = bias hi, lo
+                                         tgt    [Dh][8]: pre_a, pre_b (pending elementwise layers, applied when the element is read),
+                                                post_a, post_b (elementwise layers that follow, applied at write-back), fin_a, fin_b
+                                                (maps the written value to the standardised base-density argument; 0 unless this
+                                                layer is the last writer of the column), 0, 0
+                                         src    [Dh][2]: a, b of the pending elementwise layers on the source half
+                                         misc   [4]: sup |log2e*u_x|, sup |log2e*u_y/1000| over all inputs (from the weights), 0, 0
+                                       p[5] (first coupling op) = program blob: int32 {magic, final pass on half 0, on half 1, layers},
+                                         {sum of elementwise log-dets, base-density constant, 0, 0}, [D][2] final affine per physical
+                                         column, [D][2] (exp(-log_scale), -loc*exp(-log_scale)) of the base density per column */
 
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
@@ -158,6 +178,7 @@ int32_t b2f_abi_version(void);
 #define B2F_KERNEL_GENERIC 1
 #define B2F_KERNEL_TC 2
 #define B2F_KERNEL_ROWS 3
+#define B2F_KERNEL_TCQ 4 /* csrc/b2f_flow_tcq.cu: spline coupling programs laid out with B2F_FLAG_TCQ_OPERANDS */
 int32_t b2f_last_flow_kernel(void);
 
 #ifdef __cplusplus

@@ -2,6 +2,7 @@
 // suite check the kernels' per-element arithmetic against the oracle without a GPU.  Never part of
 // the product library.
 #include "../torchflows_b200/csrc/b2f_math.cuh"
+#include "../torchflows_b200/csrc/b2f_rqfast.cuh"
 
 using namespace b2f;
 
@@ -27,7 +28,52 @@ static void rq_run(const float* x, const float* h, float* out, float* ld, int32_
     }
 }
 
+// folded-parameter spline of the tensor-core kernel (b2f_rqfast.cuh): fold the 23 raw parameters of an element exactly like
+// torchflows_b200/_tcq.py folds the weights (log2e scaling, /1000, differences of the padded derivative logits)
+template <bool SAFE, int NY>
+static void rqfast_run(const float* x, const float* h, float* out, float* ld, int64_t n, float b, int inverse) {
+    for (int64_t i = 0; i < n; ++i) {
+        const float* u = h + i * 23;
+        float g[24];
+        for (int j = 0; j < 8; ++j) {
+            g[j] = rqf::kLog2e * u[j];
+            g[8 + j] = rqf::kLog2e * u[8 + j] / 1000.0f;
+        }
+        float a[9];
+        a[0] = a[8] = kRqEdgeU / 1000.0f;
+        for (int j = 1; j < 8; ++j) a[j] = u[16 + j - 1] / 1000.0f;
+        for (int j = 0; j < 8; ++j) g[16 + j] = a[j + 1] - a[j];
+        float ld2;
+        if (inverse) rqf::inverse<SAFE, NY>(x[i], g, b, out[i], ld2);
+        else rqf::forward<SAFE, NY>(x[i], g, b, out[i], ld2);
+        ld[i] = ld2 * rqf::kLn2;
+    }
+}
+
+template <bool SAFE, int NY>
+static void rqfast_g_run(const float* x, const float* g, float* out, float* ld2, int64_t n, float b, int inverse) {
+    for (int64_t i = 0; i < n; ++i) {
+        float gg[24];
+        for (int j = 0; j < 24; ++j) gg[j] = g[i * 24 + j];
+        if (inverse) rqf::inverse<SAFE, NY>(x[i], gg, b, out[i], ld2[i]);
+        else rqf::forward<SAFE, NY>(x[i], gg, b, out[i], ld2[i]);
+    }
+}
+
 extern "C" {
+// folded columns given directly (what the GEMM of the tensor-core kernel produces); ld2 in log2 units
+void hm_rqfast_g(const float* x, const float* g, float* out, float* ld2, int64_t n, float b, int inverse, int safe) {
+    if (safe) rqfast_g_run<true, 0>(x, g, out, ld2, n, b, inverse);
+    else rqfast_g_run<false, 2>(x, g, out, ld2, n, b, inverse);
+}
+
+void hm_rqfast(const float* x, const float* h, float* out, float* ld, int64_t n, float b, int inverse, int safe, int ny) {
+    if (safe) rqfast_run<true, 0>(x, h, out, ld, n, b, inverse);
+    else if (ny == 0) rqfast_run<false, 0>(x, h, out, ld, n, b, inverse);
+    else if (ny == 3) rqfast_run<false, 4>(x, h, out, ld, n, b, inverse);
+    else rqfast_run<false, 8>(x, h, out, ld, n, b, inverse);
+}
+
 float hm_exp_det(float t) { return exp_det(t); }
 
 void hm_rq(const float* x, const float* h, float* out, float* ld, int32_t* k, int64_t n, int nb, float b, int inverse,

@@ -15,8 +15,8 @@ def lib():
     global _lib
     if _lib is None:
         src = os.path.join(_HERE, 'host_math.cpp')
-        hdr = os.path.join(_HERE, '..', 'torchflows_b200', 'csrc', 'b2f_math.cuh')
-        if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        hdrs = [os.path.join(_HERE, '..', 'torchflows_b200', 'csrc', n) for n in ('b2f_math.cuh', 'b2f_rqfast.cuh')]
+        if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in [src] + hdrs):
             os.makedirs(os.path.dirname(_SO), exist_ok=True)
             subprocess.run(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-x', 'c++', src,
                             '-o', _SO], check=True)
@@ -40,6 +40,24 @@ def rq(x, h, n_bins, boundary, inverse, templated=True):
     lib().hm_rq(_p(xs), _p(hs), _p(out), _p(ld), _p(k), ctypes.c_int64(xs.size), ctypes.c_int(n_bins),
                 ctypes.c_float(boundary), ctypes.c_int(int(inverse)), ctypes.c_int(int(templated)))
     return torch.from_numpy(out), torch.from_numpy(ld), torch.from_numpy(k)
+
+
+def rqfast(x, h, boundary, inverse, safe=False, ny=0):
+    """Folded-parameter spline of the tensor-core kernel (csrc/b2f_rqfast.cuh); h: (..., 23) raw parameters."""
+    xs, hs = _np(x), _np(h)
+    out, ld = np.empty_like(xs), np.empty_like(xs)
+    lib().hm_rqfast(_p(xs), _p(hs), _p(out), _p(ld), ctypes.c_int64(xs.size), ctypes.c_float(boundary),
+                    ctypes.c_int(int(inverse)), ctypes.c_int(int(safe)), ctypes.c_int(ny))
+    return torch.from_numpy(out), torch.from_numpy(ld)
+
+
+def rqfast_g(x, g, boundary, inverse, safe=False):
+    """Same, the 24 folded columns per element given directly; returns out and the log-det in log2 units."""
+    xs, gs = _np(x), _np(g)
+    out, ld2 = np.empty_like(xs), np.empty_like(xs)
+    lib().hm_rqfast_g(_p(xs), _p(gs), _p(out), _p(ld2), ctypes.c_int64(xs.size), ctypes.c_float(boundary),
+                      ctypes.c_int(int(inverse)), ctypes.c_int(int(safe)))
+    return torch.from_numpy(out), torch.from_numpy(ld2)
 
 
 def rq_backward(x, h, gz, gl, n_bins, boundary):

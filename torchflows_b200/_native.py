@@ -17,11 +17,12 @@ MAX_OPS = 40
 FLAG_SEQ_LOGDET_EXACT = 1
 FLAG_TC_OPERANDS = 2
 FLAG_TC_FLIPPED = 4
+FLAG_TCQ_OPERANDS = 8
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 FLOW_MODE_FAST_KNOTS = 4
 FLOW_WS_FILLED = 8
-KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS = range(4)
+KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS, KERNEL_TCQ = range(5)
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
                 T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}
@@ -163,7 +164,7 @@ def transformer_backward(tkind, x2, h, h_row_stride, gout, gld, n_bins=8, bounda
 
 
 def last_flow_kernel() -> int:
-    """Which kernel this thread's last flow_apply launched (KERNEL_GENERIC / KERNEL_TC / KERNEL_ROWS)."""
+    """Which kernel this thread's last flow_apply launched (KERNEL_GENERIC / KERNEL_TC / KERNEL_ROWS / KERNEL_TCQ)."""
     return int(lib().b2f_last_flow_kernel())
 
 

@@ -9,12 +9,14 @@ Linear weight in *tile layout* ([element][hidden][param], see include/b2f.h) and
 by their masks, so ``kernel_params`` derives those once per parameter version and caches them on the layer.
 ``FlowFunction`` is the single ``torch.autograd.Function`` through which every fused call goes.
 """
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
 import torch
 
 from . import _native as N
+from . import _tcq
 
 
 @dataclass
@@ -169,13 +171,20 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
 
 
 def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None,
-             D: Optional[int] = None):
+             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None):
+    """b2f_op descriptors of a program.  ``tcq_plan``: the program is laid out for the second-generation spline kernel
+    (csrc/b2f_flow_tcq.cu): every coupling op carries its blob in p[4], the first one the program blob in p[5]."""
     out = []
     flipped = False
+    n_coupling = 0
     for i, op in enumerate(ops):
         p, flags = list(kernel_params(op)), op.flags
         if op.kind == N.OP_FLIP:
             flipped = not flipped
+        elif tcq_plan is not None and op.kind == N.OP_COUPLING:
+            p = p[:4] + [tcq_plan.layer_blobs[n_coupling], tcq_plan.program_blob if n_coupling == 0 else None]
+            flags |= N.FLAG_TCQ_OPERANDS
+            n_coupling += 1
         elif D is not None and grads is None and tc_eligible(op, D):
             w1c, w2c = tc_operands(op, flipped, D)
             p = p[:4] + [w1c, w2c]
@@ -313,6 +322,11 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     if needs_grad:
         y, ld, lp = FlowFunction.apply(x2, _Cfg(ops, want_log_prob, base_loc, base_log_scale, flags), *leafs)
         return y, ld, (lp if want_log_prob else None)
-    y, ld, lp = N.flow_apply(op_dicts(ops, D=x2.shape[1]), x2.detach(), want_y, True, want_log_prob, base_loc,
+    D = x2.shape[1]
+    plan = None
+    if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
+            and _tcq.eligible(ops, D)):
+        plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
+    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan), x2.detach(), want_y, True, want_log_prob, base_loc,
                              base_log_scale, flags)
     return y, ld, lp

@@ -201,6 +201,8 @@ namespace b2f {
 int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                        const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                        void* stream, float* ws);   // b2f_flow_tc.cu (ws: optional save area for the layer inputs)
+int try_launch_flow_tcq(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
+                        int64_t B, int32_t D, int32_t flags, void* stream);   // b2f_flow_tcq.cu
 int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                          const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                          void* stream);  // b2f_flow_rows.cu
@@ -222,6 +224,11 @@ static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, f
         bool has_rq = false;
         for (int i = 0; i < n_ops; ++i)
             if (ops[i].kind >= B2F_OP_COUPLING && (ops[i].tkind == B2F_T_RQ_FWD || ops[i].tkind == B2F_T_RQ_INV)) has_rq = true;
+        if (has_rq && !ws) {       // programs laid out for the second-generation spline kernel (B2F_FLAG_TCQ_OPERANDS)
+            const int rc = try_launch_flow_tcq(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream);
+            if (rc == 1) last_flow_kernel() = B2F_KERNEL_TCQ;
+            if (rc != 0) return rc == 1 ? B2F_OK : rc;
+        }
         for (int attempt = 0; attempt < 2; ++attempt) {
             const bool tc = has_rq ? attempt == 0 : attempt == 1;
             const int rc = tc ? try_launch_flow_tc(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream, ws)

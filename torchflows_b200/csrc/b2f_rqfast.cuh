@@ -1,0 +1,198 @@
+// Rational-quadratic spline transformer, "folded" formulation for the tensor-core coupling kernel
+// (b2f_flow_tcq.cu).  Same function as rq_apply in b2f_math.cuh (reference: transformers/spline/base.py:29-72,
+// transformers/spline/rational_quadratic.py:45-200), restructured so that one element costs ~150 issue slots
+// instead of ~540:
+//
+//  * the output layer of the conditioner is linear, so every *linear* step of the parameterisation is folded into
+//    its weights when the operands are laid out (torchflows_b200/_tcq.py): the 24 GEMM columns of an element are
+//        g[0..8)   L_j  = log2(e) * u_x[j]                      widths logits, ready for ex2
+//        g[8..16)  Dl_j = log2(e) * u_y[j] / 1000               heights logits are L_j + Dl_j  (rational_quadratic.py:76)
+//        g[16..24) Dd_i = a[i+1] - a[i],  a = c + [c, u_d, c]/1000   differences of the padded derivative logits
+//    (rational_quadratic.py:77,125-127: the pad value c is itself divided by 1000), so a[k] and a[k+1] are prefix sums
+//    selected by the search predicates;
+//  * knots are never materialised: the search runs on the normalised cumulative bin sizes against
+//    t = (v + b) / 2b, and the quantities of the selected bin (lower knot, upper knot for x and y, the two
+//    derivative logits) are accumulated with *predicated adds* under the 7 search predicates (monotone, so the
+//    predicated prefix sum IS the k-th cumulative sum, in the reference's summation order);
+//  * heights softmax: exp(L + Dl) = exp(L) * 2^Dl with a cubic for 2^Dl when the host proves |Dl| < 1/32 from the
+//    weights (|tanh| <= 1), else the SFU;  no max-subtraction when the host proves |L| < 40 (same bound);
+//  * one reciprocal for both softmax normalisations, one for the rational function (everything multiplied through by
+//    w^3), one lg2 for the log-determinant;  the log-det is returned in log2 units and scaled once per row.
+//
+// Tolerance-checked (1e-4 abs/rel on log_prob), not bit-checked: the bit-exact bin index contract belongs to the
+// stand-alone transformer kernel (b2f_math.cuh), whose parameters are fp32-faithful; here they come out of a TF32 GEMM.
+#pragma once
+#include "b2f_math.cuh"
+
+namespace b2f {
+namespace rqf {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kSizeScale = 0.992f;          // 1 - 1e-3 * 8   (rational_quadratic.py:47, n_bins = 8)
+constexpr float kPolyBound = 1.0f / 32.0f;    // |Dl| below which the cubic 2^Dl is exact to 1e-8
+constexpr float kNoMaxBound = 40.0f;          // |L| below which ex2 needs no max subtraction
+constexpr float kEdgeLogit = kRqEdgeU + kRqEdgeU / 1000.0f;   // logit of the two padded edge derivatives: c + c/1000
+
+B2F_HD float f_ex2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return exp2f(x);
+#endif
+}
+B2F_HD float f_lg2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return log2f(x);
+#endif
+}
+B2F_HD float f_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return 1.0f / x;
+#endif
+}
+B2F_HD float f_sqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return sqrtf(x);
+#endif
+}
+
+// derivative at a knot from its logit: 1e-5 + softplus(a)   (rational_quadratic.py:77)
+B2F_HD float delta(float a) {
+    const float e = f_ex2(fminf(a, 80.0f) * kLog2e);
+    return fmaf(f_lg2(1.0f + e), kLn2, kRqMinDelta);
+}
+
+struct Sel {            // the selected bin: knots measured from -b (cumulative bin sizes in [0, 2b]), derivative logits
+    float xl, xu, yl, yu, dl0, dl1;
+};
+
+// One search step with the predicate as a number, m = (c < t) ? 1 : 0:  lo += m a, up += m b (packed pairs),
+// dl0 += m d0, dl1 += m d1.  fma(1, x, acc) rounds exactly like acc + x, so this IS the predicated sum; as FFMA2 / FFMA
+// it stays on the FMA pipe (ptxas turns predicated packed adds into 32-bit selects on the half-rate ALU pipe).
+B2F_HD float select_step(float c, float t, f2& lo, f2& up, float& dl0, float& dl1, f2 a, f2 b, float d0, float d1) {
+    const float m = c < t ? 1.0f : 0.0f;
+    const f2 mm = mk2(m, m);
+    lo = pk_fma(mm, a, lo);
+    up = pk_fma(mm, b, up);
+    dl0 = fmaf(m, d0, dl0);
+    dl1 = fmaf(m, d1, dl1);
+    return m;
+}
+
+// Softmaxes, search and selection.  t = v + b.  INV: search on the y knots (rational_quadratic.py:147).
+// SAFE: max-subtracted exponentials and SFU for the heights (no host-side bound on the logits).
+// NY (even): how many of the 8 heights exponentials go to the SFU in the fast variant (pipe balancing; any value is exact).
+// Widths and heights travel as packed pairs (.x widths, .y heights): FADD2 / FFMA2 issue once for both.
+template <bool INV, bool SAFE, int NY>
+B2F_HD void select(const float (&g)[24], float t, float two_b, Sel& s) {
+    static_assert(NY % 2 == 0, "the cubic 2^d is evaluated on pairs of logits");
+    f2 e[8];
+    float m = 0.0f;
+    if (SAFE) {
+        m = g[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) m = fmaxf(m, g[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float a0 = SAFE ? g[j] - m : g[j], a1 = SAFE ? g[j + 1] - m : g[j + 1];
+        e[j].x = f_ex2(a0);
+        e[j + 1].x = f_ex2(a1);
+        if (SAFE || j < NY) {
+            e[j].y = f_ex2(a0 + g[8 + j]);
+            e[j + 1].y = f_ex2(a1 + g[9 + j]);
+        } else {                               // 2^d, |d| < 1/32: 1 + d ln2 + (d ln2)^2/2 + (d ln2)^3/6, two logits at a time
+            const f2 d = mk2(g[8 + j], g[9 + j]);
+            f2 p = pk_fma(d, mk2(0.0555041086648216f, 0.0555041086648216f), mk2(0.2402265069591007f, 0.2402265069591007f));
+            p = pk_fma(p, d, mk2(kLn2, kLn2));
+            p = pk_fma(p, d, mk2(1.0f, 1.0f));
+            e[j].y = e[j].x * p.x;
+            e[j + 1].y = e[j + 1].x * p.y;
+        }
+    }
+    const f2 sum = pk_add(pk_add(pk_add(e[0], e[1]), pk_add(e[2], e[3])), pk_add(pk_add(e[4], e[5]), pk_add(e[6], e[7])));
+    const float r = (kSizeScale * two_b) * f_rcp(sum.x * sum.y);
+    const f2 rr = mk2(r * sum.y, r * sum.x);
+    // bin sizes in units of the spline range: 2b (1e-3 + 0.992 softmax)   (rational_quadratic.py:46-49)
+    const float minb = kRqMinBin * two_b;
+    f2 sz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sz[j] = pk_fma(e[j], rr, mk2(minb, minb));
+    f2 lo = mk2(0.0f, 0.0f), up = sz[0];
+    s.dl0 = kEdgeLogit; s.dl1 = kEdgeLogit + g[16];
+    float c = 0.0f, m7 = 0.0f;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        c += INV ? sz[j - 1].y : sz[j - 1].x;             // cumulative size = knot j in normalised units
+        // searchsorted(right=False): knots strictly below v are counted
+        m7 = select_step(c, t, lo, up, s.dl0, s.dl1, sz[j - 1], sz[j], g[16 + j - 1], g[16 + j]);
+    }
+    if (m7 != 0.0f) up = mk2(two_b, two_b);               // bins[K] = +b is pinned (rational_quadratic.py:52)
+    s.xl = lo.x; s.yl = lo.y; s.xu = up.x; s.yu = up.y;
+}
+
+// Forward map (rational_quadratic.py:88-109, log-det :56-63).  out = spline(v), ld2 = log2 |d out / d v|.
+template <bool SAFE, int NY>
+B2F_HD void forward(float v, const float (&g)[24], float b, float& out, float& ld2) {
+    const float two_b = b + b;
+    const bool inb = fabsf(v) < b;                        // strict, spline/base.py:29-33; NaN -> identity tail
+    const float t = v + b;
+    Sel s;
+    select<false, SAFE, NY>(g, t, two_b, s);
+    const float w = s.xu - s.xl, hgt = s.yu - s.yl;
+    const float yk = s.yl - b;
+    const float a = fminf(fmaxf(t - s.xl, 0.0f), w);      // v - x_k = xi * w, xi clipped to [0, 1]  (:99)
+    const float d0 = delta(s.dl0), d1 = delta(s.dl1);
+    // out = yk + hgt (s xi^2 + d0 q) / (s + t1 q), everything multiplied through by w^3:
+    const float wa = w - a, aw = a * wa, h2 = hgt + hgt;
+    const float T = fmaf(w, d0 + d1, -h2);                // w * t1
+    const float den = fmaf(T, aw, (hgt * w) * w);         // w^3 (s + t1 q)
+    const float num = fmaf(hgt * a, a, (w * d0) * aw);    // w^3 (s xi^2 + d0 q)
+    const float R = f_rcp(den);
+    const float hR = hgt * R;
+    const float o = fmaf(hR, num, yk);
+    const float M3 = fmaf(w, fmaf(d0 * wa, wa, (d1 * a) * a), h2 * aw);   // w^3 (d1 xi^2 + 2 s q + d0 (1-xi)^2)
+    const float arg = (hR * hR) * (M3 * w);               // s^2 M / (s + t1 q)^2
+    out = inb ? o : v;
+    ld2 = f_lg2(inb ? arg : 1.0f);
+}
+
+// Inverse map (rational_quadratic.py:153-181).  out = spline^{-1}(v), ld2 = -log2 |d spline / d x| at out.
+template <bool SAFE, int NY>
+B2F_HD void inverse(float v, const float (&g)[24], float b, float& out, float& ld2) {
+    const float two_b = b + b;
+    const bool inb = fabsf(v) < b;
+    const float t = v + b;
+    Sel s;
+    select<true, SAFE, NY>(g, t, two_b, s);
+    const float w = s.xu - s.xl, hgt = s.yu - s.yl;
+    const float xk = s.xl - b;
+    const float t0 = fminf(fmaxf(t - s.yl, 0.0f), hgt);   // v - y_k
+    const float d0 = delta(s.dl0), d1 = delta(s.dl1);
+    const float h2 = hgt + hgt, hw = hgt * w;
+    const float T = fmaf(w, d0 + d1, -h2);                // w * t1
+    // quadratic of :170-178 multiplied by w:  A = hgt^2 - B,  B = hgt d0 w - t0 T,  C = -hgt t0
+    const float B2 = fmaf(-t0, T, hw * d0);
+    const float A2 = fmaf(hgt, hgt, -B2);
+    const float disc = fmaf(B2, B2, (4.0f * (A2 * hgt)) * t0);
+    const float sq = f_sqrt(fmaxf(disc, 0.0f));
+    const float xi = fminf(fmaxf((h2 * t0) * f_rcp(B2 + sq), 0.0f), 1.0f);
+    const float a = xi * w;
+    const float o = xk + a;
+    const float wa = w - a, aw = a * wa;
+    const float den = fmaf(T, aw, hw * w);
+    const float M3 = fmaf(w, fmaf(d0 * wa, wa, (d1 * a) * a), h2 * aw);
+    const float fw = (hgt * hgt) * (M3 * w);              // forward derivative = fw / den^2
+    out = inb ? o : v;
+    ld2 = f_lg2(inb ? den * den : 1.0f) - f_lg2(inb ? fw : 1.0f);
+}
+
+}  // namespace rqf
+}  // namespace b2f
