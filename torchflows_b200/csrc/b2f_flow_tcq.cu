@@ -239,58 +239,65 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
         }
         __syncwarp();
     } else if (warp == kQEpiWarps) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc1 = umma::make_idesc_tf32(128, kQN1), idesc2 = umma::make_idesc_tf32(128, kQN2);
-            const uint32_t w1a = umma::smem_u32(s.w1), a2a = umma::smem_u32(s.a2);
-            for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-                for (int li = 0; li < A.n_layers; ++li, ++lc) {
-                    const QLayer& L = A.layers[li];
-                    const int src_half = q_hdr(L.blob, 1);
-                    const uint32_t ph = lc & 1;
-                    umma::mbar_wait(&s.bars[QB_W1_FULL], ph);
-                    umma::mbar_wait(&s.bars[QB_A1_READY], ph);
-                    umma::tc_fence_after_sync();
-                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T
-                    const uint32_t xa = umma::smem_u32(s.xt[src_half]);
+        // ===================== MMA issuer =====================
+        // The whole warp runs the (warp-uniform) control flow so that addresses and descriptors stay in uniform registers;
+        // one elected lane issues the tcgen05 instructions.  Per MMA this is a 32-bit add on the descriptor's low word: the
+        // issuing thread serves 12 MMAs per round and must stay well below the epilogue's ~1800 cycles per round.
+        const uint32_t leader = umma::elect_one();
+        const uint32_t idesc1 = umma::make_idesc_tf32(128, kQN1), idesc2 = umma::make_idesc_tf32(128, kQN2);
+        const uint32_t w1a = umma::smem_u32(s.w1) >> 4, a2a = umma::smem_u32(s.a2) >> 4;
+        const uint32_t xa0 = umma::smem_u32(s.xt[0]) >> 4, xa1 = umma::smem_u32(s.xt[1]) >> 4;
+        const uint64_t d1c = umma::make_smem_desc(0, 128, Dh * 32);
+        const uint32_t d1_lo = (uint32_t)d1c, d1_hi = (uint32_t)(d1c >> 32);
+        for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
+            for (int li = 0; li < A.n_layers; ++li, ++lc) {
+                const QLayer& L = A.layers[li];
+                const int src_half = q_hdr(L.blob, 1);
+                const uint32_t ph = lc & 1;
+                umma::mbar_wait(&s.bars[QB_W1_FULL], ph);
+                umma::mbar_wait(&s.bars[QB_A1_READY], ph);
+                umma::tc_fence_after_sync();
+                if (leader) {
+                    // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T, one MMA per 8 columns (256 bytes = 16 units)
+                    const uint32_t xa = d1_lo + (src_half ? xa1 : xa0), wa = d1_lo + w1a;
                     for (int ks = 0; ks < Dh / 8; ++ks)
-                        umma::mma_tf32_ss(tbase + kQColD1, umma::make_smem_desc(xa + ks * 256, 128, Dh * 32),
-                                          umma::make_smem_desc(w1a + ks * 256, 128, Dh * 32), idesc1, ks > 0);
+                        umma::mma_tf32_ss_parts(tbase + kQColD1, xa + ks * 16, d1_hi, wa + ks * 16, d1_hi, idesc1, ks > 0);
                     umma::mma_commit(&s.bars[QB_D1_FULL]);
                     umma::mma_commit(&s.bars[QB_W1_EMPTY]);
-                    umma::mbar_wait(&s.bars[QB_A2_FULL], ph);
-                    umma::tc_fence_after_sync();
-                    for (int r = 0; r < n_chunks / 4; ++r, cc += 4) {
-                        // round r: chunk 4r + g for group g, TMEM buffer (cc / 4) & 1; groups are served as their
-                        // accumulators come free, not in index order (a slow group does not hold up the others)
-                        const uint32_t b = (cc >> 2) & 1, ph2 = (cc >> 3) & 1;
-                        umma::mbar_wait(&s.bars[QB_W2_FULL + ring], ring_ph);
-                        const uint32_t wb = umma::smem_u32(s.w2 + ring * s.w2stride);
-                        uint32_t pending = 0xFu, spins = 0;
-                        while (pending) {
+                }
+                __syncwarp();
+                umma::mbar_wait(&s.bars[QB_A2_FULL], ph);
+                umma::tc_fence_after_sync();
+                const uint64_t d2c = umma::make_smem_desc(0, 128, L.K2 * 32);
+                const uint32_t d2_lo = (uint32_t)d2c, d2_hi = (uint32_t)(d2c >> 32);
+                const uint32_t a_lo = d2_lo + a2a;
+                const int nk = L.K2 / 8;
+                const uint32_t grp_units = (kQN2 / 8) * (L.K2 * 32) / 16;      // 6 row groups of the round operand, in 16-byte units
+                for (int r = 0; r < n_chunks / 4; ++r, cc += 4) {
+                    // round r: chunk 4r + g for group g, TMEM buffer (cc / 4) & 1
+                    const uint32_t b = (cc >> 2) & 1, ph2 = (cc >> 3) & 1;
+                    umma::mbar_wait(&s.bars[QB_W2_FULL + ring], ring_ph);
+                    const uint32_t w_lo = d2_lo + (umma::smem_u32(s.w2 + ring * s.w2stride) >> 4);
 #pragma unroll
-                            for (uint32_t g = 0; g < 4; ++g) {
-                                if (!(pending & (1u << g))) continue;
-                                const uint32_t slot = g + 4 * b;
-                                if (!umma::mbar_try_wait(&s.bars[QB_D2_EMPTY + slot], ph2 ^ 1)) continue;
-                                umma::tc_fence_after_sync();
-                                const uint32_t dcol = tbase + g * (2 * kQN2) + b * kQN2;
-                                const uint32_t wg = wb + g * (kQN2 / 8) * (L.K2 * 32);     // 6 row groups of the round operand
-                                for (int ks = 0; ks < L.K2 / 8; ++ks)
-                                    umma::mma_tf32_ss(dcol, umma::make_smem_desc(a2a + ks * 256, 128, L.K2 * 32),
-                                                      umma::make_smem_desc(wg + ks * 256, 128, L.K2 * 32), idesc2, ks > 0);
-                                umma::mma_commit(&s.bars[QB_D2_FULL + slot]);
-                                pending &= ~(1u << g);
-                            }
-                            if (++spins > (1u << 24)) __trap();
+                    for (uint32_t g = 0; g < 4; ++g) {
+                        const uint32_t slot = g + 4 * b;
+                        umma::mbar_wait(&s.bars[QB_D2_EMPTY + slot], ph2 ^ 1);
+                        umma::tc_fence_after_sync();
+                        if (leader) {
+                            const uint32_t dcol = tbase + g * (2 * kQN2) + b * kQN2;
+                            const uint32_t wg = w_lo + g * grp_units;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks)
+                                if (ks < nk) umma::mma_tf32_ss_parts(dcol, a_lo + ks * 16, d2_hi, wg + ks * 16, d2_hi, idesc2, ks > 0);
+                            umma::mma_commit(&s.bars[QB_D2_FULL + slot]);
                         }
-                        umma::mma_commit(&s.bars[QB_W2_EMPTY + ring]);
-                        if (++ring == (uint32_t)s.n_ring) { ring = 0; ring_ph ^= 1; }
                     }
+                    if (leader) umma::mma_commit(&s.bars[QB_W2_EMPTY + ring]);
+                    __syncwarp();
+                    if (++ring == (uint32_t)s.n_ring) { ring = 0; ring_ph ^= 1; }
                 }
             }
         }
-        __syncwarp();
     } else {
         // ===================== epilogue warps =====================
         const int q = warp & 3, g = warp >> 2;            // TMEM lane quarter, epilogue group
