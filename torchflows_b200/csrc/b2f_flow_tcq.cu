@@ -38,7 +38,7 @@
 namespace b2f {
 
 constexpr int kQEpiWarps = 16;
-constexpr int kQThreads = (kQEpiWarps + 2) * 32;
+constexpr int kQThreads = (kQEpiWarps + 3) * 32;     // + MMA issuer, weight loader, tile IO
 constexpr int kQN1 = 32;                      // UMMA N of GEMM1 (hidden units, padded)
 constexpr int kQN2 = 48;                      // UMMA N of a GEMM2 chunk: 2 elements x 24 columns
 constexpr int kQSlots = 8;                    // TMEM accumulator slots: (group, buffer)
@@ -65,7 +65,7 @@ struct QArgs {
     const float* prog;      // program blob: [4 ints][4 consts][D x (fin_a, fin_b)][D x (in_a, in_b)]
 };
 
-enum { QB_X_FULL = 0, QB_TILE_FREE, QB_W1_FULL, QB_W1_EMPTY, QB_A1_READY, QB_D1_FULL, QB_A2_FULL,
+enum { QB_XA_FULL = 0, QB_XB_FULL, QB_EARLY_FREE, QB_TILE_DONE, QB_W1_FULL, QB_W1_EMPTY, QB_A1_READY, QB_D1_FULL, QB_A2_FULL,
        QB_W2_FULL, QB_W2_EMPTY = QB_W2_FULL + kQRing, QB_D2_FULL = QB_W2_EMPTY + kQRing,
        QB_D2_EMPTY = QB_D2_FULL + kQSlots, QB_COUNT = QB_D2_EMPTY + kQSlots };
 
@@ -104,12 +104,50 @@ __device__ __forceinline__ void q_bulk_wait_all() { asm volatile("cp.async.bulk.
 
 __device__ __forceinline__ int q_hdr(const float* blob, int i) { return __ldg(reinterpret_cast<const int*>(blob) + i); }
 
+// explicit shared-space accesses (32-bit addresses): the tile pointers depend on the per-tile buffer swap, and generic
+// pointers would turn into LD.E / ST.E with address-space resolution on the critical path
+__device__ __forceinline__ float2 q_lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void q_sts64(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 q_lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void q_sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// v = a * v + b on 4 consecutive columns; p0 = (a0, b0, a1, b1), p1 = (a2, b2, a3, b3)
+__device__ __forceinline__ float4 q_affine4(float4 v, float4 p0, float4 p1) {
+    v.x = fmaf(v.x, p0.x, p0.y); v.y = fmaf(v.y, p0.z, p0.w);
+    v.z = fmaf(v.z, p1.x, p1.y); v.w = fmaf(v.w, p1.z, p1.w);
+    return v;
+}
+
+// Cooperative pass of the 16 epilogue warps over one half of the tile: x <- a * x + b per column (params: [Dh][2]).
+// Warp w owns rows 8w..8w+7, four lanes share a row and stride over its 16-byte column groups.
+__device__ __forceinline__ void q_affine_pass(uint32_t half_addr, uint32_t row_off, const float* __restrict__ params, int Dh, int kq) {
+#pragma unroll 4
+    for (int kc = kq; kc < Dh / 4; kc += 4) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(params + 8 * kc));
+        const float4 p1 = __ldg(reinterpret_cast<const float4*>(params + 8 * kc + 4));
+        const uint32_t a = half_addr + row_off + kc * 128;
+        q_sts128(a, q_affine4(q_lds128(a), p0, p1));
+    }
+}
+
 // One coupling layer's transformer phase for one epilogue thread (row m, group g): its chunks c = g, g + 4, ...
 template <bool INV, bool SAFE>
 __device__ __forceinline__ void q_chunk_loop(const QSmem& s, const float* __restrict__ tp, float boundary, uint32_t tbase,
-                                             uint32_t lane_addr, float* xt_tgt, int Dh, int n_chunks, uint32_t cc_base, int m,
+                                             uint32_t lane_addr, uint32_t tgt_addr, int Dh, int n_chunks, uint32_t cc_base, int m,
                                              int g, int lane, float& ld2, float& sq) {
-    uint8_t* xrow = reinterpret_cast<uint8_t*>(xt_tgt) + (m >> 3) * (Dh * 32) + (m & 7) * 16;   // canon_off(m, 0, Dh)
+    const uint32_t xrow = tgt_addr + (m >> 3) * (Dh * 32) + (m & 7) * 16;       // canon_off(m, 0, Dh)
     for (int c = g; c < n_chunks; c += 4) {
         const uint32_t ccl = cc_base + c, slot = ccl & (kQSlots - 1);
         umma::mbar_wait(&s.bars[QB_D2_FULL + slot], (ccl >> 3) & 1);
@@ -127,8 +165,8 @@ __device__ __forceinline__ void q_chunk_loop(const QSmem& s, const float* __rest
         if (lane == 0) umma::mbar_arrive(&s.bars[QB_D2_EMPTY + slot]);      // the columns are in registers: hand the buffer back
         // elements 2c, 2c + 1 of the target half: adjacent columns, one 8-byte access
         const int e0 = 2 * c;
-        float2* px = reinterpret_cast<float2*>(xrow + (e0 >> 2) * 128 + (e0 & 3) * 4);
-        const float2 xv = *px;
+        const uint32_t px = xrow + (e0 >> 2) * 128 + (e0 & 3) * 4;
+        const float2 xv = q_lds64(px);
         const float4 pa = __ldg(reinterpret_cast<const float4*>(tp + e0 * 8));          // pre_a, pre_b, post_a, post_b
         const float2 fa = __ldg(reinterpret_cast<const float2*>(tp + e0 * 8 + 4));      // fin_a, fin_b
         const float4 pb = __ldg(reinterpret_cast<const float4*>(tp + e0 * 8 + 8));
@@ -143,7 +181,7 @@ __device__ __forceinline__ void q_chunk_loop(const QSmem& s, const float* __rest
             rqf::forward<SAFE, B2F_TCQ_NY>(vb, gb, boundary, ob, lb);
         }
         const float sa = fmaf(oa, pa.z, pa.w), sb = fmaf(ob, pb.z, pb.w);
-        *px = make_float2(sa, sb);
+        q_sts64(px, make_float2(sa, sb));
         const float ta = fmaf(sa, fa.x, fa.y), tb = fmaf(sb, fb.x, fb.y);
         sq = fmaf(ta, ta, sq);
         sq = fmaf(tb, tb, sq);
@@ -151,6 +189,10 @@ __device__ __forceinline__ void q_chunk_loop(const QSmem& s, const float* __rest
     }
 }
 
+// Tile buffers.  The two halves of a tile live in the two 64 KB buffers xt[0], xt[1]; which half sits in which buffer
+// alternates from tile to tile (`swap`), because the next tile is prefetched half by half into whatever the current tile
+// releases first: the source half of the LAST layer is dead once that layer's GEMM1 has read it (EARLY_FREE) and receives
+// the next tile's FIRST-layer source half; the other half follows when the tile is done (TILE_DONE).
 __global__ void __launch_bounds__(kQThreads, 1)
 flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_y) {
@@ -175,8 +217,10 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
     s.tmem_ptr = reinterpret_cast<uint32_t*>(p);
 
     if (tid == 0) {
-        umma::mbar_init(&s.bars[QB_X_FULL], 1);
-        umma::mbar_init(&s.bars[QB_TILE_FREE], 1);
+        umma::mbar_init(&s.bars[QB_XA_FULL], 1);
+        umma::mbar_init(&s.bars[QB_XB_FULL], 1);
+        umma::mbar_init(&s.bars[QB_EARLY_FREE], kQEpiWarps);
+        umma::mbar_init(&s.bars[QB_TILE_DONE], kQEpiWarps);
         umma::mbar_init(&s.bars[QB_W1_FULL], 1);
         umma::mbar_init(&s.bars[QB_W1_EMPTY], 1);
         umma::mbar_init(&s.bars[QB_A1_READY], kQEpiWarps);
@@ -200,25 +244,60 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
     const int n_chunks = Dh >> 1;
     const bool want_lp = A.log_prob != nullptr;
     const bool lp_in = want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT);
+    const int s_first = q_hdr(A.layers[0].blob, 1), s_last = q_hdr(A.layers[A.n_layers - 1].blob, 1);
+    const uint32_t swap_step = s_first != s_last ? 1u : 0u;
+    const uint32_t xt0 = umma::smem_u32(s.xt[0]), half_bytes = 128u * Dh * 4;       // buffer b starts at xt0 + b * half_bytes
 
     uint32_t lc = 0;        // coupling layers processed so far (all roles count identically)
     uint32_t cc = 0;        // GEMM2 chunks processed so far (multiple of 8 at every layer boundary)
     uint32_t tc = 0;        // tiles processed so far
+    uint32_t swap = 0;      // half h of the current tile lives in buffer h ^ swap
     uint32_t ring = 0, ring_ph = 0;   // W2 ring position and phase (loader and MMA issuer count identically)
 
-    if (warp == kQEpiWarps + 1) {
-        // ===================== loader (one thread): tile via tensor-map TMA, weights via bulk copies =====================
+    if (warp == kQEpiWarps + 2) {
+        // ===================== tile IO (one thread): tensor-map TMA loads, stores and the half-by-half prefetch =====================
         if (lane == 0) {
-            for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tc) {
-                const bool full = A.use_tma && ((long long)tile * 128 + 128 <= A.B);
-                umma::mbar_wait_backoff(&s.bars[QB_TILE_FREE], (tc & 1) ^ 1);
-                if (full) {
-                    umma::mbar_arrive_expect_tx(&s.bars[QB_X_FULL], 2u * 128 * Dh * 4);
-                    q_tma_load4(s.xt[0], &map_x, 0, 0, 0, tile * 16, &s.bars[QB_X_FULL]);
-                    q_tma_load4(s.xt[1], &map_x, 0, 0, Dh / 4, tile * 16, &s.bars[QB_X_FULL]);
+            auto is_full = [&](int t) { return A.use_tma && ((long long)t * 128 + 128 <= A.B); };
+            auto load_half = [&](int t, int h, uint32_t buf, uint64_t* bar) {
+                if (is_full(t)) {
+                    umma::mbar_arrive_expect_tx(bar, 128u * Dh * 4);
+                    q_tma_load4(reinterpret_cast<uint8_t*>(s.xt[0]) + buf * half_bytes, &map_x, 0, 0, h * (Dh / 4), t * 16, bar);
                 } else {
-                    umma::mbar_arrive(&s.bars[QB_X_FULL]);       // ragged tile: the epilogue warps load it themselves
+                    umma::mbar_arrive(bar);          // ragged tile: the epilogue warps load it themselves once both arrived
                 }
+            };
+            int tile = blockIdx.x;
+            if (tile < A.n_tiles) {
+                load_half(tile, s_first, s_first, &s.bars[QB_XA_FULL]);
+                load_half(tile, 1 - s_first, 1 - s_first, &s.bars[QB_XB_FULL]);
+            }
+            for (; tile < A.n_tiles; tile += gridDim.x, ++tc) {
+                const int next = tile + gridDim.x;
+                const bool store = A.y != nullptr && is_full(tile);
+                const uint32_t buf_e = s_last ^ swap, buf_r = buf_e ^ 1u;
+                umma::mbar_wait_backoff(&s.bars[QB_EARLY_FREE], tc & 1);
+                if (store) {
+                    q_tma_store4(&map_y, 0, 0, s_last * (Dh / 4), tile * 16, reinterpret_cast<uint8_t*>(s.xt[0]) + buf_e * half_bytes);
+                    q_bulk_commit();
+                    q_bulk_wait_read();
+                }
+                if (next < A.n_tiles) load_half(next, s_first, buf_e, &s.bars[QB_XA_FULL]);
+                umma::mbar_wait_backoff(&s.bars[QB_TILE_DONE], tc & 1);
+                if (store) {
+                    q_tma_store4(&map_y, 0, 0, (1 - s_last) * (Dh / 4), tile * 16, reinterpret_cast<uint8_t*>(s.xt[0]) + buf_r * half_bytes);
+                    q_bulk_commit();
+                    q_bulk_wait_read();
+                }
+                if (next < A.n_tiles) load_half(next, 1 - s_first, buf_r, &s.bars[QB_XB_FULL]);
+                swap ^= swap_step;
+            }
+            q_bulk_wait_all();
+        }
+        __syncwarp();
+    } else if (warp == kQEpiWarps + 1) {
+        // ===================== weight loader (one thread): bulk copies of W1 and of the W2 rounds =====================
+        if (lane == 0) {
+            for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
                 for (int li = 0; li < A.n_layers; ++li, ++lc) {
                     const QLayer& L = A.layers[li];
                     umma::mbar_wait(&s.bars[QB_W1_EMPTY], (lc & 1) ^ 1);
@@ -246,20 +325,19 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
         const uint32_t leader = umma::elect_one();
         const uint32_t idesc1 = umma::make_idesc_tf32(128, kQN1), idesc2 = umma::make_idesc_tf32(128, kQN2);
         const uint32_t w1a = umma::smem_u32(s.w1) >> 4, a2a = umma::smem_u32(s.a2) >> 4;
-        const uint32_t xa0 = umma::smem_u32(s.xt[0]) >> 4, xa1 = umma::smem_u32(s.xt[1]) >> 4;
         const uint64_t d1c = umma::make_smem_desc(0, 128, Dh * 32);
         const uint32_t d1_lo = (uint32_t)d1c, d1_hi = (uint32_t)(d1c >> 32);
         for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
             for (int li = 0; li < A.n_layers; ++li, ++lc) {
                 const QLayer& L = A.layers[li];
-                const int src_half = q_hdr(L.blob, 1);
+                const uint32_t src_buf = (uint32_t)q_hdr(L.blob, 1) ^ swap;
                 const uint32_t ph = lc & 1;
                 umma::mbar_wait(&s.bars[QB_W1_FULL], ph);
                 umma::mbar_wait(&s.bars[QB_A1_READY], ph);
                 umma::tc_fence_after_sync();
                 if (leader) {
                     // GEMM1: D1[128 x 32] = x_src[128 x Dh] * W1c[32 x Dh]^T, one MMA per 8 columns (256 bytes = 16 units)
-                    const uint32_t xa = d1_lo + (src_half ? xa1 : xa0), wa = d1_lo + w1a;
+                    const uint32_t xa = d1_lo + ((xt0 + src_buf * half_bytes) >> 4), wa = d1_lo + w1a;
                     for (int ks = 0; ks < Dh / 8; ++ks)
                         umma::mma_tf32_ss_parts(tbase + kQColD1, xa + ks * 16, d1_hi, wa + ks * 16, d1_hi, idesc1, ks > 0);
                     umma::mma_commit(&s.bars[QB_D1_FULL]);
@@ -297,6 +375,7 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                     if (++ring == (uint32_t)s.n_ring) { ring = 0; ring_ph ^= 1; }
                 }
             }
+            swap ^= swap_step;
         }
     } else {
         // ===================== epilogue warps =====================
@@ -307,19 +386,22 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
         const float* prog = A.prog;
         const int fin_pass0 = q_hdr(prog, 1), fin_pass1 = q_hdr(prog, 2);
         const float const_ld = __ldg(prog + 4), const_lp = __ldg(prog + 5);
+        const float* fin_params = prog + 8;
         const uint32_t row_off = (m8 >> 3) * (Dh * 32) + (m8 & 7) * 16;     // canon_off(m8, 0, Dh)
         for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tc) {
             const long long row0 = (long long)tile * 128;
             const int rows = (int)min(128LL, A.B - row0);
             const bool full = A.use_tma && rows == 128;
-            umma::mbar_wait(&s.bars[QB_X_FULL], tc & 1);
+            bool have_b = false;                           // waited for the second half of this tile yet?
+            umma::mbar_wait(&s.bars[QB_XA_FULL], tc & 1);
+            if (!full || lp_in) { umma::mbar_wait(&s.bars[QB_XB_FULL], tc & 1); have_b = true; }
             if (!full) {
                 const bool live = m8 < rows;
                 const float4* src = reinterpret_cast<const float4*>(A.x + (row0 + m8) * D);
                 for (int kc = kq; kc < D / 4; kc += 4) {
                     const float4 v = live ? __ldg(src + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
-                    *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(s.xt[hf]) + row_off + k4 * 128) = v;
+                    const uint32_t hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
+                    q_sts128((xt0 + (hf ^ swap) * half_bytes) + row_off + k4 * 128, v);
                 }
                 q_epi_sync();
             }
@@ -328,13 +410,12 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                 const float* ip = prog + 8 + 2 * D;
                 float acc = 0.0f;
                 for (int kc = kq; kc < D / 4; kc += 4) {
-                    const int hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
-                    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<uint8_t*>(s.xt[hf]) + row_off + k4 * 128);
+                    const uint32_t hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
+                    const float4 v = q_lds128((xt0 + (hf ^ swap) * half_bytes) + row_off + k4 * 128);
                     const float4 p0 = __ldg(reinterpret_cast<const float4*>(ip + 8 * kc));
                     const float4 p1 = __ldg(reinterpret_cast<const float4*>(ip + 8 * kc + 4));
-                    const float t0 = fmaf(v.x, p0.x, p0.y), t1 = fmaf(v.y, p0.z, p0.w);
-                    const float t2 = fmaf(v.z, p1.x, p1.y), t3 = fmaf(v.w, p1.z, p1.w);
-                    acc = fmaf(t0, t0, acc); acc = fmaf(t1, t1, acc); acc = fmaf(t2, t2, acc); acc = fmaf(t3, t3, acc);
+                    const float4 t = q_affine4(v, p0, p1);
+                    acc = fmaf(t.x, t.x, acc); acc = fmaf(t.y, t.y, acc); acc = fmaf(t.z, t.z, acc); acc = fmaf(t.w, t.w, acc);
                 }
                 acc += __shfl_xor_sync(0xffffffffu, acc, 8);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 16);
@@ -345,6 +426,7 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                 const QLayer& L = A.layers[li];
                 const float* blob = L.blob;
                 const int src_half = q_hdr(blob, 1), src_pass = q_hdr(blob, 2);
+                const uint32_t src_addr = xt0 + ((uint32_t)src_half ^ swap) * half_bytes, tgt_addr = xt0 + ((uint32_t)src_half ^ swap ^ 1u) * half_bytes;
                 const int H = L.H, K2 = L.K2;
                 const float* b1 = blob + kQHdr + kQN1 * Dh;
                 const float* tp = b1 + 32 + (size_t)n_chunks * kQN2 * K2;
@@ -352,17 +434,11 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                 const float* misc = sp + Dh * 2;
                 if (src_pass) {
                     // the elementwise layers in front of this layer, applied to the half that feeds the conditioner
-                    if (li > 0) q_epi_sync();
-                    uint8_t* base = reinterpret_cast<uint8_t*>(s.xt[src_half]) + row_off;
-                    for (int kc = kq; kc < Dh / 4; kc += 4) {
-                        float4* px = reinterpret_cast<float4*>(base + kc * 128);
-                        float4 v = *px;
-                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(sp + 8 * kc));
-                        const float4 p1 = __ldg(reinterpret_cast<const float4*>(sp + 8 * kc + 4));
-                        v.x = fmaf(v.x, p0.x, p0.y); v.y = fmaf(v.y, p0.z, p0.w);
-                        v.z = fmaf(v.z, p1.x, p1.y); v.w = fmaf(v.w, p1.z, p1.w);
-                        *px = v;
+                    if (li > 0) {
+                        if (!have_b) { umma::mbar_wait(&s.bars[QB_XB_FULL], tc & 1); have_b = true; }
+                        q_epi_sync();
                     }
+                    q_affine_pass(src_addr, row_off, sp, Dh, kq);
                 }
                 umma::fence_proxy_async_smem();            // generic-proxy writes to the tile -> tensor core
                 __syncwarp();
@@ -385,29 +461,37 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                             v[i] = (j < H + 2) ? 1.0f : 0.0f;
                         }
                     }
-                    uint8_t* a2row = reinterpret_cast<uint8_t*>(s.a2) + (m >> 3) * (K2 * 32) + (m & 7) * 16 + (2 * g) * 128;
-                    *reinterpret_cast<float4*>(a2row) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(a2row + 128) = make_float4(v[4], v[5], v[6], v[7]);
+                    const uint32_t a2row = umma::smem_u32(s.a2) + (m >> 3) * (K2 * 32) + (m & 7) * 16 + (2 * g) * 128;
+                    q_sts128(a2row, make_float4(v[0], v[1], v[2], v[3]));
+                    q_sts128(a2row + 128, make_float4(v[4], v[5], v[6], v[7]));
                 }
                 umma::tc_fence_before_sync();
                 umma::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&s.bars[QB_A2_FULL]);
+                if (li == A.n_layers - 1) {
+                    // GEMM1 of the last layer has read its source half for the last time: bring it to its final value (sampling:
+                    // the elementwise layers still pending on it) and release it -- it is stored and refilled with the next
+                    // tile's first half while this layer's transformer phase runs
+                    if (A.y && (src_half ? fin_pass1 : fin_pass0)) q_affine_pass(src_addr, row_off, fin_params + src_half * Dh * 2, Dh, kq);
+                    umma::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&s.bars[QB_EARLY_FREE]);
+                }
+                if (!have_b) { umma::mbar_wait(&s.bars[QB_XB_FULL], tc & 1); have_b = true; }
                 // transformer phase
                 const bool fast = __ldg(misc) < rqf::kNoMaxBound && __ldg(misc + 1) < rqf::kPolyBound;
-                float* xt_tgt = s.xt[1 - src_half];
                 if (L.inverse) {
-                    if (fast) q_chunk_loop<true, false>(s, tp, L.boundary, tbase, lane_addr, xt_tgt, Dh, n_chunks, cc, m, g, lane, ld2, sq);
-                    else q_chunk_loop<true, true>(s, tp, L.boundary, tbase, lane_addr, xt_tgt, Dh, n_chunks, cc, m, g, lane, ld2, sq);
+                    if (fast) q_chunk_loop<true, false>(s, tp, L.boundary, tbase, lane_addr, tgt_addr, Dh, n_chunks, cc, m, g, lane, ld2, sq);
+                    else q_chunk_loop<true, true>(s, tp, L.boundary, tbase, lane_addr, tgt_addr, Dh, n_chunks, cc, m, g, lane, ld2, sq);
                 } else {
-                    if (fast) q_chunk_loop<false, false>(s, tp, L.boundary, tbase, lane_addr, xt_tgt, Dh, n_chunks, cc, m, g, lane, ld2, sq);
-                    else q_chunk_loop<false, true>(s, tp, L.boundary, tbase, lane_addr, xt_tgt, Dh, n_chunks, cc, m, g, lane, ld2, sq);
+                    if (fast) q_chunk_loop<false, false>(s, tp, L.boundary, tbase, lane_addr, tgt_addr, Dh, n_chunks, cc, m, g, lane, ld2, sq);
+                    else q_chunk_loop<false, true>(s, tp, L.boundary, tbase, lane_addr, tgt_addr, Dh, n_chunks, cc, m, g, lane, ld2, sq);
                 }
                 cc += n_chunks;
             }
             // ---- outputs of this tile ----
             s.red[g * 128 + m] = make_float2(ld2, sq);
-            umma::fence_proxy_async_smem();       // our accesses to the tile are ordered before the next tile's TMA writes
             q_epi_sync();
             if (tid < 128) {
                 const float2 r0 = s.red[tid], r1 = s.red[128 + tid], r2 = s.red[256 + tid], r3 = s.red[384 + tid];
@@ -420,50 +504,25 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                 }
             }
             if (A.y) {
-                // elementwise layers still pending at the end of the program (the half the last layer did not write)
-                const float* fp = prog + 8;
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    if (!(hf ? fin_pass1 : fin_pass0)) continue;
-                    uint8_t* base = reinterpret_cast<uint8_t*>(s.xt[hf]) + row_off;
-                    const float* fph = fp + hf * Dh * 2;
-                    for (int kc = kq; kc < Dh / 4; kc += 4) {
-                        float4* px = reinterpret_cast<float4*>(base + kc * 128);
-                        float4 v = *px;
-                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(fph + 8 * kc));
-                        const float4 p1 = __ldg(reinterpret_cast<const float4*>(fph + 8 * kc + 4));
-                        v.x = fmaf(v.x, p0.x, p0.y); v.y = fmaf(v.y, p0.z, p0.w);
-                        v.z = fmaf(v.z, p1.x, p1.y); v.w = fmaf(v.w, p1.z, p1.w);
-                        *px = v;
-                    }
-                }
-                if (full) {
-                    umma::fence_proxy_async_smem();
-                    q_epi_sync();
-                    if (tid == 0) {
-                        q_tma_store4(&map_y, 0, 0, 0, tile * 16, s.xt[0]);
-                        q_tma_store4(&map_y, 0, 0, Dh / 4, tile * 16, s.xt[1]);
-                        q_bulk_commit();
-                        q_bulk_wait_read();
-                        umma::mbar_arrive(&s.bars[QB_TILE_FREE]);
-                    }
-                } else {
+                // the half the last layer wrote: elementwise layers still pending at the end of the program, then out
+                const uint32_t hf = 1 - s_last;
+                if (hf ? fin_pass1 : fin_pass0) q_affine_pass((xt0 + (hf ^ swap) * half_bytes), row_off, fin_params + hf * Dh * 2, Dh, kq);
+                if (!full) {
                     q_epi_sync();
                     if (m8 < rows) {
                         float4* dst = reinterpret_cast<float4*>(A.y + (row0 + m8) * D);
                         for (int kc = kq; kc < D / 4; kc += 4) {
-                            const int hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
-                            dst[kc] = *reinterpret_cast<const float4*>(reinterpret_cast<uint8_t*>(s.xt[hf]) + row_off + k4 * 128);
+                            const uint32_t h2 = (4 * kc) >= Dh, k4 = kc - h2 * (Dh / 4);
+                            dst[kc] = q_lds128((xt0 + (h2 ^ swap) * half_bytes) + row_off + k4 * 128);
                         }
                     }
-                    q_epi_sync();
-                    if (tid == 0) umma::mbar_arrive(&s.bars[QB_TILE_FREE]);
                 }
-            } else {
-                if (tid == 0) umma::mbar_arrive(&s.bars[QB_TILE_FREE]);    // after q_epi_sync: nobody touches the tile any more
             }
+            umma::fence_proxy_async_smem();       // our accesses to the tile are ordered before the TMA store / the next tile's TMA writes
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&s.bars[QB_TILE_DONE]);
+            swap ^= swap_step;
         }
-        if (tid == 0) q_bulk_wait_all();
     }
     umma::tc_fence_before_sync();
     __syncthreads();
