@@ -140,6 +140,10 @@ int b2f_flow_backward(const b2f_op_t *ops, int32_t n_ops, const float *x, const 
                       const float *glog_prob, const float *base_loc, const float *base_log_scale, float *gx,
                       void *workspace, int64_t B, int32_t D, int32_t flags, void *stream);
 int64_t b2f_flow_backward_workspace(const b2f_op_t *ops, int32_t n_ops, int64_t B, int32_t D);
+/* 1 if b2f_flow_backward can run this program at event size D (some tile shape of the backward kernel fits shared memory),
+ * else 0.  Only kind, tkind, n_hidden and n_bins of the ops are looked at, so callers can ask before any parameter exists
+ * (torchflows_b200 decides at construction time whether a layer trains through the fused kernel or as a composite). */
+int32_t b2f_flow_backward_fits(const b2f_op_t *ops, int32_t n_ops, int32_t D);
 
 /* Elementwise transformer given materialised parameters h (TensorTransformer.forward / inverse,
  * transformers/base.py:24-42): x,out:(n_rows, n_event); h:(n_rows, n_event, P) with row stride

@@ -63,12 +63,12 @@ def affine_inverse(z: Tensor, h: Tensor, n_event_dims: int = 1) -> Tuple[Tensor,
 
 def shift_forward(x: Tensor, h: Tensor, n_event_dims: int = 1) -> Tuple[Tensor, Tensor]:
     """affine.py:149-153."""
-    return x + h[..., 0], torch.zeros(x.shape[: x.dim() - n_event_dims])
+    return x + h[..., 0], torch.zeros(x.shape[: x.dim() - n_event_dims], device=x.device)
 
 
 def shift_inverse(z: Tensor, h: Tensor, n_event_dims: int = 1) -> Tuple[Tensor, Tensor]:
     """affine.py:155-159."""
-    return z - h[..., 0], torch.zeros(z.shape[: z.dim() - n_event_dims])
+    return z - h[..., 0], torch.zeros(z.shape[: z.dim() - n_event_dims], device=z.device)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -169,7 +169,7 @@ def rq_forward(x: Tensor, h: Tensor, n_bins: int = 8, boundary: float = 50.0, n_
     """MonotonicSpline.forward (spline/base.py:53-60): strict in-bounds mask, identity tails."""
     z = torch.clone(x)
     ld = torch.zeros_like(z)
-    kk = torch.full(x.shape, -1, dtype=torch.int64)
+    kk = torch.full(x.shape, -1, dtype=torch.int64, device=x.device)
     mask = (x > -boundary) & (x < boundary)
     if torch.any(mask):
         z[mask], ld[mask], kk[mask] = rq_forward_1d(x[mask], h[mask], n_bins, boundary)
@@ -182,7 +182,7 @@ def rq_inverse(z: Tensor, h: Tensor, n_bins: int = 8, boundary: float = 50.0, n_
     """MonotonicSpline.inverse (spline/base.py:65-72)."""
     x = torch.clone(z)
     ld = torch.zeros_like(x)
-    kk = torch.full(z.shape, -1, dtype=torch.int64)
+    kk = torch.full(z.shape, -1, dtype=torch.int64, device=z.device)
     mask = (z > -boundary) & (z < boundary)
     if torch.any(mask):
         x[mask], ld[mask], kk[mask] = rq_inverse_1d(z[mask], h[mask], n_bins, boundary)
@@ -304,13 +304,16 @@ class OracleFlow:
     """Flow(preset(event_shape)) evaluated from a reference ``state_dict`` (flows.py:606-713)."""
 
     def __init__(self, preset: str, event_shape, state_dict: Dict[str, Tensor], n_layers: int = 2,
-                 n_bins: int = 8, boundary: float = 50.0):
+                 n_bins: int = 8, boundary: float = 50.0, device: str = 'cpu'):
+        """``device='cuda:0'`` runs the very same ATen op sequence eagerly on the GPU: the reference's own "CUDA support"
+        is nn.Module.cuda() (docs/source/guides/cuda.rst:4-18), so this is the existing-Blackwell-path baseline of
+        bench.py's ``gpu_eager_baseline``; parity checks always use the CPU default."""
         if isinstance(event_shape, int):
             event_shape = (event_shape,)
         self.preset = preset
         self.event_shape = tuple(event_shape)
         self.n_dim = int(math.prod(self.event_shape))
-        self.sd = {k: v.detach().clone().cpu() for k, v in state_dict.items()}
+        self.sd = {k: v.detach().clone().to(device) for k, v in state_dict.items()}
         self.layers = preset_layers(preset, n_layers)
         self.n_bins = n_bins
         self.boundary = boundary
@@ -354,7 +357,7 @@ class OracleFlow:
         """MaskedAutoregressiveBijection.inverse (layers_base.py:213-223): D full passes; returns
         the log-det of the LAST pass."""
         x = torch.clone(z)
-        ld = torch.zeros(z.shape[:-1])
+        ld = torch.zeros(z.shape[:-1], device=z.device)
         for i in range(self.n_dim):
             tmp, ld = self._ma_one_pass(spec, torch.clone(x), 'inverse')
             x[..., i] = tmp[..., i]
@@ -364,7 +367,7 @@ class OracleFlow:
         if spec.kind in ('elementwise_affine', 'actnorm'):
             return self._elementwise(spec, x, direction)
         if spec.kind == 'reverse':  # matrix/permutation.py:19-37 (a flip is its own inverse), log-det 0
-            return torch.flip(x, dims=(-1,)), torch.zeros(x.shape[:-1])
+            return torch.flip(x, dims=(-1,)), torch.zeros(x.shape[:-1], device=x.device)
         if spec.kind == 'coupling':
             return self._coupling(spec, x, direction)
         if spec.kind == 'ma':
@@ -376,7 +379,7 @@ class OracleFlow:
     # -- composition (bijections/base.py:203-232) -------------------------------------------------
     def forward(self, x: Tensor) -> Tuple[Tensor, Tensor]:
         xf = self._flat(x)
-        log_det = torch.zeros(xf.shape[:-1])
+        log_det = torch.zeros(xf.shape[:-1], device=xf.device)
         for spec in self.layers:
             xf, ld = self.layer_apply(spec, xf, 'forward')
             log_det += ld
@@ -384,7 +387,7 @@ class OracleFlow:
 
     def inverse(self, z: Tensor) -> Tuple[Tensor, Tensor]:
         zf = self._flat(z)
-        log_det = torch.zeros(zf.shape[:-1])
+        log_det = torch.zeros(zf.shape[:-1], device=zf.device)
         for spec in self.layers[::-1]:
             zf, ld = self.layer_apply(spec, zf, 'inverse')
             log_det += ld

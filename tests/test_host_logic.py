@@ -162,6 +162,39 @@ assert torch.allclose(w.grad, w2.grad, atol=1e-6) and torch.allclose(b.grad, b2.
 xs = x[lo:hi].double()
 s, q, n = _allreduce_stats(xs.sum(0), (xs * xs).sum(0), torch.tensor(float(hi - lo), dtype=torch.float64))
 assert torch.allclose(s, x.double().sum(0)) and torch.allclose(q, (x.double() ** 2).sum(0)) and float(n) == 11
+# GradBuckets: gradients live in per-layer buckets, each bucket is all-reduced from a hook while backward is still running
+from torchflows_b200.flows import GradBuckets
+class Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(1)
+        self.bijection = torch.nn.Module()
+        self.bijection.layers = torch.nn.ModuleList([torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 3)])
+        self.extra = torch.nn.Parameter(torch.randn(3))
+        self.frozen = torch.nn.Parameter(torch.randn(2), requires_grad=False)
+    def forward(self, t):
+        for layer in self.bijection.layers:
+            t = layer(t)
+        return t + self.extra
+GradBuckets.MIN_BUCKET_BYTES = 0            # one bucket per layer even for these tiny layers
+toy, ref = Toy(), Toy()
+buckets = GradBuckets(toy, 2)
+assert len(buckets.flats) == 3 and buckets.nbytes == 4 * sum(p.numel() for p in toy.parameters() if p.requires_grad)
+for step in range(3):
+    xs = torch.randn(10, 5, generator=torch.Generator().manual_seed(step))
+    lo, hi = shard_bounds(10, rank, 2)
+    buckets.begin_step()
+    (toy(xs[lo:hi]) ** 2).sum().mul(2 / 10).backward()
+    buckets.finish()
+    for p in ref.parameters():
+        p.grad = None
+    (ref(xs) ** 2).sum().mul(1 / 10).backward()
+    for (n, p), q in zip(toy.named_parameters(), ref.parameters()):
+        if p.requires_grad:
+            assert torch.allclose(p.grad, q.grad, atol=1e-6), (step, n)
+            assert p.grad.data_ptr() == buckets.flats[buckets.bucket_of[id(p)]].data_ptr() + 4 * sum(
+                r.numel() for r in buckets.params[buckets.bucket_of[id(p)]][:[id(r) for r in buckets.params[buckets.bucket_of[id(p)]]].index(id(p))])
+buckets.close()
 dist.destroy_process_group()
 print('ok', rank)
 '''

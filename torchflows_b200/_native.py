@@ -7,7 +7,7 @@ from typing import List, Optional, Sequence
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libb2f.so')
+LIB_PATH = os.environ.get('B2F_LIB') or os.path.join(_HERE, 'lib', 'libb2f.so')      # B2F_LIB: A/B builds of the library
 
 # enum b2f_transformer
 T_SHIFT_ADD, T_SHIFT_SUB, T_AFFINE_FWD, T_AFFINE_INV, T_RQ_FWD, T_RQ_INV = range(6)
@@ -61,6 +61,8 @@ def lib():
         L.b2f_flow_backward.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
         L.b2f_flow_backward_workspace.argtypes = [ctypes.POINTER(Op), i32, i64, i32]
         L.b2f_flow_backward_workspace.restype = i64
+        L.b2f_flow_backward_fits.argtypes = [ctypes.POINTER(Op), i32, i32]
+        L.b2f_flow_backward_fits.restype = i32
         L.b2f_transformer_apply.argtypes = [i32, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
@@ -161,6 +163,14 @@ def transformer_backward(tkind, x2, h, h_row_stride, gout, gld, n_bins=8, bounda
         check(lib().b2f_transformer_backward(tkind, ptr(x2), ptr(h), ptr(gout), ptr(gld), ptr(gx), ptr(gh), n_rows, E,
                                              h_row_stride, n_bins, boundary, flags, stream_ptr(x2.device)))
     return gx, gh
+
+
+def flow_backward_fits(kind: int, tkind: int, n_hidden: int, n_bins: int, D: int) -> bool:
+    """Can b2f_flow_backward take a program with a layer of this shape at event size D (shared-memory footprint of the
+    backward kernel, csrc/b2f_flow_bwd.cu)?  Host-only query: no device, no parameters needed."""
+    arr = (Op * 1)()
+    arr[0].kind, arr[0].tkind, arr[0].n_hidden, arr[0].n_bins = kind, tkind, n_hidden, n_bins
+    return bool(lib().b2f_flow_backward_fits(arr, 1, D))
 
 
 def last_flow_kernel() -> int:

@@ -9,7 +9,9 @@ Linear weight in *tile layout* ([element][hidden][param], see include/b2f.h) and
 by their masks, so ``kernel_params`` derives those once per parameter version and caches them on the layer.
 ``FlowFunction`` is the single ``torch.autograd.Function`` through which every fused call goes.
 """
+import dataclasses
 import os
+import warnings
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -280,6 +282,7 @@ class FlowFunction(torch.autograd.Function):
         return (gx if need_gx else None, None, *leaf_grads)
 
 
+_warned_seq_exact = False
 _MODE_FLAGS = {'default': 0, 'precise': N.FLOW_MODE_PRECISE, 'fast': N.FLOW_MODE_FAST_KNOTS}
 _mode = 'default'
 
@@ -320,6 +323,21 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     leafs = [t for op in ops for t in op.leafs]
     needs_grad = torch.is_grad_enabled() and (x2.requires_grad or any(t.requires_grad for t in leafs))
     if needs_grad:
+        # The reference's last-iteration log-det of a sequential spline layer has no fused gradient:
+        # when gradients are needed the layer is lowered with the exact log-determinant instead (same value to ~1e-5 at
+        # initialisation, a well-defined objective afterwards), so that fit() / variational_fit() work out of the box.
+        quirky = [i for i, op in enumerate(ops) if op.kind == N.OP_MADE_SEQ and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV)
+                  and not (op.flags & N.FLAG_SEQ_LOGDET_EXACT)]
+        if quirky:
+            global _warned_seq_exact
+            if not _warned_seq_exact:
+                _warned_seq_exact = True
+                warnings.warn('gradients through the sequential direction of a spline masked-autoregressive layer use the '
+                              'exact log-determinant (the reference reports the log-det of its last iteration, which has '
+                              'no fused gradient); set layer.sequential_log_det_reference_quirk = False to use the exact '
+                              'value for inference as well')
+            for i in quirky:
+                ops[i] = dataclasses.replace(ops[i], flags=ops[i].flags | N.FLAG_SEQ_LOGDET_EXACT)
         y, ld, lp = FlowFunction.apply(x2, _Cfg(ops, want_log_prob, base_loc, base_log_scale, flags), *leafs)
         return y, ld, (lp if want_log_prob else None)
     D = x2.shape[1]

@@ -51,12 +51,16 @@ class _TF32Linear(torch.autograd.Function):
         return gx, gw, gb
 
 
-def _fits_fused_kernel(n_dim: int, n_hidden: int) -> bool:
-    """Mirror of the shared-memory budget of csrc/b2f_flow.cu at its smallest tile (32 samples): the sample tile
-    [32][D|1] plus the hidden activations [32][H|1] (twice for the backward kernel's gradient tile) must fit in
-    ~200 KB.  Wider layers (e.g. D=1024 with n_hidden=1024) run as a composite: library GEMMs for the conditioner and
-    the stand-alone transformer kernel."""
-    return 4 * (2 * 32 * (n_dim | 1) + 2 * 32 * (n_hidden | 1) + 3 * n_dim + 32 * 24 * 8 + 1024) <= 200 * 1024
+def _fits_fused_kernel(n_dim: int, n_hidden: int, kind: int = N.OP_ELEMENTWISE, tkind: int = N.T_AFFINE_FWD,
+                       n_bins: int = 0) -> bool:
+    """Can a layer of this shape run -- and TRAIN -- inside the fused flow kernels?  Forward: mirror of the shared-memory
+    budget of csrc/b2f_flow.cu at its smallest tile (32 samples): the sample tile [32][D|1] plus the hidden activations
+    [32][H|1].  Backward: the library is asked (b2f_flow_backward_fits: the backward kernel keeps a gradient tile next to
+    the sample tile and stages spline weights per warp, so it runs out of shared memory first -- at D = 768 for MADE
+    layers).  Layers that do not fit (e.g. D=1024 with n_hidden=1024) run as a composite: library GEMMs for the
+    conditioner and the stand-alone transformer kernel."""
+    forward = 4 * (2 * 32 * (n_dim | 1) + 2 * 32 * (n_hidden | 1) + 3 * n_dim + 32 * 24 * 8 + 1024) <= 200 * 1024
+    return forward and N.flow_backward_fits(kind, tkind, max(n_hidden, 1), n_bins, n_dim)
 
 
 def _transformer_fusable(tr) -> bool:
@@ -112,7 +116,9 @@ class CouplingBijection(AutoregressiveBijection):
         # as a composite (conditioner = library GEMMs on [x_A, context], transformer = stand-alone kernel)
         self._fusable = (context_shape is None and isinstance(coupling, HalfSplit) and type(ct) is FeedForward
                          and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
-                         and _transformer_fusable(transformer) and _fits_fused_kernel(self.n_dim, ct.n_hidden))
+                         and _transformer_fusable(transformer)
+                         and _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_COUPLING, transformer._tkind_forward,
+                                                self._spline_args()[0]))
 
     # -- reference API ---------------------------------------------------------------------------------------
     def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
@@ -226,6 +232,9 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
                 raise NotImplementedError('MADE masks let the context reach the outputs; this configuration is not fused')
         fin = ct.sequential[0].mask[:, :self.n_dim].sum(dim=1).to(torch.int32)
         self.register_buffer('_fin_steps', fin, persistent=False)
+        # event sizes whose backward tile no longer fits shared memory (D >= 768) run as a composite, see _composite_*
+        self._fusable = _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_MADE, transformer._tkind_forward,
+                                           self._spline_args()[0])
 
     def _lower(self, one_pass: bool, transformer_direction: str):
         seq = self.conditioner_transform.sequential
@@ -240,24 +249,56 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
                                n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, flags=flags, owner=self)]
 
     def lower(self, direction: str):
+        if not self._fusable:
+            return None
         return self._lower(True, 'forward') if direction == 'forward' else self._lower(False, 'inverse')
 
     def apply_conditioner_transformer(self, inputs, context, forward: bool = True):
         h = self.conditioner_transform(inputs, context)
         return self.transformer.forward(inputs, h) if forward else self.transformer.inverse(inputs, h)
 
+    # -- composite path (layers too large for the fused kernels) ------------------------------------------------------
+    def _composite_one_pass(self, x: torch.Tensor, context, transformer_forward: bool):
+        """Masked conditioner as library GEMMs, transformer as the stand-alone kernel (layers_base.py:202-211)."""
+        return self.apply_conditioner_transformer(x, context, forward=transformer_forward)
+
+    def _composite_sequential(self, z: torch.Tensor, context, transformer_forward: bool):
+        """The reference's D-step loop (layers_base.py:213-223), one dimension fixed per iteration.  With the default
+        ``sequential_log_det_reference_quirk`` the log-det is the last iteration's, as in the reference; otherwise it is
+        the exact one, evaluated by one extra pass in the opposite direction at the result."""
+        batch_shape = get_batch_shape(z, self.event_shape)
+        x = flatten_event(z, self.event_shape)
+        log_det = None
+        for i in range(self.n_dim):
+            tmp, log_det = self.apply_conditioner_transformer(unflatten_event(x, self.event_shape), context,
+                                                              forward=transformer_forward)
+            tmp = flatten_event(tmp, self.event_shape)
+            x = torch.cat([x[..., :i], tmp[..., i:i + 1], x[..., i + 1:]], dim=-1)
+        out = unflatten_event(x, self.event_shape)
+        if not self.sequential_log_det_reference_quirk:
+            log_det = -self.apply_conditioner_transformer(out, context, forward=not transformer_forward)[1]
+        return out, log_det.reshape(batch_shape)
+
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_fused(x, 'forward')
+        return self._run_fused(x, 'forward') if self._fusable else self._composite_one_pass(x, context, True)
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_fused(z, 'inverse')
+        return self._run_fused(z, 'inverse') if self._fusable else self._composite_sequential(z, context, False)
 
 
 class InverseMaskedAutoregressiveBijection(MaskedAutoregressiveBijection):
     """forward = sequential direction (with transformer.inverse), inverse = one pass (layers_base.py:226-234)."""
 
     def lower(self, direction: str):
+        if not self._fusable:
+            return None
         return self._lower(False, 'inverse') if direction == 'forward' else self._lower(True, 'forward')
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(x, 'forward') if self._fusable else self._composite_sequential(x, context, False)
+
+    def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_fused(z, 'inverse') if self._fusable else self._composite_one_pass(z, context, True)
 
 
 class ElementwiseBijection(AutoregressiveBijection):

@@ -716,6 +716,53 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
 
 static int ilog2b(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+// Tile shape of the backward kernel for a program: rows per tile TM, threads NT, and whether spline layers stage one
+// element's output-layer weights per warp (wst_stride > 0: tensor-core path).  Preferred shapes first, then smaller ones
+// (fewer warps, then without the weight staging) until the shared-memory footprint fits; false if nothing fits.
+// b2f_flow_backward_fits() answers the same question for callers that must decide before building a program.
+struct BwdShape { int TM, NT, wst_stride; size_t smem; };
+
+static bool bwd_tile_shape(const b2f_op_t* ops, int32_t n_ops, int32_t D, int32_t flags, BwdShape& out) {
+    int Hmax = 1, Hrq = 0;
+    bool rq_aligned = true;
+    for (int i = 0; i < n_ops; ++i) {
+        const b2f_op_t& o = ops[i];
+        if (o.kind == B2F_OP_COUPLING || o.kind == B2F_OP_MADE || o.kind == B2F_OP_MADE_SEQ) Hmax = std::max(Hmax, o.n_hidden);
+        if ((o.kind == B2F_OP_COUPLING || o.kind == B2F_OP_MADE) && (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV) &&
+            o.n_hidden <= 31) {
+            Hrq = std::max(Hrq, o.n_hidden);
+            if (reinterpret_cast<uintptr_t>(o.p[2]) & 15) rq_aligned = false;
+        }
+    }
+    const int XS = D | 1, HS = Hmax | 1;
+    const int wst_pref = (Hrq > 0 && rq_aligned && !(flags & B2F_FLOW_MODE_PRECISE)) ? ((Hrq * 24 + 24 + 3) & ~3) : 0;
+    auto smem_bytes = [&](int tm, int nt, int wst) {
+        const int wpg = (nt / 32) / (tm / 32);
+        return (size_t)sizeof(float) * (2 * (size_t)tm * XS + 2 * (size_t)tm * HS + (((size_t)wpg * tm * HS + 3) & ~3) +
+                                        (size_t)wpg * tm + tm + ((3 * D + 3) & ~3) + (size_t)(nt / 32) * 32 * 24 +
+                                        (size_t)(nt / 32) * 2 * wst + 4);
+    };
+    // spline programs: 12 warps on one 32-row tile (the kernel is latency-bound: measured 10.4 ms against 11.6 ms for
+    // 8 warps on 64 rows, CouplingRQNSF-256, 131072 rows); everything else: 8 warps on 64 rows
+    struct Try { int tm, nt, wst; };
+    Try tries[8];
+    int n = 0;
+    const char *etm = getenv("B2F_BWD_TM"), *ent = getenv("B2F_BWD_NT");
+    if (etm || ent) tries[n++] = {etm ? atoi(etm) : (wst_pref ? 32 : 64), ent ? atoi(ent) : (wst_pref ? 384 : 256), wst_pref};
+    if (wst_pref) { tries[n++] = {32, 384, wst_pref}; tries[n++] = {32, 256, wst_pref}; tries[n++] = {32, 128, wst_pref}; }
+    tries[n++] = {64, 256, 0}; tries[n++] = {32, 256, 0}; tries[n++] = {32, 128, 0}; tries[n++] = {32, 64, 0};
+    for (size_t limit : {(size_t)200 * 1024, (size_t)227 * 1024})       // leave room for a second resident CTA first
+        for (int i = 0; i < n; ++i) {
+            const int TM = tries[i].tm, NT = tries[i].nt;
+            if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 384 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32) continue;
+            const size_t smem = smem_bytes(TM, NT, tries[i].wst);
+            if (smem > limit) continue;
+            out.TM = TM; out.NT = NT; out.wst_stride = tries[i].wst; out.smem = smem;
+            return true;
+        }
+    return false;
+}
+
 }  // namespace b2f
 
 using namespace b2f;
@@ -725,6 +772,12 @@ extern "C" int64_t b2f_flow_backward_workspace(const b2f_op_t* ops, int32_t n_op
     for (int i = 0; i < n_ops; ++i)
         if (ops[i].kind == B2F_OP_COUPLING || ops[i].kind == B2F_OP_MADE || ops[i].kind == B2F_OP_MADE_SEQ) ++n;
     return n * B * (int64_t)D * (int64_t)sizeof(float);
+}
+
+extern "C" int32_t b2f_flow_backward_fits(const b2f_op_t* ops, int32_t n_ops, int32_t D) {
+    if (!ops || n_ops < 0 || n_ops > B2F_MAX_OPS || D <= 0) return 0;
+    BwdShape shape;
+    return bwd_tile_shape(ops, n_ops, D, 0, shape) ? 1 : 0;
 }
 
 extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float* x, const float* gy,
@@ -802,34 +855,12 @@ extern "C" int b2f_flow_backward(const b2f_op_t* ops, int32_t n_ops, const float
     }
     if (getenv("B2F_BWD_NO_MMA")) A.flags |= B2F_FLOW_MODE_PRECISE;
     if (getenv("B2F_BWD_DEBUG_CLOCK")) A.flags |= 0x200;
-    // spline one-pass layers: per-warp double buffer for one element's output-layer weights (tensor-core path)
-    int Hrq = 0;
-    bool rq_aligned = true;
-    for (int i = 0; i < n_ops; ++i) {
-        const b2f_op_t& o = ops[i];
-        if ((o.kind == B2F_OP_COUPLING || o.kind == B2F_OP_MADE) && (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV) &&
-            o.n_hidden <= 31) {
-            Hrq = std::max(Hrq, o.n_hidden);
-            if (reinterpret_cast<uintptr_t>(o.p[2]) & 15) rq_aligned = false;
-        }
-    }
-    A.wst_stride = (Hrq > 0 && rq_aligned && !(A.flags & B2F_FLOW_MODE_PRECISE)) ? ((Hrq * 24 + 24 + 3) & ~3) : 0;
-    // spline programs: 12 warps on one 32-row tile (the kernel is latency-bound: measured 10.4 ms against 11.6 ms for
-    // 8 warps on 64 rows, CouplingRQNSF-256, 131072 rows); everything else: 8 warps on 64 rows
-    int TM = A.wst_stride ? 32 : 64, NT = A.wst_stride ? 384 : 256;
-    if (const char* e = getenv("B2F_BWD_TM")) TM = atoi(e);
-    if (const char* e = getenv("B2F_BWD_NT")) NT = atoi(e);
-    auto smem_bytes = [&](int tm, int nt) {
-        const int wpg = (nt / 32) / (tm / 32);
-        return (size_t)sizeof(float) * (2 * (size_t)tm * A.XS + 2 * (size_t)tm * A.HS + (((size_t)wpg * tm * A.HS + 3) & ~3) +
-                                        (size_t)wpg * tm + tm + ((3 * D + 3) & ~3) + (size_t)(nt / 32) * 32 * 24 +
-                                        (size_t)(nt / 32) * 2 * A.wst_stride + 4);
-    };
-    while (TM > 32 && smem_bytes(TM, NT) > 200 * 1024) TM >>= 1;
-    if (TM < 32 || (TM & (TM - 1)) || NT % 32 || NT > 384 || (NT / 32) % (TM / 32) || NT / 32 < TM / 32)
-        return fail(B2F_ERR_INVALID, "b2f_flow_backward: bad tile shape TM=%d NT=%d", TM, NT);
-    const size_t smem = smem_bytes(TM, NT);
-    if (smem > 227 * 1024) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: D=%d H=%d does not fit shared memory", D, Hmax);
+    BwdShape shape;
+    if (!bwd_tile_shape(ops, n_ops, D, A.flags, shape))
+        return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: D=%d H=%d does not fit shared memory", D, Hmax);
+    A.wst_stride = shape.wst_stride;
+    const int TM = shape.TM, NT = shape.NT;
+    const size_t smem = shape.smem;
     A.TM = TM; A.logTM = ilog2b(TM); A.G = TM / 32; A.WPG = (NT / 32) / A.G;
     const long long grid = (B + TM - 1) / TM;
     if (grid > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_backward: batch too large for one launch");

@@ -36,7 +36,8 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def allreduce_gradients(parameters, world: int) -> None:
-    """Mean of the gradients over all ranks: one flat bucket, one all-reduce (NCCL on GPU)."""
+    """Mean of the gradients over all ranks in one flat bucket (kept for callers that hold plain ``.grad`` tensors; ``fit``
+    and ``train_step`` use ``GradBuckets``, which overlaps the exchange with the backward pass and copies nothing)."""
     import torch.distributed as dist
     grads = [p.grad for p in parameters if p.grad is not None]
     if not grads or world == 1:
@@ -49,6 +50,95 @@ def allreduce_gradients(parameters, world: int) -> None:
         n = g.numel()
         g.copy_(flat[offset:offset + n].view_as(g))
         offset += n
+
+
+class GradBuckets:
+    """Data-parallel gradient exchange of ``Flow.fit``: one bucket per layer of the bijection, gradients
+    LIVING in the bucket (every ``p.grad`` is a view into its bucket's flat buffer, so nothing is packed or copied back),
+    and each bucket's all-reduce launched from a post-accumulate hook the moment the backward pass has produced the last
+    gradient of that layer -- it runs on NCCL's stream while autograd is still working on the layers in front of it.
+    ``finish()`` waits for the exchanges before the optimizer step.  Mean over ranks: ``ReduceOp.AVG`` on NCCL (no extra
+    pass), sum + scale elsewhere (gloo, CPU tests)."""
+
+    MIN_BUCKET_BYTES = 1 << 20      # neighbouring layers are merged up to this size: launch latency, not link count
+
+    def __init__(self, flow, world: int):
+        import torch.distributed as dist
+        self.world = world
+        self.avg = dist.get_backend() == 'nccl'
+        groups, seen = [], set()
+        layers = list(getattr(flow.bijection, 'layers', [flow.bijection]))
+        for layer in reversed(layers):           # backward finishes the last layer first
+            ps = [p for p in layer.parameters() if p.requires_grad and id(p) not in seen]
+            seen.update(id(p) for p in ps)
+            if ps:
+                groups.append(ps)
+        rest = [p for p in flow.parameters() if p.requires_grad and id(p) not in seen]
+        if rest:
+            groups.append(rest)
+        merged = []
+        for ps in groups:
+            size = sum(p.numel() * p.element_size() for p in ps)
+            if merged and merged[-1][1] < self.MIN_BUCKET_BYTES:
+                merged[-1][0].extend(ps)
+                merged[-1][1] += size
+            else:
+                merged.append([list(ps), size])
+        self.flats, self.params, self.pending, self.bucket_of, self.hooks, self.handles = [], [], [], {}, [], []
+        for bi, (ps, _) in enumerate(merged):
+            flat = torch.zeros(sum(p.numel() for p in ps), device=ps[0].device, dtype=ps[0].dtype)
+            offset = 0
+            for p in ps:
+                p.grad = flat[offset:offset + p.numel()].view_as(p)
+                offset += p.numel()
+                self.bucket_of[id(p)] = bi
+                self.hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+            self.flats.append(flat)
+            self.params.append(ps)
+            self.pending.append(len(ps))
+        self.launched = [False] * len(self.flats)
+        self.nbytes = sum(f.numel() * f.element_size() for f in self.flats)
+
+    def begin_step(self):
+        """Instead of optimizer.zero_grad(): the gradients stay views of the buckets."""
+        torch._foreach_zero_(self.flats)
+        self.pending = [len(ps) for ps in self.params]
+        self.launched = [False] * len(self.flats)
+        self.handles = []
+
+    def _launch(self, bi):
+        import torch.distributed as dist
+        flat = self.flats[bi]
+        offset = 0
+        for p in self.params[bi]:               # a gradient that autograd re-bound instead of accumulating in place
+            view = flat[offset:offset + p.numel()]
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad.reshape(-1))
+                p.grad = view.view_as(p)
+            offset += p.numel()
+        self.handles.append(dist.all_reduce(flat, op=dist.ReduceOp.AVG if self.avg else dist.ReduceOp.SUM, async_op=True))
+        self.launched[bi] = True
+
+    def _on_grad(self, p):
+        bi = self.bucket_of[id(p)]
+        self.pending[bi] -= 1
+        if self.pending[bi] == 0 and not self.launched[bi]:
+            self._launch(bi)
+
+    def finish(self):
+        for bi in range(len(self.flats)):       # layers that received no gradient this step still take part (zeros)
+            if not self.launched[bi]:
+                self._launch(bi)
+        for h in self.handles:
+            h.wait()
+        if not self.avg:
+            torch._foreach_div_(self.flats, float(self.world))
+        self.handles = []
+
+    def close(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
 
 
 def _allreduce_stats(s, q, n):
@@ -117,6 +207,7 @@ class BaseFlow(nn.Module):
             raise ValueError(f'Invalid base distribution: {base_distribution}')
         self.register_buffer('device_buffer', torch.empty(size=()))
         self._optimizer = None
+        self._buckets = None        # GradBuckets while training data-parallel
 
     def get_device(self):
         return self.device_buffer.device
@@ -164,6 +255,38 @@ class BaseFlow(nn.Module):
             context_val: torch.Tensor = None, keep_best_weights: bool = True, early_stopping: bool = False,
             early_stopping_threshold: int = 50, max_batch_size_mb: int = None,
             time_limit_seconds: Union[float, int] = None, reset_optimizer: bool = True, cuda_graph: bool = False):
+        """See ``_fit`` for the training loop.  This wrapper owns what data-parallel training adds around it and undoes it
+        whatever happens inside: every rank starts from rank 0's weights and buffers and shuffles with rank 0's seed,
+        ActNorm initialises from all-reduced statistics, gradients are exchanged through ``GradBuckets``."""
+        rank, world = _dist_info()
+        seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64)      # from the global RNG, like a DataLoader's shuffle
+        trains = any(p.requires_grad for p in self.parameters())
+        if world > 1 and trains:
+            import torch.distributed as dist
+            device = self.get_device()
+            for t in self.state_dict().values():
+                if t.numel() > 0:
+                    dist.broadcast(t, src=0)
+            seed_dev = seed.to(device)
+            dist.broadcast(seed_dev, src=0)
+            seed = seed_dev.cpu()
+            self.bijection._stats_reduce_fn = _allreduce_stats
+            self._buckets = GradBuckets(self, world)
+        try:
+            return self._fit(x_train, n_epochs, lr, batch_size, shuffle, show_progress, w_train, context_train, x_val, w_val,
+                             context_val, keep_best_weights, early_stopping, early_stopping_threshold, max_batch_size_mb,
+                             time_limit_seconds, reset_optimizer, cuda_graph, int(seed))
+        finally:
+            # a later ActNorm initialisation or train_step outside this process group must not try to communicate
+            if world > 1 and trains:
+                self.bijection._stats_reduce_fn = None
+                if self._buckets is not None:
+                    self._buckets.close()
+                self._buckets = None
+
+    def _fit(self, x_train, n_epochs, lr, batch_size, shuffle, show_progress, w_train, context_train, x_val, w_val,
+             context_val, keep_best_weights, early_stopping, early_stopping_threshold, max_batch_size_mb,
+             time_limit_seconds, reset_optimizer, cuda_graph, shuffle_seed):
         """Maximum-likelihood fit with the reference's semantics (flows.py:226-455): AdamW, minibatches in a fresh
         random order every epoch, best-weights snapshot, divergence rollback, optional validation / early stopping /
         adaptive batch size / time limit.  The data are moved to the flow's device once and batches are index
@@ -226,10 +349,9 @@ class BaseFlow(nn.Module):
             use_graph = False        # an optimizer kept from an earlier call cannot be stepped inside a graph: stay eager
         trainable = [p for p in self.parameters() if p.requires_grad]
         graph_step, eager_steps, replayed, loss = None, 0, False, None
-        if world > 1:
-            self.bijection._stats_reduce_fn = _allreduce_stats     # ActNorm initialises from global statistics
+        buckets = self._buckets
         gen = torch.Generator(device='cpu')
-        gen.manual_seed(int(torch.initial_seed()) & 0x7fffffff)    # identical batch order on every rank
+        gen.manual_seed(shuffle_seed)                               # identical batch order on every rank
 
         val_loss = None
         best_val_loss = best_train_loss = float('inf')
@@ -238,7 +360,13 @@ class BaseFlow(nn.Module):
         diverged = False
 
         for epoch in (pbar := tqdm(range(n_epochs), desc='Fitting NF', disable=not show_progress)):
-            if time_limit_seconds is not None and time.time() - t0 >= time_limit_seconds:
+            out_of_time = time_limit_seconds is not None and time.time() - t0 >= time_limit_seconds
+            if world > 1 and time_limit_seconds is not None:
+                import torch.distributed as dist
+                flag = torch.tensor([float(out_of_time)], device=device)      # ranks stop together or not at all: one rank
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)                  # leaving alone would hang the others' collectives
+                out_of_time = bool(flag.item())
+            if out_of_time:
                 print('Training time limit exceeded')
                 break
             if adaptive and epoch % 10 == 9 and batch_size < max_batch_size:
@@ -285,8 +413,8 @@ class BaseFlow(nn.Module):
                 total += float(loss_value)
                 n_batches += 1
                 loss.backward()
-                if world > 1:
-                    allreduce_gradients(trainable, world)
+                if buckets is not None:
+                    buckets.finish()
                 self._optimizer.step()
                 if show_progress:
                     msg = f'Training loss (batch): {float(loss_value):.4f} [{best_train_loss:.4f} @ {best_train_epoch}]'
@@ -332,7 +460,11 @@ class BaseFlow(nn.Module):
         """Loss of this rank's slice of a minibatch, scaled so that the mean over ranks of the gradients is the gradient
         of the global-batch loss -mean(w*log_prob)/event_size + regularization (flows.py:199-224); returns the local
         loss tensor (to call backward on) and the global loss value (all-reduced when world > 1)."""
-        self._optimizer.zero_grad()
+        buckets = getattr(self, '_buckets', None)
+        if buckets is not None:
+            buckets.begin_step()                 # gradients are views of the all-reduce buckets: zero them in place
+        else:
+            self._optimizer.zero_grad()
         if world == 1:
             batch = (xb, wb) if cb is None else (xb, wb, cb)
             loss = self._base_batch_loss(batch, reduction=torch.mean, use_regularization=True)
@@ -353,10 +485,12 @@ class BaseFlow(nn.Module):
             self._optimizer = _make_adamw(self.parameters(), 0.05)
         if wb is None:
             wb = torch.ones(len(xb), device=xb.device)
+        if world > 1 and getattr(self, '_buckets', None) is None:
+            self._buckets = GradBuckets(self, world)           # kept for the following steps; fit() builds its own
         loss, loss_value = self._loss_and_backward_inputs(xb, wb, n_global or len(xb) * world, world)
         loss.backward()
         if world > 1:
-            allreduce_gradients([p for p in self.parameters() if p.requires_grad], world)
+            self._buckets.finish()
         self._optimizer.step()
         return loss_value
 
