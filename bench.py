@@ -34,8 +34,10 @@ WORKLOADS = {
 
 
 # the kernel each workload's log_prob launch dispatches to (b2f_flow_apply: csrc/b2f_flow.cu)
-KERNELS = {'q256': 'b2f::flow_tc_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_rows_kernel',
+KERNELS = {'q256': 'b2f::flow_tcq_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_rows_kernel',
            'm128': 'b2f::flow_rows_kernel'}
+KERNEL_IDS = {0: 'none', 1: 'generic (b2f_flow.cu)', 2: 'tc (b2f_flow_tc.cu)', 3: 'rows (b2f_flow_rows.cu)',
+              4: 'tcq (b2f_flow_tcq.cu)'}
 
 
 def algorithmic_bytes(D):
@@ -135,24 +137,39 @@ def build_flow(preset, D, device=None, init_rows=None):
     return flow
 
 
-def cpu_oracle_throughput(preset, D, state_dict, chunk, rows, steps, warmup, seed=1):
-    """The reference's CPU path (oracle/flow_oracle.py: the same ATen CPU ops in the same order, validated bit for
-    bit against the real reference) on all host cores: log_prob + sample over `rows` rows in chunks of `chunk`."""
+def cpu_oracle_throughput(preset, D, state_dict, chunk, rows, steps, warmup, seed=1, init_state_t=False, device='cpu'):
+    """The reference's own op sequence (oracle/flow_oracle.py: the same ATen ops in the same order, validated bit for bit
+    against the real reference on the CPU): log_prob + sample over `rows` rows in chunks of `chunk`.  device='cpu': all host
+    cores (the reference's CPU path).  device='cuda:0': the same ops eagerly on the B200, TF32 off -- the reference's own
+    "CUDA support" is nn.Module.cuda() (docs/source/guides/cuda.rst), i.e. this is the existing Blackwell path.
+    init_state_t: data-initialise ActNorm by the oracle itself on 8192 synthetic rows (state T of SURVEY 8d)."""
     import torch
     from oracle.flow_oracle import OracleFlow
     torch.set_num_threads(os.cpu_count() or 1)
-    o = OracleFlow(preset, (D,), state_dict)
+    if device != 'cpu':
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+    o = OracleFlow(preset, (D,), state_dict, device=device)
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(rows, D, generator=g)
-    z = torch.randn(rows, D, generator=g)
+    if init_state_t:
+        with torch.no_grad():
+            o.actnorm_initialise(torch.randn(8192, D, generator=g).to(device))
+    x = torch.randn(rows, D, generator=g).to(device)
+    z = torch.randn(rows, D, generator=g).to(device)
+
+    def sync():
+        if device != 'cpu':
+            torch.cuda.synchronize()
     times = []
     with torch.no_grad():
         for it in range(warmup + steps):
+            sync()
             t0 = time.perf_counter()
             for s in range(0, rows, chunk):
                 o.log_prob(x[s:s + chunk])
             for s in range(0, rows, chunk):
                 o.sample_from_noise(z[s:s + chunk])
+            sync()
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
     t = statistics.median(times)
@@ -167,14 +184,16 @@ def run_reference(args):
     flow = build_flow(preset, D)           # CPU module: only a weight container here
     flow.eval()
     sd = flow.state_dict()
-    value, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, args.steps, args.warmup)
-    sample = f'{cpu_rows} rows in chunks of {chunk} per step (log_prob + sample), state E weights'
+    value, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, args.steps, args.warmup, init_state_t=True)
+    sample = (f'{cpu_rows} rows in chunks of {chunk} per step (log_prob + sample); weights: constructor under seed 0, ActNorm '
+              f'data-initialised by the oracle on 8192 synthetic rows (state T, like the repo arm)')
     line = {
         'impl': 'reference', 'metric': 'log_prob+sample samples/s', 'value': value, 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{preset} n_dim={D}: log_prob + sample, CPU (oracle port of the reference, torch CPU ops)',
-                   'rows_per_step': cpu_rows, 'chunk': chunk},
+                   'weights': 'random init (seed 0), ActNorm data-initialised (state T)', 'rows_per_step': cpu_rows,
+                   'chunk': chunk},
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -261,20 +280,12 @@ def run_ours(args):
         lp_ms = [ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)]
         s_ms = [ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]
         del xs
-        # opt-in 'fast' arithmetic mode (SFU exponentials for the spline knots), reported beside the default
-        import torchflows_b200
-        torchflows_b200.set_math_mode('fast')
-        for _ in range(2):
-            step()
-        sync_all()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(args.steps):
-            step()
-        f1.record(stream)
-        sync_all()
-        fast_ms = f0.elapsed_time(f1) / args.steps
-        torchflows_b200.set_math_mode('default')
+        from torchflows_b200 import _native as N_
+        flow._sample_from_base(z[:4096], no_grad=True)
+        k_s = N_.last_flow_kernel()
+        lp = flow.log_prob(x)
+        k_lp_full = N_.last_flow_kernel()
+        del lp
 
         # ---- end to end through the public API: pinned host buffers in, host buffers out -----------------------
         e2e_steps = max(2, min(args.steps, 5))
@@ -345,15 +356,31 @@ def run_ours(args):
         t1.record(stream)
         sync_all()
         e2e_ms = t0.elapsed_time(t1) / e2e_steps
+        # the copies alone, both directions at once, same buffers: what the host side of this box can move
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        xd_tmp = torch.empty(B, D, device=dev)
+        sync_all()
+        c0.record(stream)
+        for _ in range(2):
+            with torch.cuda.stream(h2d_stream):
+                xd_tmp.copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(d2h_stream):
+                xs_host.copy_(x, non_blocking=True)
+        stream.wait_stream(h2d_stream)
+        stream.wait_stream(d2h_stream)
+        c1.record(stream)
+        sync_all()
+        copy_ms = c0.elapsed_time(c1) / 2
+        del xd_tmp
         gc.enable()
         sampler.stop_flag = True           # clocks were sampled across the device-resident, fast-mode and e2e regions
         sampler.join(timeout=3)
 
     # max over ranks
-    times = torch.tensor([total_ms, e2e_ms, fast_ms], device=dev, dtype=torch.float64)
+    times = torch.tensor([total_ms, e2e_ms, copy_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, fast_ms = float(times[0]), float(times[1]), float(times[2])
+    total_ms, e2e_ms, copy_ms = float(times[0]), float(times[1]), float(times[2])
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
     lp_avg_ms, s_avg_ms = statistics.mean(lp_ms), statistics.mean(s_ms)
@@ -380,7 +407,8 @@ def run_ours(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{preset} n_dim={D}, {B} rows per GPU: Flow.log_prob + Flow.sample (inverse pass)',
                    'weights': 'random init (seed 0), ActNorm data-initialised (state T)', 'rows_per_gpu': B,
-                   'l2': f'inputs larger than L2 ({B * D * 4 >> 20} MiB per tensor)', 'precision_mode': 'default (SFU after bin search)'},
+                   'l2': f'inputs larger than L2 ({B * D * 4 >> 20} MiB per tensor)',
+                   'precision_mode': 'default: TF32 conditioner GEMMs (tcgen05), SFU ex2/lg2/rcp in the spline epilogue'},
         'log_prob_samples_per_s': world * B / (lp_avg_ms * 1e-3), 'sample_samples_per_s': world * B / (s_avg_ms * 1e-3),
         'roofline': {'bound': 'hbm', 'kernel': KERNELS[args.workload] + ' (log_prob launch)', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
@@ -388,10 +416,15 @@ def run_ours(args):
                      'sample_launch': {'achieved': by_s * B / (s_avg_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_row': by_s,
                                        'launch_ms': s_avg_ms}},
         'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': B * D * 4,
-                'd2h_bytes_per_step': B * 4 + B * D * 4, 'ms_per_step': e2e_ms},
+                'd2h_bytes_per_step': B * 4 + B * D * 4, 'ms_per_step': e2e_ms, 'bound': 'host',
+                'copies_only_ms': copy_ms, 'h2d_GBps_per_gpu': B * D * 4 / (copy_ms * 1e-3) / 1e9,
+                'd2h_GBps_per_gpu': B * D * 4 / (copy_ms * 1e-3) / 1e9,
+                'note': 'pinned host memory <-> HBM over PCIe, both directions concurrently; copies_only_ms is the same '
+                        'traffic without any kernel (max over ranks): the end-to-end step is bound by the host side of the '
+                        'box (one NUMA node shared by all ranks), not by the GPU'},
         'gpu_launches': 2 * args.steps,
-        'fast_math_mode': {'value': world * B / (fast_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': fast_ms,
-                           'note': "torchflows_b200.set_math_mode('fast'): opt-in, bin indices not bit-reproducible"},
+        'dispatch': {'log_prob': KERNEL_IDS.get(k_lp_full, str(k_lp_full)), 'sample': KERNEL_IDS.get(k_s, str(k_s)),
+                     'note': 'kernel each call of the timed loop ran on (b2f_last_flow_kernel): 100 % on the fused path'},
         'clocks': sampler.summary(),
     }
     if rank == 0:
@@ -401,15 +434,102 @@ def run_ours(args):
             line['per_layer_roofline'] = transformer_kernel_roofline(torch, dev, hbm_peak)
         except Exception as e:       # never let the side measurement take the headline down
             line['per_layer_roofline'] = {'error': str(e)[:200]}
+    if rank == 0 and not args.no_cpu:
+        # the reference's op sequence run eagerly on this B200 (TF32 off): the existing Blackwell path (SURVEY 8d,
+        # BASELINE.md section 3), same weights (state T of this run), same chunking as the CPU arm
+        try:
+            sd = {k: v.detach().clone() for k, v in flow.state_dict().items()}
+            rows_e = min(B, 8 * chunk)
+            v, t, _ = cpu_oracle_throughput(preset, D, sd, chunk, rows_e, 3, 1, device=str(dev))
+            line['gpu_eager_baseline'] = {
+                'value': v, 'unit': 'samples/s', 'kind': 'port', 'device': torch.cuda.get_device_name(dev),
+                'sample': f'{rows_e} rows in chunks of {chunk} (log_prob + sample), allow_tf32=False, median of 3',
+                'speedup_of_this_repo': (B / (ms_per_step * 1e-3)) / v}
+        except Exception as e:
+            line['gpu_eager_baseline'] = {'error': str(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu:
         sd = {k: v.cpu() for k, v in flow.state_dict().items()}
         v, t, cores = cpu_oracle_throughput(preset, D, sd, chunk, cpu_rows, 3, 1)
         line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
-                                'sample': f'{cpu_rows} rows in chunks of {chunk} (log_prob + sample), median of 3'}
+                                'sample': f'{cpu_rows} rows in chunks of {chunk} (log_prob + sample), same weights as the '
+                                          f'repo arm (state T), median of 3'}
+    if not args.no_fit:
+        # Flow.fit, data-parallel over the same ranks: the path of this repo that has a collective in it
+        del x, z, x_host, xs_host, lp_host
+        in_flight.clear()
+        torch.cuda.empty_cache()
+        fit = {}
+        for wl in ('q256fit', 'w1024fit'):
+            try:
+                fit[wl] = fit_probe(torch, dist, dev, rank, world, wl)
+            except Exception as e:          # never let the side measurement take the headline down
+                fit[wl] = {'error': str(e)[:200]}
+        line['fit'] = fit
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def fit_probe(torch, dist, dev, rank, world, workload, steps=5, warmup=3, rows=0):
+    """ms per optimisation step of Flow.fit's inner loop (Flow.train_step: forward, backward, gradient exchange, AdamW) on
+    this rank's GPU, data-parallel over the visible ranks, plus the gradient all-reduce on its own (the same buckets, no
+    compute to hide behind).  Part of the default bench line so that the driver's 1/2/4/8-GPU run records the path that
+    has a collective in it (BASELINE.json configs[4])."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF
+    if workload == 'w1024fit':
+        D, H, per_gpu, kwargs = 1024, 1024, rows or 16384, {'conditioner_kwargs': {'n_hidden': 1024}}
+    else:
+        D, H, per_gpu, kwargs = 256, 17, rows or 131072, {}
+    torch.manual_seed(0)
+    flow = Flow(CouplingRQNSF(D, **kwargs)).to(dev)
+    n_params = sum(p.numel() for p in flow.parameters() if p.requires_grad)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x = torch.randn(per_gpu, D, device=dev, generator=g)
+    flow.train()
+    flow._optimizer = torch.optim.AdamW(flow.parameters(), lr=1e-3)
+    for _ in range(warmup):
+        flow.train_step(x, n_global=per_gpu * world)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = flow.train_step(x, n_global=per_gpu * world)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = [e0.elapsed_time(e1) / steps, 0.0]
+    nbytes = 0
+    if world > 1 and flow._buckets is not None:
+        b = flow._buckets
+        nbytes = b.nbytes
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(steps):
+            b.begin_step()
+            b.finish()
+        a1.record()
+        torch.cuda.synchronize()
+        t[1] = a0.elapsed_time(a1) / steps
+        b.close()
+    ms = torch.tensor(t, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step, ms_ar = float(ms[0]), float(ms[1])
+    path = 'composite (library GEMMs for the conditioner, b2f transformer kernels)' if D > 512 else \
+        'fused (b2f_flow_apply_saving + b2f_flow_backward)'
+    out = {'workload': f'CouplingRQNSF n_dim={D} n_hidden={H}, {per_gpu} rows per GPU', 'ms_per_step': ms_step,
+           'samples_per_s': world * per_gpu / (ms_step * 1e-3), 'trainable_parameters': n_params, 'path': path,
+           'allreduce_bytes_per_step': nbytes, 'allreduce_alone_ms': ms_ar, 'final_loss': float(loss)}
+    del flow, x
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_fit(args):
@@ -480,7 +600,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='q256', choices=sorted(WORKLOADS) + ['w1024fit', 'q256fit'])
     ap.add_argument('--rows', type=int, default=0, help='override rows per GPU')
-    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline and gpu_eager_baseline legs')
+    ap.add_argument('--no-fit', action='store_true', help='skip the Flow.fit probe (q256fit, w1024fit) of the default line')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else max(args.warmup, 1)
     if args.workload in ('w1024fit', 'q256fit'):

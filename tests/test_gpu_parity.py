@@ -259,3 +259,27 @@ def test_empty_batch_and_odd_shapes(dev):
             assert xs.shape == (B, D) and torch.isfinite(xs).all() and torch.isfinite(lps).all()
             # row i of a batch does not depend on the other rows or on the tile it lands in
             assert torch.equal(flow.log_prob(x[B // 2:B // 2 + 1]), lp[B // 2:B // 2 + 1])
+
+
+@pytest.mark.parametrize('state', ['E', 'T'])
+def test_mq128_many_tiles_vs_oracle(dev, state):
+    """MaskedAutoregressiveRQNSF(128) through the persistent tcgen05 kernel at 32768 + 77 rows (257 tiles on 148 SMs: the
+    mbarrier phases carry over tiles), states E and T, log_prob within 1e-4 abs/rel of the oracle (chunked on the CPU)."""
+    import torchflows_b200.architectures as arch
+    from torchflows_b200 import Flow, _native as N
+    torch.manual_seed(3)
+    D, B = 128, 32768 + 77
+    flow = Flow(arch.MaskedAutoregressiveRQNSF(D)).to(dev)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, D, generator=g)
+    if state == 'T':
+        flow.train()
+        with torch.no_grad():
+            flow.log_prob((torch.randn(4096, D, generator=g) * 1.3 + 0.2).to(dev))
+    flow.eval()
+    o = fo.OracleFlow('MaskedAutoregressiveRQNSF', (D,), {k: v.cpu() for k, v in flow.state_dict().items()})
+    with torch.no_grad():
+        lp = flow.log_prob(x.to(dev))
+    assert N.last_flow_kernel() == N.KERNEL_TC
+    ref = torch.cat([o.log_prob(x[i:i + 4096]) for i in range(0, B, 4096)])
+    close(lp, ref, f'MQ128 log_prob state {state}', LP_TOL, LP_TOL)
