@@ -160,6 +160,38 @@ int b2f_transformer_backward(int32_t tkind, const float *x, const float *h, cons
                              const float *glog_det, float *gx, float *gh, int64_t n_rows, int32_t n_event,
                              int64_t h_row_stride, int32_t n_bins, float boundary, int32_t flags, void *stream);
 
+/* ---- wide-conditioner spline coupling layer (csrc/b2f_wide.cu) ------------------------------------------------------
+ * One CouplingBijection with HalfSplit + FeedForward(n_layers=2, Tanh) + RationalQuadratic(n_bins=8) whose hidden
+ * width is too large for the whole-flow kernels (e.g. n_dim = 1024, n_hidden = 1024): layers_base.py:119-163,
+ * conditioning/transforms.py:274-307, transformers/spline/rational_quadratic.py:45-200.  Every contraction (forward,
+ * recompute, dgrad, wgrad) runs on tcgen05 kind::tf32; the conditioner output h = (B, D/2 * 23) is never written to
+ * memory (the spline, or its backward, is the epilogue of the output-layer GEMM reading tensor memory).
+ * Parameters in the reference's own layout: W1 (H, D/2), b1 (H), W2 (D/2 * 23, H), b2 (D/2 * 23).
+ * Requirements: D % 64 == 0, H % 32 == 0, n_bins == 8; x, y, workspace 16-byte aligned. */
+typedef struct b2f_wide_layer {
+    int32_t D;        /* event size; the first D/2 columns are the conditioner input, the rest are transformed */
+    int32_t H;        /* n_hidden */
+    int32_t tkind;    /* B2F_T_RQ_FWD (CouplingBijection.forward) or B2F_T_RQ_INV (.inverse) */
+    int32_t n_bins;   /* 8 */
+    float boundary;
+    int32_t reserved;
+    const float *W1, *b1, *W2, *b2;
+} b2f_wide_layer_t;
+
+/* Scratch bytes b2f_wide_coupling_forward (backward = 0) / b2f_wide_coupling_backward (backward = 1) need for B rows. */
+int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t backward);
+
+/* y:(B,D) = layer(x:(B,D)), log_det:(B) (nullable).  Nothing is kept for the backward except what the caller already
+ * has (x): b2f_wide_coupling_backward recomputes the hidden activations and h. */
+int b2f_wide_coupling_forward(const b2f_wide_layer_t *layer, const float *x, float *y, float *log_det, int64_t B,
+                              void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Given the layer INPUT x and upstream gy:(B,D) (nullable), glog_det:(B) (nullable): gx:(B,D) and the parameter gradients
+ * gW1, gb1, gW2, gb2 (reference layouts; overwritten, not accumulated).  Replaces autograd through the reference code above. */
+int b2f_wide_coupling_backward(const b2f_wide_layer_t *layer, const float *x, const float *gy, const float *glog_det,
+                               float *gx, float *gW1, float *gb1, float *gW2, float *gb2, int64_t B, void *workspace,
+                               int64_t workspace_bytes, void *stream);
+
 /* Per-dimension batch statistics for ActNorm's data-dependent initialisation (layers.py:58-68):
  * sum:(D) and sumsq:(D) of x:(B,D), accumulated in fp64 (must be zeroed by the caller). */
 int b2f_column_stats(const float *x, double *sum, double *sumsq, int64_t B, int32_t D, void *stream);

@@ -1,0 +1,130 @@
+"""Wide-conditioner spline coupling layer (csrc/b2f_wide.cu, include/b2f.h b2f_wide_coupling_*) against the oracle.
+
+The layer is CouplingBijection + FeedForward(n_hidden) + RationalQuadratic of the reference
+(layers_base.py:119-163, conditioning/transforms.py:274-307, transformers/spline/rational_quadratic.py:45-200); the
+checker is oracle/flow_oracle.py (the reference's ATen ops) in fp32 and fp64 on the CPU.  Tolerances: log_det 1e-4
+abs/rel (north star) -- the conditioner GEMMs run in TF32 like the fused whole-flow kernel -- outputs 1e-4 abs/rel.
+Gradients: dL/dh of this layer is two orders of magnitude more sensitive to h than the values are (an fp64 evaluation
+with only the GEMM operands rounded to TF32 moves the parameter gradients by 1e-2 relative for random upstream gradients,
+scripts/wide_diag.py), so the gradient checker is the oracle in fp64 with the *specified* operand rounding (x_A, W1,
+tanh(.), W2 to TF32, straight-through), tolerance 2e-3 relative L2 (TF32 operands of the three gradient GEMMs); the
+end-to-end check against the unrounded fp64 oracle on the real loss is tests/test_gpu_training.py::
+test_gradients_at_benchmark_shapes_with_fp64_referee."""
+import pytest
+import torch
+
+from oracle import flow_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _params(D, H, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    Dh = D // 2
+    W1 = (torch.rand(H, Dh, generator=g) * 2 - 1) / Dh ** 0.5
+    b1 = (torch.rand(H, generator=g) * 2 - 1) / Dh ** 0.5
+    W2 = (torch.rand(Dh * 23, H, generator=g) * 2 - 1) / H ** 0.5 * scale
+    b2 = (torch.rand(Dh * 23, generator=g) * 2 - 1) / H ** 0.5 * scale
+    return W1, b1, W2, b2
+
+
+def _tf32_st(t):
+    """Round to TF32 (nearest, ties away: cvt.rna) with a straight-through gradient."""
+    r = ((t.detach().float().contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).to(t.dtype)
+    return t + (r - t).detach()
+
+
+def _oracle_layer(x, W1, b1, W2, b2, direction, boundary, dtype, tf32_operands=False):
+    """The reference's coupling layer restated with the oracle's functions: returns (y, log_det).  tf32_operands: the
+    arithmetic the kernels specify -- GEMM operands rounded to TF32, everything else in `dtype`."""
+    x, W1, b1, W2, b2 = (t.to(dtype) for t in (x, W1, b1, W2, b2))
+    Dh = x.shape[1] // 2
+    xa, xb = x[:, :Dh], x[:, Dh:]
+    rnd = _tf32_st if tf32_operands else (lambda t: t)
+    h = (rnd(torch.tanh(rnd(xa) @ rnd(W1).t() + b1)) @ rnd(W2).t() + b2).view(x.shape[0], Dh, 23)
+    fn = O.rq_forward if direction == 'forward' else O.rq_inverse
+    yb, ld = fn(xb, h, n_bins=8, boundary=boundary)
+    return torch.cat([xa, yb], dim=1), ld
+
+
+@pytest.mark.parametrize('B,D,H,direction', [(300, 64, 32, 'forward'), (300, 64, 32, 'inverse'), (1000, 128, 96, 'forward'),
+                                             (513, 192, 256, 'inverse'), (2048, 256, 320, 'forward'), (1, 64, 64, 'forward')])
+def test_wide_layer_forward_vs_oracle(B, D, H, direction):
+    from torchflows_b200 import _native as N
+    dev = torch.device('cuda:0')
+    W1, b1, W2, b2 = _params(D, H, seed=B + D + H)       # nn.Linear's default init range, like the presets
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, D, generator=g) * 2.0
+    x[0, D // 2] = 7.5                       # outside the spline: identity tail
+    boundary = 5.0
+    tk = N.T_RQ_FWD if direction == 'forward' else N.T_RQ_INV
+    y, ld = N.wide_coupling_forward(tk, x.to(dev), *(t.to(dev) for t in (W1, b1, W2, b2)), n_bins=8, boundary=boundary)
+    torch.cuda.synchronize()
+    y64, ld64 = _oracle_layer(x, W1, b1, W2, b2, direction, boundary, torch.float64)
+    assert torch.equal(y[:, :D // 2].cpu(), x[:, :D // 2])
+    assert float(y[0, D // 2]) == 7.5
+    err_y = (y.cpu().double() - y64).abs() / (1 + y64.abs())
+    err_ld = (ld.cpu().double() - ld64).abs() / (1 + ld64.abs())
+    assert float(err_y.max()) < 1e-4, float(err_y.max())
+    assert float(err_ld.max()) < 1e-4, float(err_ld.max())
+
+
+@pytest.mark.parametrize('B,D,H,direction', [(300, 64, 32, 'forward'), (700, 128, 96, 'forward'), (515, 128, 64, 'inverse'),
+                                             (1024, 256, 288, 'forward')])
+def test_wide_layer_backward_vs_oracle_autograd(B, D, H, direction):
+    from torchflows_b200 import _native as N
+    dev = torch.device('cuda:0')
+    W1, b1, W2, b2 = _params(D, H, seed=3 * B + D + H, scale=2.0)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, D, generator=g) * 2.0
+    gy = torch.randn(B, D, generator=g)
+    gld = torch.randn(B, generator=g)
+    boundary = 5.0
+    tk = N.T_RQ_FWD if direction == 'forward' else N.T_RQ_INV
+    ours = N.wide_coupling_backward(tk, x.to(dev), gy.to(dev), gld.to(dev), *(t.to(dev) for t in (W1, b1, W2, b2)),
+                                    n_bins=8, boundary=boundary)
+    torch.cuda.synchronize()
+
+    leaves = [t.double().clone().requires_grad_(True) for t in (x, W1, b1, W2, b2)]
+    yo, ldo = _oracle_layer(*leaves, direction, boundary, torch.float64, tf32_operands=True)
+    ((yo * gy.double()).sum() + (ldo * gld.double()).sum()).backward()
+    for name, o, leaf in zip(('gx', 'gW1', 'gb1', 'gW2', 'gb2'), ours, leaves):
+        assert rel(o, leaf.grad) <= 2e-3, f'{name}: ours vs fp64 oracle with TF32 operands {rel(o, leaf.grad):.2e}'
+
+
+def test_wide_preset_runs_on_the_wide_kernels_and_matches_the_oracle_flow():
+    """CouplingRQNSF with a hidden width beyond the whole-flow kernels: every coupling layer reports the wide path, and
+    Flow.log_prob / sample agree with OracleFlow on the same state_dict."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    D = 128
+    flow = Flow(CouplingRQNSF(D, conditioner_kwargs={'n_hidden': 512})).eval()
+    layers = [l for l in flow.bijection.layers if hasattr(l, '_wide')]
+    assert layers and all(l._wide and not l._fusable for l in layers)
+    sd = {k: v.detach().clone() for k, v in flow.state_dict().items()}
+    o = O.OracleFlow('CouplingRQNSF', (D,), {k: v.double() for k, v in sd.items()})
+    x = torch.randn(777, D) * 1.5
+    flow = flow.to(dev)
+    with torch.no_grad():
+        lp = flow.log_prob(x.to(dev)).cpu().double()
+        lp64 = o.log_prob(x.double())
+        assert float(((lp - lp64).abs() / (1 + lp64.abs())).max()) < 1e-4
+        z = torch.randn(300, D)
+        xs = flow._sample_from_base(z.to(dev), no_grad=True).cpu().double()
+        xs64 = o.sample_from_noise(z.double())
+        assert rel(xs, xs64) < 1e-4
+
+
+def test_wide_layer_rejects_unsupported_shapes():
+    from torchflows_b200 import _native as N
+    dev = torch.device('cuda:0')
+    W1, b1, W2, b2 = (t.to(dev) for t in _params(96, 32, seed=0))
+    with pytest.raises(N.B2FError):
+        N.wide_coupling_forward(N.T_RQ_FWD, torch.zeros(8, 96, device=dev), W1, b1, W2, b2)

@@ -39,6 +39,13 @@ class Op(ctypes.Structure):
                 ('p', ctypes.c_void_p * 6), ('g', ctypes.c_void_p * 6)]
 
 
+class WideLayer(ctypes.Structure):
+    """struct b2f_wide_layer (include/b2f.h)."""
+    _fields_ = [('D', ctypes.c_int32), ('H', ctypes.c_int32), ('tkind', ctypes.c_int32), ('n_bins', ctypes.c_int32),
+                ('boundary', ctypes.c_float), ('reserved', ctypes.c_int32), ('W1', ctypes.c_void_p), ('b1', ctypes.c_void_p),
+                ('W2', ctypes.c_void_p), ('b2', ctypes.c_void_p)]
+
+
 _lib = None
 
 
@@ -67,6 +74,10 @@ def lib():
         L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
         L.b2f_debug_umma_gemm.argtypes = [vp, vp, vp, i32, i32, vp]
+        L.b2f_wide_coupling_workspace.argtypes = [i64, i32, i32, i32]
+        L.b2f_wide_coupling_workspace.restype = i64
+        L.b2f_wide_coupling_forward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, i64, vp, i64, vp]
+        L.b2f_wide_coupling_backward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp]
         _lib = L
     return _lib
 
@@ -196,3 +207,64 @@ def debug_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(A.device):
         check(lib().b2f_debug_umma_gemm(ptr(A), ptr(B), ptr(C), B.shape[0], A.shape[1], stream_ptr(A.device)))
     return C
+
+
+# ---- wide-conditioner spline coupling layer (csrc/b2f_wide.cu) -------------------------------------------------------------
+def wide_eligible(D: int, H: int, n_bins: int) -> bool:
+    """Mirror of check_layer in csrc/b2f_wide.cu."""
+    return D >= 64 and D % 64 == 0 and H >= 32 and H % 32 == 0 and n_bins == 8
+
+
+_wide_ws = {}
+
+
+def _wide_workspace(device, B: int, D: int, H: int, backward: bool) -> torch.Tensor:
+    """Scratch of the wide layer kernels, one buffer per device that only grows (the layers of a flow run one after the
+    other on one stream and nothing in it outlives a call)."""
+    need = int(lib().b2f_wide_coupling_workspace(B, D, H, int(backward)))
+    key = (device.type, device.index)
+    buf = _wide_ws.get(key)
+    if buf is None or buf.numel() * 4 < need:
+        _wide_ws[key] = buf = torch.empty((need + 3) // 4, device=device, dtype=torch.float32)
+    return buf
+
+
+def _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2) -> WideLayer:
+    L = WideLayer()
+    L.D, L.H, L.tkind, L.n_bins, L.boundary, L.reserved = D, H, tkind, n_bins, float(boundary), 0
+    L.W1, L.b1, L.W2, L.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()
+    return L
+
+
+def wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins=8, boundary=50.0):
+    """x2: (B, D).  Returns (y, log_det)."""
+    x2 = require_cuda_f32(x2, 'coupling input')
+    W1, b1, W2, b2 = (require_cuda_f32(t, 'conditioner parameter') for t in (W1, b1, W2, b2))
+    B, D = x2.shape
+    H = W1.shape[0]
+    y = torch.empty_like(x2)
+    ld = torch.empty(B, device=x2.device, dtype=torch.float32)
+    with torch.cuda.device(x2.device):
+        ws = _wide_workspace(x2.device, B, D, H, False)
+        layer = _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2)
+        check(lib().b2f_wide_coupling_forward(ctypes.byref(layer), ptr(x2), ptr(y), ptr(ld), B, ptr(ws), ws.numel() * 4,
+                                              stream_ptr(x2.device)))
+    return y, ld
+
+
+def wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins=8, boundary=50.0):
+    """Returns (gx, gW1, gb1, gW2, gb2) given the layer input x2 and upstream gradients (either may be None)."""
+    x2 = require_cuda_f32(x2, 'coupling input')
+    W1, b1, W2, b2 = (require_cuda_f32(t, 'conditioner parameter') for t in (W1, b1, W2, b2))
+    gy = None if gy is None else require_cuda_f32(gy, 'upstream gradient')
+    gld = None if gld is None else require_cuda_f32(gld, 'upstream gradient')
+    B, D = x2.shape
+    H = W1.shape[0]
+    gx = torch.empty_like(x2)
+    gW1, gb1, gW2, gb2 = (torch.empty_like(t) for t in (W1, b1, W2, b2))
+    with torch.cuda.device(x2.device):
+        ws = _wide_workspace(x2.device, B, D, H, True)
+        layer = _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2)
+        check(lib().b2f_wide_coupling_backward(ctypes.byref(layer), ptr(x2), ptr(gy), ptr(gld), ptr(gx), ptr(gW1), ptr(gb1),
+                                               ptr(gW2), ptr(gb2), B, ptr(ws), ws.numel() * 4, stream_ptr(x2.device)))
+    return gx, gW1, gb1, gW2, gb2

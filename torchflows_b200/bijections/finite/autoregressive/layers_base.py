@@ -51,6 +51,26 @@ class _TF32Linear(torch.autograd.Function):
         return gx, gw, gb
 
 
+class _WideCoupling(torch.autograd.Function):
+    """One wide-conditioner spline coupling layer on libb2f's tcgen05 GEMM pipeline (csrc/b2f_wide.cu): conditioner GEMMs,
+    spline and log-det in the forward; recompute, spline backward, dgrad and wgrad GEMMs in the backward.  Only the layer
+    input is kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, x2, W1, b1, W2, b2, tkind, n_bins, boundary):
+        y, ld = N.wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins, boundary)
+        ctx.save_for_backward(x2, W1, b1, W2, b2)
+        ctx.cfg = (tkind, n_bins, boundary)
+        return y, ld
+
+    @staticmethod
+    def backward(ctx, gy, gld):
+        x2, W1, b1, W2, b2 = ctx.saved_tensors
+        tkind, n_bins, boundary = ctx.cfg
+        gx, gW1, gb1, gW2, gb2 = N.wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins, boundary)
+        return gx, gW1, gb1, gW2, gb2, None, None, None
+
+
 def _fits_fused_kernel(n_dim: int, n_hidden: int, kind: int = N.OP_ELEMENTWISE, tkind: int = N.T_AFFINE_FWD,
                        n_bins: int = 0) -> bool:
     """Can a layer of this shape run -- and TRAIN -- inside the fused flow kernels?  Forward: mirror of the shared-memory
@@ -119,6 +139,12 @@ class CouplingBijection(AutoregressiveBijection):
                          and _transformer_fusable(transformer)
                          and _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_COUPLING, transformer._tkind_forward,
                                                 self._spline_args()[0]))
+        # too wide for the whole-flow kernels (e.g. n_dim = 1024, n_hidden = 1024): the layer runs on the tcgen05 GEMM
+        # pipeline of csrc/b2f_wide.cu (spline as the output-layer GEMM's epilogue, h never in memory)
+        self._wide = (not self._fusable and context_shape is None and isinstance(coupling, HalfSplit)
+                      and type(ct) is FeedForward and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
+                      and isinstance(transformer, RationalQuadratic)
+                      and N.wide_eligible(self.n_dim, ct.n_hidden, transformer.n_bins))
 
     # -- reference API ---------------------------------------------------------------------------------------
     def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
@@ -170,8 +196,19 @@ class CouplingBijection(AutoregressiveBijection):
                 a = module(a)
         return a.reshape(*xa.shape[:-1], -1)
 
+    def _run_wide(self, x: torch.Tensor, direction: str):
+        batch_shape = get_batch_shape(x, self.event_shape)
+        xf = flatten_event(x, self.event_shape).reshape(-1, self.n_dim)
+        seq = self.conditioner_transform.sequential
+        n_bins, boundary = self._spline_args()
+        y, log_det = _WideCoupling.apply(xf, seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias,
+                                         self._tkind(direction), n_bins, boundary)
+        return unflatten_event(y.reshape(*batch_shape, self.n_dim), self.event_shape), log_det.reshape(batch_shape)
+
     def _composite(self, x: torch.Tensor, context, direction: str):
         """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""
+        if self._wide and context is None and x.is_cuda and x.dtype == torch.float32:
+            return self._run_wide(x, direction)
         batch_shape = get_batch_shape(x, self.event_shape)
         xf = flatten_event(x, self.event_shape)
         fn = self.transformer.forward if direction == 'forward' else self.transformer.inverse

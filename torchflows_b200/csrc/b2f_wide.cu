@@ -1,0 +1,682 @@
+// Wide-conditioner spline coupling layer (CouplingRQNSF with n_hidden in the hundreds or thousands, e.g. the
+// n_dim = 1024 / n_hidden = 1024 data-parallel training configuration): every dense contraction of the layer -- forward,
+// recompute, dgrad and wgrad -- on tcgen05 (kind::tf32, fp32 accumulation in tensor memory), fed by the TMA engine.
+//
+// Replaces, for one layer (file:line relative to /root/reference/torchflows/bijections/finite/autoregressive):
+//   layers_base.py:119-163            CouplingBijection.forward / inverse
+//   conditioning/transforms.py:274-307   FeedForward: Linear(Dh, H) -> Tanh -> Linear(H, Dh * 23)
+//   transformers/spline/rational_quadratic.py:45-200  the spline applied to the target half, and their autograd backward.
+//
+// The conditioner output h (Dh * 23 floats per sample: 47 KB at Dh = 512) is never written to HBM: the output-layer GEMM
+// keeps a [256 samples x 8 elements x 24] accumulator in tensor memory and the spline (or its backward) is the GEMM's
+// epilogue.  Backward recomputes h the same way; what the backward does write is dL/dh, once, because it feeds two
+// contractions with different reduction axes (over the batch for dL/dW2, over the parameters for dL/dhid) whose
+// accumulators ([12288 x 1024] and [B x 1024] fp32) cannot both stay on chip.
+//
+// Operand format ("tiled", T(R, K)): a [R x K] matrix whose K axis is the contraction axis is stored k-block-major,
+//     offset(r, k) = ((k / 32) * (R / 8) + r / 8) * 256 + ((k % 32) / 4) * 32 + (r % 8) * 4 + k % 4      (floats)
+// so that any run of rows (a multiple of 8) of one 32-wide k-block is ONE contiguous chunk already in the UMMA canonical
+// K-major no-swizzle order (8 x 16-byte core matrices, LBO = 128 B, SBO = 1024 B): one cp.async.bulk per operand per
+// pipeline stage, no tensor map.  Producers (the pack kernel and the GEMM epilogues) write this format directly.
+//
+// One GEMM kernel (wide_gemm_kernel): persistent, 1 CTA / SM, 18 warps = 16 epilogue + MMA issuer + loader.  A work
+// item is a [256 x NT] output block (two M = 128 UMMA tiles sharing every B stage: 32 + NT / 8 KB of operands per 32-wide
+// k-block, the L2 -> SM traffic is what bounds a TF32 GEMM on this part) over a k-block range (split-K for the
+// gradient GEMMs whose output grid is smaller than the machine).  Epilogues: plain store / atomic add (row-major),
+// spline forward / inverse, spline backward.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "b2f_common.cuh"
+#include "b2f_math.cuh"
+#include "b2f_umma.cuh"
+
+namespace b2f {
+namespace wide {
+
+constexpr int kEpiWarps = 16;
+constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kABytes = 256 * 128;        // one k-block of the two M tiles
+constexpr int kTmemCols = 512;
+constexpr int kMaxStages = 4;
+
+enum { EPI_STORE = 0, EPI_SPLINE_FWD, EPI_SPLINE_INV, EPI_SPLINE_BWD_FWD, EPI_SPLINE_BWD_INV };
+
+struct GArgs {
+    const float* A;          // T(RA, K)
+    const float* Bm;         // T(RB, K)
+    int RA8, RB8;            // rows / 8 of the tiled operands
+    int RB;                  // real rows of B (multiple of 16): the last N chunk may be narrower than NT
+    int NT;                  // N chunk: 192 (spline epilogues: 8 elements x 24 columns) or up to 256
+    int n_mt, n_nt, n_split; // items = n_mt * n_nt * n_split (nt fastest, then mt, then the k split)
+    int kb_total;            // K / 32
+    int stages;
+    // EPI_STORE
+    float* C;
+    long long ldc;
+    int M_real, N_real;      // rows / columns actually written
+    int remap24;             // output row m -> (m / 24) * 23 + m % 24, rows with m % 24 == 23 dropped (padded parameter slot)
+    int atomic;              // red.global.add instead of st.global
+    // spline epilogues
+    const float* x;          // layer input (B, D); the target half starts at column Dh
+    float* y;                // layer output (B, D) (target half written here)
+    long long ldx;           // D
+    int Dh;
+    long long B, Bp;
+    const float* b2p;        // output-layer bias padded to 24 per element
+    float boundary;
+    float* ldp;              // [2 * n_nt][Bp] partial log-determinants (natural log)
+    const float* gy;         // backward: dL/dy (B, D) (nullable)
+    const float* gld;        // backward: dL/dlog_det (B) (nullable)
+    float* gx;               // backward: dL/dx (B, D), target half written here
+    float* dhA;              // backward: dL/dh as T(Bp, P)
+    float* dhT;              // backward: dL/dh as T(Pp, Bp)
+    int Pp8;                 // rows / 8 of dhT
+};
+
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__host__ __device__ __forceinline__ size_t tiled_off(long long r, long long k, long long R8) {
+    return (size_t)(((k >> 5) * R8 + (r >> 3)) * 256 + ((k & 31) >> 2) * 32 + (r & 7) * 4 + (k & 3));
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+enum { WB_FULL = 0, WB_EMPTY = kMaxStages, WB_D_FULL = 2 * kMaxStages, WB_D_EMPTY, WB_COUNT };
+
+// ---- epilogues ------------------------------------------------------------------------------------------------------------
+// Thread mapping: warp w owns TMEM lanes 32 (w % 4) .. +31 (hardware rule), i.e. row 32 (w % 4) + lane of M tile
+// t = w / 8, and the column half (w / 4) % 2 of the accumulator [128 x NT] of that tile (columns t * NT .. ).
+
+template <class Release>
+__device__ __forceinline__ void epi_store(const GArgs& G, int mt, int nt, int ncols, uint32_t tbase, int warp, int lane,
+                                          const Release& release) {
+    const int q = warp & 3, t = warp >> 3, half = (warp >> 2) & 1;
+    const int hc = G.NT >> 1;                                // columns per half
+    const long long m = (long long)mt * 256 + t * 128 + q * 32 + lane;
+    long long row = m;
+    bool live = m < G.M_real;
+    if (G.remap24) {
+        const long long e = m / 24;
+        const int i = (int)(m - e * 24);
+        row = e * 23 + i;
+        live = live && i < 23;
+    }
+    float* crow = G.C + row * G.ldc;
+    const uint32_t taddr = tbase + ((uint32_t)(q * 32) << 16) + t * G.NT + half * hc;
+    const int col0 = nt * G.NT + half * hc;
+    const bool vec = (G.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(G.C) & 15) == 0;
+    for (int c = 0; c < hc; c += 16) {
+        float v[16];
+        if (half * hc + c < ncols) {                         // warp-uniform
+            umma::tmem_ld8_nowait<0>(taddr + c, v);
+            umma::tmem_ld8_nowait<8>(taddr + c + 8, v);
+            umma::tmem_ld_wait();
+        }
+        if (c + 16 >= hc) release();
+        if (half * hc + c >= ncols || !live) continue;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const int col = col0 + c + j;
+            if (vec && col + 3 < G.N_real && half * hc + c + j + 3 < ncols) {
+                if (G.atomic) red_add_v4(crow + col, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                else *reinterpret_cast<float4*>(crow + col) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (col + u < G.N_real && half * hc + c + j + u < ncols) {
+                        if (G.atomic) atomicAdd(crow + col + u, v[j + u]);
+                        else crow[col + u] = v[j + u];
+                    }
+            }
+        }
+    }
+}
+
+template <int EPI, class Release>
+__device__ __forceinline__ void epi_spline(const GArgs& G, int mt, int nt, uint32_t tbase, int warp, int lane,
+                                           const Release& release) {
+    constexpr bool BWD = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
+    constexpr bool INV = EPI == EPI_SPLINE_INV || EPI == EPI_SPLINE_BWD_INV;
+    const int q = warp & 3, t = warp >> 3, half = (warp >> 2) & 1;
+    const long long row = (long long)mt * 256 + t * 128 + q * 32 + lane;
+    const bool live = row < G.B;
+    const uint32_t taddr = tbase + ((uint32_t)(q * 32) << 16) + t * 192 + half * 96;
+    const int e0 = nt * 8 + half * 4;                        // first of this thread's 4 elements of the target half
+    const float* xrow = G.x + row * G.ldx + G.Dh;
+    float ldacc = 0.0f;
+    float GL = 0.0f;
+    if (BWD) GL = (live && G.gld) ? __ldg(G.gld + row) : 0.0f;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        float p[24];
+        umma::tmem_ld8_nowait<0>(taddr + j * 24, p);
+        umma::tmem_ld8_nowait<8>(taddr + j * 24 + 8, p);
+        umma::tmem_ld8_nowait<16>(taddr + j * 24 + 16, p);
+        umma::tmem_ld_wait();
+        if (j == 3) release();
+        const int e = e0 + j;
+        const float4* bp = reinterpret_cast<const float4*>(G.b2p + (size_t)e * 24);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            const float4 bv = __ldg(bp + c);
+            p[4 * c] += bv.x; p[4 * c + 1] += bv.y; p[4 * c + 2] += bv.z; p[4 * c + 3] += bv.w;
+        }
+        const float v = live ? __ldg(xrow + e) : 0.0f;
+        auto h = [&](int i) { return p[i]; };
+        if constexpr (!BWD) {
+            float out, ld;
+            int k;
+            rq_apply<8, INV, 1>(v, h, 8, G.boundary, out, ld, k);
+            if (live) G.y[row * G.ldx + G.Dh + e] = out;
+            ldacc += ld;
+        } else {
+            const float GZ = (live && G.gy) ? __ldg(G.gy + row * G.ldx + G.Dh + e) : 0.0f;
+            float dp[24];
+            dp[23] = 0.0f;
+            auto g = [&](int i, float val) { dp[i] = val; };
+            float dv;
+            if constexpr (INV) rq_backward_inv<8, 1>(v, h, 8, G.boundary, GZ, GL, dv, g);
+            else rq_backward_fwd<8, 1>(v, h, 8, G.boundary, GZ, GL, dv, g);
+            if (live) G.gx[row * G.ldx + G.Dh + e] = dv;
+#pragma unroll
+            for (int i = 0; i < 24; ++i) dp[i] = live ? tf32_rn(dp[i]) : 0.0f;
+            // dL/dh in both operand orientations: (row, k = parameter) and (parameter, k = row)
+            const long long n0 = (long long)e * 24;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+                *reinterpret_cast<float4*>(G.dhA + tiled_off(row, n0 + 4 * c, G.Bp >> 3)) =
+                    make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
+#pragma unroll
+            for (int i = 0; i < 24; ++i) G.dhT[tiled_off(n0 + i, row, G.Pp8)] = dp[i];
+        }
+    }
+    if constexpr (!BWD) G.ldp[(size_t)(nt * 2 + half) * G.Bp + row] = ldacc;
+}
+
+// ---- the GEMM kernel -------------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1) wide_gemm_kernel(const __grid_constant__ GArgs G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int stage_bytes = kABytes + G.NT * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)G.stages * stage_bytes);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + WB_COUNT);
+
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            umma::mbar_init(&bars[WB_FULL + i], 1);
+            umma::mbar_init(&bars[WB_EMPTY + i], 1);
+        }
+        umma::mbar_init(&bars[WB_D_FULL], 1);
+        umma::mbar_init(&bars[WB_D_EMPTY], kEpiWarps);
+        umma::fence_barrier_init();
+    }
+    if (warp == kEpiWarps) umma::tmem_alloc(tmem_ptr, kTmemCols);
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    umma::tc_fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+
+    const int n_items = G.n_mt * G.n_nt * G.n_split;
+    const int kb_per = (G.kb_total + G.n_split - 1) / G.n_split;
+    auto decode = [&](int item, int& mt, int& nt, int& kb0, int& kb1) {
+        nt = item % G.n_nt;
+        const int r = item / G.n_nt;
+        mt = r % G.n_mt;
+        const int sp = r / G.n_mt;
+        kb0 = sp * kb_per;
+        kb1 = min(G.kb_total, kb0 + kb_per);
+    };
+
+    if (warp == kEpiWarps + 1) {
+        // ===================== loader: two bulk copies per stage =====================
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int mt, nt, kb0, kb1;
+                decode(item, mt, nt, kb0, kb1);
+                const int ncols = min(G.NT, G.RB - nt * G.NT);
+                const uint32_t b_bytes = (uint32_t)ncols * 128;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    umma::mbar_wait(&bars[WB_EMPTY + st], ph ^ 1);
+                    uint8_t* sa = smem_raw + (size_t)st * stage_bytes;
+                    umma::mbar_arrive_expect_tx(&bars[WB_FULL + st], kABytes + b_bytes);
+                    umma::bulk_g2s(sa, G.A + ((size_t)kb * G.RA8 + (size_t)mt * 32) * 256, kABytes, &bars[WB_FULL + st]);
+                    umma::bulk_g2s(sa + kABytes, G.Bm + ((size_t)kb * G.RB8 + (size_t)nt * (G.NT >> 3)) * 256, b_bytes,
+                                   &bars[WB_FULL + st]);
+                    if (++st == (uint32_t)G.stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kEpiWarps) {
+        // ===================== MMA issuer =====================
+        const uint32_t leader = umma::elect_one();
+        const uint64_t dc = umma::make_smem_desc(0, 128, 1024);
+        const uint32_t d_lo = (uint32_t)dc, d_hi = (uint32_t)(dc >> 32);
+        const uint32_t s0 = umma::smem_u32(smem_raw) >> 4;
+        uint32_t st = 0, ph = 0, it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            int mt, nt, kb0, kb1;
+            decode(item, mt, nt, kb0, kb1);
+            const int ncols = min(G.NT, G.RB - nt * G.NT);
+            const uint32_t idesc = umma::make_idesc_tf32(128, ncols);
+            umma::mbar_wait(&bars[WB_D_EMPTY], (it & 1) ^ 1);          // the epilogue has drained the accumulators
+            umma::tc_fence_after_sync();
+            for (int kb = kb0; kb < kb1; ++kb) {
+                umma::mbar_wait(&bars[WB_FULL + st], ph);
+                umma::tc_fence_after_sync();
+                if (leader) {
+                    const uint32_t a_lo = d_lo + s0 + st * (stage_bytes >> 4);
+                    const uint32_t b_lo = a_lo + (kABytes >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t acc = (kb > kb0 || ks > 0) ? 1u : 0u;
+                        umma::mma_tf32_ss_parts(tbase, a_lo + ks * 16, d_hi, b_lo + ks * 16, d_hi, idesc, acc);
+                        umma::mma_tf32_ss_parts(tbase + G.NT, a_lo + (128 * 128 >> 4) + ks * 16, d_hi, b_lo + ks * 16, d_hi, idesc, acc);
+                    }
+                    umma::mma_commit(&bars[WB_EMPTY + st]);
+                    if (kb == kb1 - 1) umma::mma_commit(&bars[WB_D_FULL]);
+                }
+                __syncwarp();
+                if (++st == (uint32_t)G.stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            int mt, nt, kb0, kb1;
+            decode(item, mt, nt, kb0, kb1);
+            const int ncols = min(G.NT, G.RB - nt * G.NT);
+            umma::mbar_wait_backoff(&bars[WB_D_FULL], it & 1);
+            umma::tc_fence_after_sync();
+            auto release = [&]() {
+                umma::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bars[WB_D_EMPTY]);
+            };
+            if constexpr (EPI == EPI_STORE) epi_store(G, mt, nt, ncols, tbase, warp, lane, release);
+            else epi_spline<EPI>(G, mt, nt, tbase, warp, lane, release);
+        }
+    }
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kEpiWarps) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+// ---- pack kernel: row-major -> tiled operands -------------------------------------------------------------------------------
+enum { PACK_COPY = 0, PACK_TANH_BIAS = 1, PACK_DTANH = 2 };
+
+struct PArgs {
+    const float* src;        // [R x C] row-major, row stride ld (rows >= R / columns >= C read as zero)
+    long long ld;
+    long long R, C;
+    int remap24;             // source row of logical row n: (n / 24) * 23 + n % 24, zero when n % 24 == 23
+    int op;
+    const float* bias;       // TANH_BIAS / DTANH: per column
+    const float* aux;        // DTANH: pre-activations [R x C] row-major (row stride ld_aux); value = src * (1 - tanh(aux + bias)^2)
+    long long ld_aux;
+    float* outA;             // T(A_rows, A_k): rows = R axis, k = C axis (nullable); pads are written as zeros
+    long long RA8, A_rows, A_k;
+    float* outT;             // T(T_rows, T_k): rows = C axis, k = R axis (nullable)
+    long long RT8, T_rows, T_k;
+    float* colsum;           // DTANH: per-column sums of the result, atomically added (nullable)
+};
+
+// one 32 x 32 patch per block (256 threads): both output formats store a patch as 1024 contiguous floats
+__global__ void __launch_bounds__(256) pack_kernel(const PArgs P) {
+    __shared__ float s[32][33];
+    const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rr = ty + 8 * i;
+        const long long r = r0 + rr, c = c0 + tx;
+        float v = 0.0f;
+        if (r < P.R && c < P.C) {
+            long long sr = r;
+            bool ok = true;
+            if (P.remap24) {
+                const long long e = r / 24;
+                const int k = (int)(r - e * 24);
+                sr = e * 23 + k;
+                ok = k < 23;
+            }
+            if (ok) {
+                v = __ldg(P.src + sr * P.ld + c);
+                if (P.op == PACK_TANH_BIAS) v = tanhf(v + __ldg(P.bias + c));
+                else if (P.op == PACK_DTANH) {
+                    const float th = tanhf(__ldg(P.aux + sr * P.ld_aux + c) + __ldg(P.bias + c));
+                    v *= fmaf(-th, th, 1.0f);
+                }
+            }
+        }
+        s[rr][tx] = v;
+    }
+    __syncthreads();
+    if (P.colsum && threadIdx.x < 32) {
+        float a = 0.0f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) a += s[i][threadIdx.x];
+        if (c0 + threadIdx.x < P.C) atomicAdd(P.colsum + c0 + threadIdx.x, a);
+    }
+    const int i = threadIdx.x;                 // float4 slot of the patch: [8-group (4)][k4 (8)][row in group (8)]
+    const int g = i >> 6, k4 = (i >> 3) & 7, r8 = i & 7;
+    if (P.outA && r0 < P.A_rows && c0 < P.A_k) {
+        const int rr = g * 8 + r8;
+        float4 v = make_float4(tf32_rn(s[rr][4 * k4]), tf32_rn(s[rr][4 * k4 + 1]), tf32_rn(s[rr][4 * k4 + 2]), tf32_rn(s[rr][4 * k4 + 3]));
+        *reinterpret_cast<float4*>(P.outA + tiled_off(r0 + rr, c0 + 4 * k4, P.RA8)) = v;
+    }
+    if (P.outT && c0 < P.T_rows && r0 < P.T_k) {
+        const int cc = g * 8 + r8;
+        float4 v = make_float4(tf32_rn(s[4 * k4][cc]), tf32_rn(s[4 * k4 + 1][cc]), tf32_rn(s[4 * k4 + 2][cc]), tf32_rn(s[4 * k4 + 3][cc]));
+        *reinterpret_cast<float4*>(P.outT + tiled_off(c0 + cc, r0 + 4 * k4, P.RT8)) = v;
+    }
+}
+
+// per-row sums of a tiled matrix T(R, K) over k < K: out[(n / 24) * 23 + n % 24] for rows n < n_rows with n % 24 < 23
+// (dL/db2 = sum over the batch of dL/dh).  One block per 8-row group.
+__global__ void __launch_bounds__(256) rowsum_tiled_kernel(const float* __restrict__ T, long long R8, long long kb_total,
+                                                           long long n_rows, float* __restrict__ out) {
+    __shared__ float s[256];
+    const long long rg = blockIdx.x;
+    const int i = threadIdx.x;                 // [k4 (8)][row in group (8)][k % 4 (4)]
+    float a = 0.0f;
+    for (long long kb = 0; kb < kb_total; ++kb) a += __ldg(T + (kb * R8 + rg) * 256 + i);
+    s[i] = a;
+    __syncthreads();
+    if (i < 8) {
+        float t = 0.0f;
+        for (int k4 = 0; k4 < 8; ++k4)
+            for (int u = 0; u < 4; ++u) t += s[k4 * 32 + i * 4 + u];
+        const long long n = rg * 8 + i;
+        const long long e = n / 24;
+        const int k = (int)(n - e * 24);
+        if (n < n_rows && k < 23) out[e * 23 + k] = t;
+    }
+}
+
+// bias padded to 24 per element
+__global__ void pad_bias_kernel(const float* __restrict__ b2, float* __restrict__ b2p, int Dh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Dh * 24) {
+        const int e = i / 24, k = i % 24;
+        b2p[i] = k < 23 ? b2[e * 23 + k] : 0.0f;
+    }
+}
+
+// source half passes through (dst[:, :Dh] = src[:, :Dh]); optionally log_det[r] = sum of the partials
+__global__ void finish_kernel(const float* __restrict__ src, float* __restrict__ dst, long long B, int D, int Dh,
+                              const float* __restrict__ ldp, int n_part, long long Bp, float* __restrict__ log_det) {
+    const long long n4 = B * (Dh / 4);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const long long r = i / (Dh / 4);
+        const int c = (int)(i - r * (Dh / 4)) * 4;
+        if (dst && dst != src)
+            *reinterpret_cast<float4*>(dst + r * D + c) =
+                src ? __ldg(reinterpret_cast<const float4*>(src + r * D + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (log_det) {
+        for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < B; r += stride) {
+            float a = 0.0f;
+            for (int p = 0; p < n_part; ++p) a += ldp[(size_t)p * Bp + r];
+            log_det[r] = a;
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------------
+static inline long long up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+struct Shapes {
+    long long B, Bp;
+    int D, Dh, H, P, Pp, Hp, Dhp;
+};
+
+static Shapes shapes(long long B, int D, int H) {
+    Shapes s;
+    s.B = B; s.Bp = up(std::max<long long>(B, 1), 256);
+    s.D = D; s.Dh = D / 2; s.H = H;
+    s.P = s.Dh * 24; s.Pp = (int)up(s.P, 256); s.Hp = (int)up(H, 256); s.Dhp = (int)up(s.Dh, 256);
+    return s;
+}
+
+struct Workspace {           // offsets in floats
+    size_t xaA, xaT, W1t, W1T, W2p, W2pT, b2p, pre, hidA, hidT, ldp, dhA, dhT, dhid, dpreA, dpreT, total;
+};
+
+static Workspace layout(const Shapes& s, bool backward) {
+    Workspace w;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t at = o; o += (n + 63) / 64 * 64; return at; };
+    w.xaA = take((size_t)s.Bp * s.Dh);
+    w.W1t = take((size_t)s.Hp * s.Dh);
+    w.W2p = take((size_t)s.Pp * s.H);
+    w.b2p = take((size_t)s.P);
+    w.pre = take((size_t)s.Bp * s.H);
+    w.hidA = take((size_t)s.Bp * s.H);
+    w.ldp = take((size_t)(s.P / 192) * 2 * s.Bp);
+    w.xaT = w.W1T = w.W2pT = w.hidT = w.dhA = w.dhT = w.dhid = w.dpreA = w.dpreT = 0;
+    if (backward) {
+        w.xaT = take((size_t)s.Dhp * s.Bp);
+        w.W1T = take((size_t)s.Dhp * s.H);
+        w.W2pT = take((size_t)s.Hp * s.P);
+        w.hidT = take((size_t)s.Hp * s.Bp);
+        w.dhA = take((size_t)s.Bp * s.P);
+        w.dhT = take((size_t)s.Pp * s.Bp);
+        w.dhid = take((size_t)s.Bp * s.H);
+        w.dpreA = take((size_t)s.Bp * s.H);
+        w.dpreT = take((size_t)s.Hp * s.Bp);
+    }
+    w.total = o;
+    return w;
+}
+
+static int n_sm() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+// src [R x C] -> outA = T(A_rows, up(C, 32)) and / or outT = T(T_rows, T_k) (the transpose: k runs over the R axis)
+static int pack(cudaStream_t st, const float* src, long long ld, long long R, long long C, int remap24, int op,
+                const float* bias, const float* aux, long long ld_aux, float* outA, long long A_rows, float* outT,
+                long long T_rows, long long T_k, float* colsum) {
+    PArgs P;
+    P.src = src; P.ld = ld; P.R = R; P.C = C; P.remap24 = remap24; P.op = op; P.bias = bias; P.aux = aux; P.ld_aux = ld_aux;
+    P.outA = outA; P.RA8 = A_rows / 8; P.A_rows = A_rows; P.A_k = up(C, 32);
+    P.outT = outT; P.RT8 = T_rows / 8; P.T_rows = T_rows; P.T_k = T_k; P.colsum = colsum;
+    const long long Rgrid = std::max(outA ? A_rows : 0, outT ? T_k : 0), Cgrid = std::max(outA ? P.A_k : 0, outT ? T_rows : 0);
+    dim3 grid((unsigned)(Cgrid / 32), (unsigned)(Rgrid / 32));
+    pack_kernel<<<grid, 256, 0, st>>>(P);
+    return check_launch("b2f_wide (pack)");
+}
+
+template <int EPI>
+static int launch_gemm(cudaStream_t st, GArgs& G, const char* what) {
+    G.stages = std::min(kMaxStages, (int)((227 * 1024 - 256) / (kABytes + G.NT * 128)));
+    const size_t smem = (size_t)G.stages * (kABytes + G.NT * 128) + WB_COUNT * 8 + 16;
+    const int items = G.n_mt * G.n_nt * G.n_split;
+    if (items <= 0) return B2F_OK;
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)wide_gemm_kernel<EPI>, smem);
+    if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute(wide gemm): %s", cudaGetErrorString(ce));
+    wide_gemm_kernel<EPI><<<std::min(items, n_sm()), kThreads, smem, st>>>(G);
+    return check_launch(what);
+}
+
+// plain GEMM C[M x N] (+)= A[T(RAp, K)] * B[T(RBp, K)]^T
+static int gemm_store(cudaStream_t st, const float* A, long long RAp, const float* Bm, long long RBp, int RB, long long K,
+                      float* C, long long ldc, long long M_real, int N_real, int remap24, int atomic, int n_split, int NT) {
+    GArgs G;
+    memset(&G, 0, sizeof(G));
+    G.A = A; G.Bm = Bm; G.RA8 = (int)(RAp / 8); G.RB8 = (int)(RBp / 8); G.RB = RB; G.NT = NT;
+    G.n_mt = (int)(RAp / 256); G.n_nt = (RB + NT - 1) / NT; G.kb_total = (int)(K / 32);
+    G.n_split = std::max(1, std::min(n_split, G.kb_total));
+    // every split must own at least one k-block (an empty item would never signal its accumulator)
+    const int kb_per = (G.kb_total + G.n_split - 1) / G.n_split;
+    G.n_split = (G.kb_total + kb_per - 1) / kb_per;
+    G.C = C; G.ldc = ldc; G.M_real = (int)M_real; G.N_real = N_real; G.remap24 = remap24; G.atomic = atomic;
+    return launch_gemm<EPI_STORE>(st, G, "b2f_wide (gemm)");
+}
+
+// split factor that brings the item count close to a whole number of waves
+static int pick_split(int items, int kb_total) {
+    const int sms = n_sm();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 8 && s <= kb_total; ++s) {
+        const int n = items * s;
+        const double eff = (double)n / ((double)((n + sms - 1) / sms) * sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+static int check_layer(const b2f_wide_layer_t* L, long long B) {
+    if (!L || !L->W1 || !L->b1 || !L->W2 || !L->b2) return fail(B2F_ERR_INVALID, "wide coupling: null layer / parameter");
+    if (L->tkind != B2F_T_RQ_FWD && L->tkind != B2F_T_RQ_INV) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: spline transformers only");
+    if (L->n_bins != 8) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_bins must be 8");
+    if (L->D < 64 || L->D % 64 != 0) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_dim must be a multiple of 64");
+    if (L->H < 32 || L->H % 32 != 0) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_hidden must be a multiple of 32");
+    if (!(L->boundary > 0.0f)) return fail(B2F_ERR_INVALID, "wide coupling: boundary");
+    if (B < 0 || B > (1LL << 30)) return fail(B2F_ERR_INVALID, "wide coupling: batch size");
+    return B2F_OK;
+}
+
+// conditioner up to the hidden activations: xaA (and xaT), W1t, pre = xa W1^T, hidA (and hidT) = tanh(pre + b1)
+static int hidden_layer(cudaStream_t st, const b2f_wide_layer_t* L, const Shapes& s, const Workspace& w, float* ws, const float* x,
+                        bool backward) {
+    int rc;
+    if ((rc = pack(st, x, s.D, s.B, s.Dh, 0, PACK_COPY, nullptr, nullptr, 0, ws + w.xaA, s.Bp, backward ? ws + w.xaT : nullptr,
+                   s.Dhp, s.Bp, nullptr)) != B2F_OK) return rc;
+    if ((rc = pack(st, L->W1, s.Dh, s.H, s.Dh, 0, PACK_COPY, nullptr, nullptr, 0, ws + w.W1t, s.Hp, backward ? ws + w.W1T : nullptr,
+                   s.Dhp, s.H, nullptr)) != B2F_OK) return rc;
+    if ((rc = gemm_store(st, ws + w.xaA, s.Bp, ws + w.W1t, s.Hp, s.H, s.Dh, ws + w.pre, s.H, s.Bp, s.H, 0, 0, 1, 256)) != B2F_OK) return rc;
+    return pack(st, ws + w.pre, s.H, s.B, s.H, 0, PACK_TANH_BIAS, L->b1, nullptr, 0, ws + w.hidA, s.Bp, backward ? ws + w.hidT : nullptr,
+                s.Hp, s.Bp, nullptr);
+}
+
+static void spline_gemm_args(GArgs& G, const b2f_wide_layer_t* L, const Shapes& s, const Workspace& w, float* ws, const float* x) {
+    memset(&G, 0, sizeof(G));
+    G.A = ws + w.hidA; G.Bm = ws + w.W2p; G.RA8 = (int)(s.Bp / 8); G.RB8 = s.Pp / 8; G.RB = s.P; G.NT = 192;
+    G.n_mt = (int)(s.Bp / 256); G.n_nt = s.P / 192; G.n_split = 1; G.kb_total = s.H / 32;
+    G.x = x; G.ldx = s.D; G.Dh = s.Dh; G.B = s.B; G.Bp = s.Bp; G.b2p = ws + w.b2p; G.boundary = L->boundary;
+}
+
+}  // namespace wide
+}  // namespace b2f
+
+using namespace b2f;
+using namespace b2f::wide;
+
+extern "C" int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t backward) {
+    if (B < 0 || D < 2 || H < 1) return 0;
+    return (int64_t)(layout(shapes(B, D, H), backward != 0).total * sizeof(float));
+}
+
+extern "C" int b2f_wide_coupling_forward(const b2f_wide_layer_t* L, const float* x, float* y, float* log_det, int64_t B,
+                                         void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_layer(L, B);
+    if (rc != B2F_OK) return rc;
+    if (B == 0) return B2F_OK;
+    if (!x || !y || !workspace) return fail(B2F_ERR_INVALID, "wide coupling: null buffer");
+    const Shapes s = shapes(B, L->D, L->H);
+    const Workspace w = layout(s, false);
+    if ((size_t)workspace_bytes < w.total * sizeof(float)) return fail(B2F_ERR_INVALID, "wide coupling: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+        return fail(B2F_ERR_INVALID, "wide coupling: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace;
+    if ((rc = hidden_layer(st, L, s, w, ws, x, false)) != B2F_OK) return rc;
+    if ((rc = pack(st, L->W2, s.H, s.P, s.H, 1, PACK_COPY, nullptr, nullptr, 0, ws + w.W2p, s.Pp, nullptr, 0, 0, nullptr)) != B2F_OK) return rc;
+    pad_bias_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(L->b2, ws + w.b2p, s.Dh);
+    if ((rc = check_launch("b2f_wide (bias)")) != B2F_OK) return rc;
+    GArgs G;
+    spline_gemm_args(G, L, s, w, ws, x);
+    G.y = y; G.ldp = ws + w.ldp;
+    rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
+                                  : launch_gemm<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
+    if (rc != B2F_OK) return rc;
+    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(x, y, B, s.D, s.Dh, ws + w.ldp, 2 * G.n_nt, s.Bp, log_det);
+    return check_launch("b2f_wide (finish)");
+}
+
+extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float* x, const float* gy, const float* glog_det,
+                                          float* gx, float* gW1, float* gb1, float* gW2, float* gb2, int64_t B, void* workspace,
+                                          int64_t workspace_bytes, void* stream) {
+    int rc = check_layer(L, B);
+    if (rc != B2F_OK) return rc;
+    if (!x || !gx || !gW1 || !gb1 || !gW2 || !gb2 || !workspace) return fail(B2F_ERR_INVALID, "wide coupling backward: null buffer");
+    const Shapes s = shapes(B, L->D, L->H);
+    const Workspace w = layout(s, true);
+    if ((size_t)workspace_bytes < w.total * sizeof(float)) return fail(B2F_ERR_INVALID, "wide coupling backward: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace;
+    const size_t P23 = (size_t)s.Dh * 23;
+    cudaMemsetAsync(gW1, 0, (size_t)s.H * s.Dh * 4, st);
+    cudaMemsetAsync(gb1, 0, (size_t)s.H * 4, st);
+    cudaMemsetAsync(gW2, 0, P23 * s.H * 4, st);
+    cudaMemsetAsync(gb2, 0, P23 * 4, st);
+    if (B == 0) return check_launch("b2f_wide_coupling_backward");
+    cudaMemsetAsync(ws + w.dhid, 0, (size_t)s.Bp * s.H * 4, st);
+    // rows beyond P of dhT (P is a multiple of 768, so there are none unless Pp > P) and the T-form pads stay zero
+    if (s.Pp > s.P) cudaMemsetAsync(ws + w.dhT, 0, (size_t)s.Pp * s.Bp * 4, st);
+    if ((rc = hidden_layer(st, L, s, w, ws, x, true)) != B2F_OK) return rc;
+    // output-layer weights in both orientations: T(Pp, H) for the recompute, T(Hp, P) for dL/dhid
+    if ((rc = pack(st, L->W2, s.H, s.P, s.H, 1, PACK_COPY, nullptr, nullptr, 0, ws + w.W2p, s.Pp, ws + w.W2pT, s.Hp, s.P, nullptr)) != B2F_OK) return rc;
+    pad_bias_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(L->b2, ws + w.b2p, s.Dh);
+    if ((rc = check_launch("b2f_wide (bias)")) != B2F_OK) return rc;
+    // recompute h tile by tile, spline backward in the epilogue: gx (target half), dL/dh in both orientations
+    GArgs G;
+    spline_gemm_args(G, L, s, w, ws, x);
+    G.gy = gy; G.gld = glog_det; G.gx = gx; G.dhA = ws + w.dhA; G.dhT = ws + w.dhT; G.Pp8 = s.Pp / 8;
+    rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_BWD_INV>(st, G, "b2f_wide_coupling_backward (spline)")
+                                  : launch_gemm<EPI_SPLINE_BWD_FWD>(st, G, "b2f_wide_coupling_backward (spline)");
+    if (rc != B2F_OK) return rc;
+    rowsum_tiled_kernel<<<s.Pp / 8, 256, 0, st>>>(ws + w.dhT, s.Pp / 8, s.Bp / 32, s.P, gb2);
+    if ((rc = check_launch("b2f_wide (bias gradient)")) != B2F_OK) return rc;
+    // dL/dW2[n, j] = sum_b dh[b, n] hid[b, j]
+    {
+        const int items = (s.Pp / 256) * ((s.H + 255) / 256);
+        if ((rc = gemm_store(st, ws + w.dhT, s.Pp, ws + w.hidT, s.Hp, s.H, s.Bp, gW2, s.H, s.P, s.H, 1, 1,
+                             pick_split(items, (int)(s.Bp / 32)), 256)) != B2F_OK) return rc;
+    }
+    // dL/dhid[b, j] = sum_n dh[b, n] W2[n, j]
+    {
+        const int items = (int)(s.Bp / 256) * ((s.H + 255) / 256);
+        if ((rc = gemm_store(st, ws + w.dhA, s.Bp, ws + w.W2pT, s.Hp, s.H, s.P, ws + w.dhid, s.H, s.Bp, s.H, 0, 1,
+                             pick_split(items, s.P / 32), 256)) != B2F_OK) return rc;
+    }
+    // through the tanh: dpre = dhid (1 - hid^2) in both orientations, dL/db1 = column sums
+    if ((rc = pack(st, ws + w.dhid, s.H, s.B, s.H, 0, PACK_DTANH, L->b1, ws + w.pre, s.H, ws + w.dpreA, s.Bp, ws + w.dpreT, s.Hp,
+                   s.Bp, gb1)) != B2F_OK) return rc;
+    // dL/dW1[j, i] = sum_b dpre[b, j] xa[b, i]
+    {
+        const int items = (s.Hp / 256) * ((s.Dh + 255) / 256);
+        if ((rc = gemm_store(st, ws + w.dpreT, s.Hp, ws + w.xaT, s.Dhp, s.Dh, s.Bp, gW1, s.Dh, s.H, s.Dh, 0, 1,
+                             pick_split(items, (int)(s.Bp / 32)), 256)) != B2F_OK) return rc;
+    }
+    // dL/dxa = gy[:, :Dh] + dpre W1
+    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(gy, gx, B, s.D, s.Dh, nullptr, 0, s.Bp, nullptr);
+    if ((rc = check_launch("b2f_wide (finish)")) != B2F_OK) return rc;
+    {
+        const int items = (int)(s.Bp / 256) * ((s.Dh + 255) / 256);
+        if ((rc = gemm_store(st, ws + w.dpreA, s.Bp, ws + w.W1T, s.Dhp, s.Dh, s.H, gx, s.D, s.B, s.Dh, 0, 1,
+                             pick_split(items, s.H / 32), 256)) != B2F_OK) return rc;
+    }
+    return B2F_OK;
+}
