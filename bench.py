@@ -471,6 +471,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def fit_path(flow):
+    """Which kernels a Flow.fit step of this flow runs on, read off the layers' own dispatch flags."""
+    layers = [l for l in flow.bijection.layers if hasattr(l, '_fusable') and hasattr(l, 'coupling')]
+    if layers and all(getattr(l, '_wide', False) for l in layers):
+        return 'fused (b2f_wide_coupling_forward / _backward: tcgen05 TF32 GEMM pipeline, spline in the GEMM epilogue)'
+    if layers and all(l._fusable for l in layers):
+        return 'fused (b2f_flow_apply_saving + b2f_flow_backward)'
+    return 'composite (library GEMMs for the conditioner, b2f transformer kernels)'
+
+
 def fit_probe(torch, dist, dev, rank, world, workload, steps=5, warmup=3, rows=0):
     """ms per optimisation step of Flow.fit's inner loop (Flow.train_step: forward, backward, gradient exchange, AdamW) on
     this rank's GPU, data-parallel over the visible ranks, plus the gradient all-reduce on its own (the same buckets, no
@@ -522,8 +532,7 @@ def fit_probe(torch, dist, dev, rank, world, workload, steps=5, warmup=3, rows=0
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step, ms_ar = float(ms[0]), float(ms[1])
-    path = 'composite (library GEMMs for the conditioner, b2f transformer kernels)' if D > 512 else \
-        'fused (b2f_flow_apply_saving + b2f_flow_backward)'
+    path = fit_path(flow)
     out = {'workload': f'CouplingRQNSF n_dim={D} n_hidden={H}, {per_gpu} rows per GPU', 'ms_per_step': ms_step,
            'samples_per_s': world * per_gpu / (ms_step * 1e-3), 'trainable_parameters': n_params, 'path': path,
            'allreduce_bytes_per_step': nbytes, 'allreduce_alone_ms': ms_ar, 'final_loss': float(loss)}
@@ -585,8 +594,7 @@ def run_fit(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'CouplingRQNSF n_dim={D} n_hidden={H}: Flow.fit step (fwd + bwd + all-reduce + AdamW), '
                                    f'{per_gpu} rows per GPU', 'trainable_parameters': n_params,
-                       'path': 'composite (library GEMMs for the conditioner, b2f transformer kernels)' if D > 512
-                       else 'fused (b2f_flow_apply + b2f_flow_backward)'},
+                       'path': fit_path(flow)},
             'final_loss': float(loss)}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,19 +178,24 @@ typedef struct b2f_wide_layer {
     const float *W1, *b1, *W2, *b2;
 } b2f_wide_layer_t;
 
-/* Scratch bytes b2f_wide_coupling_forward (backward = 0) / b2f_wide_coupling_backward (backward = 1) need for B rows. */
-int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t backward);
+/* Two caller-owned buffers.  `keep`: packed operands and hidden activations of one layer call -- what the backward of the
+ * same step can reuse; `scratch`: temporaries of one call (may be shared by all layers of a flow).
+ * which = 0: keep bytes, forward only; 1: keep bytes when a backward follows; 2: scratch bytes of the forward; 3: of the backward. */
+int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t which);
 
-/* y:(B,D) = layer(x:(B,D)), log_det:(B) (nullable).  Nothing is kept for the backward except what the caller already
- * has (x): b2f_wide_coupling_backward recomputes the hidden activations and h. */
-int b2f_wide_coupling_forward(const b2f_wide_layer_t *layer, const float *x, float *y, float *log_det, int64_t B,
-                              void *workspace, int64_t workspace_bytes, void *stream);
+#define B2F_WIDE_FOR_BACKWARD 1 /* forward flag: also lay out the operands the backward needs (keep sized with which = 1) */
+#define B2F_WIDE_KEPT 2         /* backward flag: `keep` still holds what the forward (with B2F_WIDE_FOR_BACKWARD, same x, same
+                                   parameters) left there; without it the backward rebuilds it from x and the parameters */
+
+/* y:(B,D) = layer(x:(B,D)), log_det:(B) (nullable).  The conditioner output is never stored; the backward recomputes it. */
+int b2f_wide_coupling_forward(const b2f_wide_layer_t *layer, const float *x, float *y, float *log_det, int64_t B, void *keep,
+                              int64_t keep_bytes, void *scratch, int64_t scratch_bytes, int32_t flags, void *stream);
 
 /* Given the layer INPUT x and upstream gy:(B,D) (nullable), glog_det:(B) (nullable): gx:(B,D) and the parameter gradients
  * gW1, gb1, gW2, gb2 (reference layouts; overwritten, not accumulated).  Replaces autograd through the reference code above. */
 int b2f_wide_coupling_backward(const b2f_wide_layer_t *layer, const float *x, const float *gy, const float *glog_det,
-                               float *gx, float *gW1, float *gb1, float *gW2, float *gb2, int64_t B, void *workspace,
-                               int64_t workspace_bytes, void *stream);
+                               float *gx, float *gW1, float *gb1, float *gW2, float *gb2, int64_t B, void *keep,
+                               int64_t keep_bytes, void *scratch, int64_t scratch_bytes, int32_t flags, void *stream);
 
 /* Per-dimension batch statistics for ActNorm's data-dependent initialisation (layers.py:58-68):
  * sum:(D) and sumsq:(D) of x:(B,D), accumulated in fp64 (must be zeroed by the caller). */

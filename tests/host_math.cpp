@@ -76,6 +76,17 @@ void hm_rqfast(const float* x, const float* h, float* out, float* ld, int64_t n,
 
 float hm_exp_det(float t) { return exp_det(t); }
 
+// fast backward of the wide-conditioner kernel (b2f_rqfast.cuh rqf::backward_fwd): h (n, 23) raw parameters
+void hm_rq_backward_fast(const float* x, const float* h, const float* gz, const float* gl, float* dx, float* dh, int64_t n, float b) {
+    for (int64_t i = 0; i < n; ++i) {
+        float p[24], dp[24];
+        for (int j = 0; j < 23; ++j) p[j] = h[i * 23 + j];
+        p[23] = 0.0f;
+        rqf::backward_fwd(x[i], p, b, gz[i], gl[i], dx[i], dp);
+        for (int j = 0; j < 23; ++j) dh[i * 23 + j] = dp[j];
+    }
+}
+
 void hm_rq(const float* x, const float* h, float* out, float* ld, int32_t* k, int64_t n, int nb, float b, int inverse,
            int templated) {
     if (templated && nb == 8) rq_run<8>(x, h, out, ld, k, n, nb, b, inverse);

@@ -68,6 +68,15 @@ def rq_backward(x, h, gz, gl, n_bins, boundary):
     return torch.from_numpy(dv), torch.from_numpy(dh)
 
 
+def rq_backward_fast(x, h, gz, gl, boundary):
+    """rqf::backward_fwd (csrc/b2f_rqfast.cuh): the wide-conditioner kernel's backward epilogue, n_bins = 8."""
+    xs, hs, gzs, gls = _np(x), _np(h), _np(gz), _np(gl)
+    dv, dh = np.empty_like(xs), np.empty_like(hs)
+    lib().hm_rq_backward_fast(_p(xs), _p(hs), _p(gzs), _p(gls), _p(dv), _p(dh), ctypes.c_int64(xs.size),
+                              ctypes.c_float(boundary))
+    return torch.from_numpy(dv), torch.from_numpy(dh)
+
+
 def rq_backward_inv(z, h, gx, gl, n_bins, boundary):
     zs, hs, gxs, gls = _np(z), _np(h), _np(gx), _np(gl)
     dz, dh = np.empty_like(zs), np.empty_like(hs)

@@ -124,6 +124,40 @@ def test_hostmath_rq_backward_vs_autograd(n_bins):
     assert dv[0] == gz[0] and dv[1] == gz[1] and (dh[:2] == 0).all()      # out-of-bounds: dL/dv = GZ, dL/dh = 0
 
 
+@pytest.mark.parametrize('boundary,scale', [(50.0, 3.0), (5.0, 2.0)])
+def test_hostmath_fast_rq_backward_vs_autograd(boundary, scale):
+    """rqf::backward_fwd (the backward epilogue of the wide-conditioner GEMM kernel, csrc/b2f_rqfast.cuh) against the
+    reference's autograd through the oracle: same bar as rq_backward_fwd above."""
+    g = torch.Generator().manual_seed(21)
+    n = 8192
+    x = torch.randn(n, generator=g) * scale
+    x[:4] = torch.tensor([60.0, -70.0, 0.0, boundary - 0.1])
+    h = torch.randn(n, 23, generator=g)
+    gz = torch.randn(n, generator=g)
+    gl = torch.randn(n, generator=g)
+
+    def autograd(dt):
+        xd, hd = x.to(dt).requires_grad_(True), h.to(dt).requires_grad_(True)
+        z, ld = fo.rq_forward(xd[:, None], hd[:, None, :], n_bins=8, boundary=boundary)
+        (z[:, 0] * gz.to(dt)).sum().add((ld * gl.to(dt)).sum()).backward()
+        return xd.grad.double(), hd.grad.double()
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm()).item()
+
+    x64, h64 = autograd(torch.float64)
+    x32, h32 = autograd(torch.float32)
+    dv, dh = hostmath.rq_backward_fast(x, h, gz, gl, boundary)
+    assert torch.isfinite(dv).all() and torch.isfinite(dh).all()
+    assert rel(dv.double(), x64) <= 2 * rel(x32, x64) + 1e-5
+    assert rel(dh.double(), h64) <= 2 * rel(h32, h64) + 1e-5
+    assert dv[0] == gz[0] and dv[1] == gz[1] and (dh[:2] == 0).all()
+    # and against the deterministic-knot backward it replaces in that kernel
+    dv0, dh0 = hostmath.rq_backward(x, h, gz, gl, 8, boundary)
+    assert rel(dv.double(), dv0.double()) < 1e-5
+    assert rel(dh.double(), dh0.double()) < 2e-3
+
+
 @pytest.mark.parametrize('inverse', [False, True])
 def test_hostmath_affine_backward_vs_autograd(inverse):
     g = torch.Generator().manual_seed(12)

@@ -63,7 +63,7 @@ def test_wide_layer_forward_vs_oracle(B, D, H, direction):
     x[0, D // 2] = 7.5                       # outside the spline: identity tail
     boundary = 5.0
     tk = N.T_RQ_FWD if direction == 'forward' else N.T_RQ_INV
-    y, ld = N.wide_coupling_forward(tk, x.to(dev), *(t.to(dev) for t in (W1, b1, W2, b2)), n_bins=8, boundary=boundary)
+    y, ld, _ = N.wide_coupling_forward(tk, x.to(dev), *(t.to(dev) for t in (W1, b1, W2, b2)), n_bins=8, boundary=boundary)
     torch.cuda.synchronize()
     y64, ld64 = _oracle_layer(x, W1, b1, W2, b2, direction, boundary, torch.float64)
     assert torch.equal(y[:, :D // 2].cpu(), x[:, :D // 2])
@@ -86,9 +86,14 @@ def test_wide_layer_backward_vs_oracle_autograd(B, D, H, direction):
     gld = torch.randn(B, generator=g)
     boundary = 5.0
     tk = N.T_RQ_FWD if direction == 'forward' else N.T_RQ_INV
-    ours = N.wide_coupling_backward(tk, x.to(dev), gy.to(dev), gld.to(dev), *(t.to(dev) for t in (W1, b1, W2, b2)),
-                                    n_bins=8, boundary=boundary)
+    params = [t.to(dev) for t in (W1, b1, W2, b2)]
+    ours = N.wide_coupling_backward(tk, x.to(dev), gy.to(dev), gld.to(dev), *params, n_bins=8, boundary=boundary)
+    # same gradients when the backward reuses what the forward of the step kept (packed operands, hidden activations)
+    _, _, keep = N.wide_coupling_forward(tk, x.to(dev), *params, n_bins=8, boundary=boundary, for_backward=True)
+    kept = N.wide_coupling_backward(tk, x.to(dev), gy.to(dev), gld.to(dev), *params, n_bins=8, boundary=boundary, keep=keep)
     torch.cuda.synchronize()
+    for a, b_ in zip(ours, kept):
+        assert rel(b_, a) < 1e-5            # split-K atomics: summation order only
 
     leaves = [t.double().clone().requires_grad_(True) for t in (x, W1, b1, W2, b2)]
     yo, ldo = _oracle_layer(*leaves, direction, boundary, torch.float64, tf32_operands=True)

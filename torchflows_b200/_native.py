@@ -76,8 +76,9 @@ def lib():
         L.b2f_debug_umma_gemm.argtypes = [vp, vp, vp, i32, i32, vp]
         L.b2f_wide_coupling_workspace.argtypes = [i64, i32, i32, i32]
         L.b2f_wide_coupling_workspace.restype = i64
-        L.b2f_wide_coupling_forward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, i64, vp, i64, vp]
-        L.b2f_wide_coupling_backward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp]
+        L.b2f_wide_coupling_forward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, i64, vp, i64, vp, i64, i32, vp]
+        L.b2f_wide_coupling_backward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i64,
+                                                 i32, vp]
         _lib = L
     return _lib
 
@@ -215,14 +216,15 @@ def wide_eligible(D: int, H: int, n_bins: int) -> bool:
     return D >= 64 and D % 64 == 0 and H >= 32 and H % 32 == 0 and n_bins == 8
 
 
+WIDE_FOR_BACKWARD, WIDE_KEPT = 1, 2
 _wide_ws = {}
 
 
-def _wide_workspace(device, B: int, D: int, H: int, backward: bool) -> torch.Tensor:
-    """Scratch of the wide layer kernels, one buffer per device that only grows (the layers of a flow run one after the
-    other on one stream and nothing in it outlives a call)."""
-    need = int(lib().b2f_wide_coupling_workspace(B, D, H, int(backward)))
-    key = (device.type, device.index)
+def _wide_buffer(device, role: str, need: int) -> torch.Tensor:
+    """Shared buffers of the wide layer kernels, one per (device, role) that only grows: the layers of a flow run one
+    after the other on one stream and nothing in them outlives a call (what must survive until the backward is allocated
+    per call instead, see wide_coupling_forward)."""
+    key = (device.type, device.index, role)
     buf = _wide_ws.get(key)
     if buf is None or buf.numel() * 4 < need:
         _wide_ws[key] = buf = torch.empty((need + 3) // 4, device=device, dtype=torch.float32)
@@ -236,8 +238,9 @@ def _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2) -> WideLayer:
     return L
 
 
-def wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins=8, boundary=50.0):
-    """x2: (B, D).  Returns (y, log_det)."""
+def wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins=8, boundary=50.0, for_backward=False):
+    """x2: (B, D).  Returns (y, log_det, keep): with for_backward, `keep` holds the packed operands and hidden activations
+    of this call for wide_coupling_backward (None otherwise)."""
     x2 = require_cuda_f32(x2, 'coupling input')
     W1, b1, W2, b2 = (require_cuda_f32(t, 'conditioner parameter') for t in (W1, b1, W2, b2))
     B, D = x2.shape
@@ -245,15 +248,22 @@ def wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins=8, boundary=50.0):
     y = torch.empty_like(x2)
     ld = torch.empty(B, device=x2.device, dtype=torch.float32)
     with torch.cuda.device(x2.device):
-        ws = _wide_workspace(x2.device, B, D, H, False)
+        L = lib()
+        if for_backward:
+            keep = torch.empty((int(L.b2f_wide_coupling_workspace(B, D, H, 1)) + 3) // 4, device=x2.device, dtype=torch.float32)
+        else:
+            keep = _wide_buffer(x2.device, 'keep', int(L.b2f_wide_coupling_workspace(B, D, H, 0)))
+        scratch = _wide_buffer(x2.device, 'scratch', int(L.b2f_wide_coupling_workspace(B, D, H, 2)))
         layer = _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2)
-        check(lib().b2f_wide_coupling_forward(ctypes.byref(layer), ptr(x2), ptr(y), ptr(ld), B, ptr(ws), ws.numel() * 4,
-                                              stream_ptr(x2.device)))
-    return y, ld
+        check(L.b2f_wide_coupling_forward(ctypes.byref(layer), ptr(x2), ptr(y), ptr(ld), B, ptr(keep), keep.numel() * 4,
+                                          ptr(scratch), scratch.numel() * 4, WIDE_FOR_BACKWARD if for_backward else 0,
+                                          stream_ptr(x2.device)))
+    return y, ld, (keep if for_backward else None)
 
 
-def wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins=8, boundary=50.0):
-    """Returns (gx, gW1, gb1, gW2, gb2) given the layer input x2 and upstream gradients (either may be None)."""
+def wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins=8, boundary=50.0, keep=None):
+    """Returns (gx, gW1, gb1, gW2, gb2) given the layer input x2 and upstream gradients (either may be None).  `keep`: what
+    wide_coupling_forward(..., for_backward=True) returned for the same x2 and (unchanged) parameters."""
     x2 = require_cuda_f32(x2, 'coupling input')
     W1, b1, W2, b2 = (require_cuda_f32(t, 'conditioner parameter') for t in (W1, b1, W2, b2))
     gy = None if gy is None else require_cuda_f32(gy, 'upstream gradient')
@@ -263,8 +273,13 @@ def wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins=8, boundar
     gx = torch.empty_like(x2)
     gW1, gb1, gW2, gb2 = (torch.empty_like(t) for t in (W1, b1, W2, b2))
     with torch.cuda.device(x2.device):
-        ws = _wide_workspace(x2.device, B, D, H, True)
+        L = lib()
+        flags = WIDE_KEPT if keep is not None else 0
+        if keep is None:
+            keep = _wide_buffer(x2.device, 'keep', int(L.b2f_wide_coupling_workspace(B, D, H, 1)))
+        scratch = _wide_buffer(x2.device, 'scratch', int(L.b2f_wide_coupling_workspace(B, D, H, 3)))
         layer = _wide_layer(D, H, tkind, n_bins, boundary, W1, b1, W2, b2)
-        check(lib().b2f_wide_coupling_backward(ctypes.byref(layer), ptr(x2), ptr(gy), ptr(gld), ptr(gx), ptr(gW1), ptr(gb1),
-                                               ptr(gW2), ptr(gb2), B, ptr(ws), ws.numel() * 4, stream_ptr(x2.device)))
+        check(L.b2f_wide_coupling_backward(ctypes.byref(layer), ptr(x2), ptr(gy), ptr(gld), ptr(gx), ptr(gW1), ptr(gb1),
+                                           ptr(gW2), ptr(gb2), B, ptr(keep), keep.numel() * 4, ptr(scratch),
+                                           scratch.numel() * 4, flags, stream_ptr(x2.device)))
     return gx, gW1, gb1, gW2, gb2

@@ -58,16 +58,22 @@ class _WideCoupling(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x2, W1, b1, W2, b2, tkind, n_bins, boundary):
-        y, ld = N.wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins, boundary)
+        training = any(ctx.needs_input_grad[:5])
+        y, ld, keep = N.wide_coupling_forward(tkind, x2, W1, b1, W2, b2, n_bins, boundary, for_backward=training)
         ctx.save_for_backward(x2, W1, b1, W2, b2)
         ctx.cfg = (tkind, n_bins, boundary)
+        # packed operands + hidden activations of this call, reusable by the backward while the parameters are unchanged
+        ctx.keep = keep
+        ctx.versions = tuple(t._version for t in (W1, b1, W2, b2))
         return y, ld
 
     @staticmethod
     def backward(ctx, gy, gld):
         x2, W1, b1, W2, b2 = ctx.saved_tensors
         tkind, n_bins, boundary = ctx.cfg
-        gx, gW1, gb1, gW2, gb2 = N.wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins, boundary)
+        keep = ctx.keep if ctx.versions == tuple(t._version for t in (W1, b1, W2, b2)) else None
+        gx, gW1, gb1, gW2, gb2 = N.wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins, boundary, keep=keep)
+        ctx.keep = None
         return gx, gW1, gb1, gW2, gb2, None, None, None
 
 

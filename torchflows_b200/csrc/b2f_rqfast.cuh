@@ -194,5 +194,123 @@ B2F_HD void inverse(float v, const float (&g)[24], float b, float& out, float& l
     ld2 = f_lg2(inb ? den * den : 1.0f) - f_lg2(inb ? fw : 1.0f);
 }
 
+
+// ---- backward of the forward-direction spline on the RAW 23 parameters (p[0..8) widths logits, p[8..16) heights
+// offsets, p[16..23) interior derivative logits; p[23] unused) for the wide-conditioner kernel (b2f_wide.cu), whose
+// backward is the epilogue of a GEMM and must be short.  Same partial derivatives as rq_backward_fwd (b2f_math.cuh,
+// SURVEY Appendix D), restructured: the two softmaxes are evaluated ONCE (SFU ex2, shared by the knots and by the softmax
+// backward -- rq_backward_fwd evaluates 32 polynomial exponentials), reciprocals instead of divisions, the sigmoid of the
+// two selected derivative logits only.  ~450 issue slots instead of ~1700.  Tolerance-checked against rq_backward_fwd
+// (tests/test_c_oracle_and_hostmath.py) like everything downstream of a TF32 GEMM.
+B2F_HD float f_rcpn(float x) {            // reciprocal + one Newton step (~1 ulp)
+    const float y = f_rcp(x);
+    return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
+
+B2F_HD void backward_fwd(float v, const float (&p)[24], float b, float GZ, float GL, float& dv, float (&dp)[24]) {
+    const bool inb = v > -b && v < b;
+    const float lo = -b, span = b + b;
+    // softmaxes (rational_quadratic.py:75-76, 46-47)
+    float px[8], py[8];
+    float mx = p[0], my = fmaf(p[8], 1e-3f, p[0]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        px[j] = p[j];
+        py[j] = fmaf(p[8 + j], 1e-3f, p[j]);
+        mx = fmaxf(mx, px[j]);
+        my = fmaxf(my, py[j]);
+    }
+    float sx = 0.0f, sy = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        px[j] = f_ex2((px[j] - mx) * kLog2e);
+        py[j] = f_ex2((py[j] - my) * kLog2e);
+        sx += px[j];
+        sy += py[j];
+    }
+    const float isx = f_rcpn(sx), isy = f_rcpn(sy);
+    // knots, search (searchsorted right=False: knots strictly below v), selection of the bin's quantities
+    float cx = 0.0f, cy = 0.0f;
+    float xk = lo, yk = lo, xk1 = b, yk1 = b, ud0 = kRqEdgeU, ud1 = kRqEdgeU;
+    int k = 0;
+    bool prev_below = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        px[j] *= isx;
+        py[j] *= isy;
+        cx += fmaf(px[j], kSizeScale, kRqMinBin);
+        cy += fmaf(py[j], kSizeScale, kRqMinBin);
+        const bool last = j == 7;
+        const float kx = last ? b : fmaf(span, cx, lo);
+        const float ky = last ? b : fmaf(span, cy, lo);
+        const float ud = last ? kRqEdgeU : p[16 + (last ? 0 : j)];
+        const bool below = kx < v;
+        const bool take = prev_below && !below;
+        if (below) { xk = kx; yk = ky; ud0 = ud; k = j + 1; }
+        if (take) { xk1 = kx; yk1 = ky; ud1 = ud; }
+        prev_below = below;
+    }
+    // evaluation inside the bin (rational_quadratic.py:88-109)
+    const float w = xk1 - xk, hgt = yk1 - yk;
+    const float iw = f_rcpn(w);
+    const float sk = hgt * iw;
+    const float xr = (v - xk) * iw;
+    const float a0 = fmaf(ud0, 1e-3f, kRqEdgeU), a1 = fmaf(ud1, 1e-3f, kRqEdgeU);
+    const float e0 = f_ex2(a0 * kLog2e), e1 = f_ex2(a1 * kLog2e);
+    const float d0 = fmaf(f_lg2(1.0f + e0), kLn2, kRqMinDelta), d1 = fmaf(f_lg2(1.0f + e1), kLn2, kRqMinDelta);
+    const float t1 = d1 + d0 - 2.0f * sk;
+    const float xi = fminf(fmaxf(xr, 0.0f), 1.0f);
+    const bool clipped = (xr < 0.0f) || (xr > 1.0f);
+    const float omx = 1.0f - xi;
+    const float q = xi * omx;
+    const float Dn = fmaf(t1, q, sk);
+    const float M = fmaf(d1 * xi, xi, fmaf(2.0f * sk, q, d0 * omx * omx));
+    const float iDn = f_rcpn(Dn), iM = f_rcpn(M), isk = f_rcpn(sk);
+    const float A = fmaf(sk * xi, xi, d0 * q);
+    const float omq = 1.0f - 2.0f * q, om2x = 1.0f - 2.0f * xi;
+    const float hD2 = hgt * iDn * iDn;
+    // partials (Appendix D)
+    const float out_xi = hD2 * sk * M;
+    const float out_s = hD2 * fmaf(xi * xi, Dn, -A * omq);
+    const float out_d0 = hD2 * q * (Dn - A);
+    const float out_d1 = -hD2 * A * q;
+    const float ld_xi = 2.0f * (fmaf(d1, xi, fmaf(sk, om2x, -d0 * omx)) * iM - t1 * om2x * iDn);
+    const float ld_s = 2.0f * (isk + q * iM - omq * iDn);
+    const float ld_d0 = fmaf(omx * omx, iM, -2.0f * q * iDn);
+    const float ld_d1 = fmaf(xi * xi, iM, -2.0f * q * iDn);
+    float Gxi = fmaf(GZ, out_xi, GL * ld_xi);
+    if (clipped) Gxi = 0.0f;
+    const float Gs = fmaf(GZ, out_s, GL * ld_s);
+    const float dvi = Gxi * iw;
+    const float Gxk = -dvi;
+    const float Gw = -(fmaf(Gxi, xi, Gs * sk)) * iw;
+    const float Ghgt = fmaf(GZ * A, iDn, Gs * iw);
+    const float Gd0 = fmaf(GZ, out_d0, GL * ld_d0), Gd1 = fmaf(GZ, out_d1, GL * ld_d1);
+    // softmax backward: knot gradients g_j = span ([j < k] G_below + [j == k] G_at); J(p, g)_j = c1 p_j (g_j - sum_i p_i g_i)
+    float gxv[8], gyv[8];
+    float dotx = 0.0f, doty = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        gxv[j] = span * (j < k ? Gxk : (j == k ? Gw : 0.0f));
+        gyv[j] = span * (j < k ? GZ : (j == k ? Ghgt : 0.0f));
+        dotx = fmaf(px[j], gxv[j], dotx);
+        doty = fmaf(py[j], gyv[j], doty);
+    }
+    // out of bounds (identity tail): zero parameter gradient -- selected, not multiplied (w = 0 there, the values are NaN)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float jx = kSizeScale * px[j] * (gxv[j] - dotx);
+        const float jy = kSizeScale * py[j] * (gyv[j] - doty);
+        dp[j] = inb ? jx + jy : 0.0f;
+        dp[8 + j] = inb ? jy * 1e-3f : 0.0f;
+    }
+    // derivative logits: softplus' = sigmoid = e / (1 + e); only knots k (lower) and k + 1 (upper) receive anything
+    const float g0 = Gd0 * e0 * f_rcpn(1.0f + e0) * 1e-3f, g1 = Gd1 * e1 * f_rcpn(1.0f + e1) * 1e-3f;
+#pragma unroll
+    for (int jj = 1; jj < 8; ++jj) dp[16 + jj - 1] = inb ? (jj == k ? g0 : 0.0f) + (jj == k + 1 ? g1 : 0.0f) : 0.0f;
+    dp[23] = 0.0f;
+    dv = inb ? dvi : GZ;
+}
+
 }  // namespace rqf
 }  // namespace b2f

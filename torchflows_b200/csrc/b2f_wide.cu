@@ -32,6 +32,7 @@
 
 #include "b2f_common.cuh"
 #include "b2f_math.cuh"
+#include "b2f_rqfast.cuh"
 #include "b2f_umma.cuh"
 
 namespace b2f {
@@ -75,6 +76,7 @@ struct GArgs {
     float* dhA;              // backward: dL/dh as T(Bp, P)
     float* dhT;              // backward: dL/dh as T(Pp, Bp)
     int Pp8;                 // rows / 8 of dhT
+    float* gb2;              // backward: dL/db2 (Dh * 23), accumulated atomically (zeroed by the caller)
 };
 
 __device__ __forceinline__ float tf32_rn(float v) {
@@ -142,9 +144,15 @@ __device__ __forceinline__ void epi_store(const GArgs& G, int mt, int nt, int nc
     }
 }
 
+// Backward staging (per warp, 3 blocks of 8 parameters x 32 rows): the transposed orientation of dL/dh leaves the warp as
+// three contiguous 1 KB runs of T(Pp, Bp) instead of 24 scattered 4-byte stores per thread; row stride 36 floats per
+// 4-row group keeps the transposing writes conflict-free.  The same tile gives the bias gradient (column sums).
+constexpr int kStageBlk = 8 * 36;                    // floats per staged block [k4 = row / 4 (8)][36: n % 8 (8) x row % 4 (4), padded]
+constexpr int kStageWarp = 3 * kStageBlk;
+
 template <int EPI, class Release>
 __device__ __forceinline__ void epi_spline(const GArgs& G, int mt, int nt, uint32_t tbase, int warp, int lane,
-                                           const Release& release) {
+                                           float* stage, const Release& release) {
     constexpr bool BWD = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
     constexpr bool INV = EPI == EPI_SPLINE_INV || EPI == EPI_SPLINE_BWD_INV;
     const int q = warp & 3, t = warp >> 3, half = (warp >> 2) & 1;
@@ -186,18 +194,40 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, int mt, int nt, uint3
             auto g = [&](int i, float val) { dp[i] = val; };
             float dv;
             if constexpr (INV) rq_backward_inv<8, 1>(v, h, 8, G.boundary, GZ, GL, dv, g);
-            else rq_backward_fwd<8, 1>(v, h, 8, G.boundary, GZ, GL, dv, g);
+            else rqf::backward_fwd(v, p, G.boundary, GZ, GL, dv, dp);        // density direction: the training hot path
             if (live) G.gx[row * G.ldx + G.Dh + e] = dv;
 #pragma unroll
             for (int i = 0; i < 24; ++i) dp[i] = live ? tf32_rn(dp[i]) : 0.0f;
-            // dL/dh in both operand orientations: (row, k = parameter) and (parameter, k = row)
+            // dL/dh in both operand orientations: (row, k = parameter) directly, (parameter, k = row) through the staging tile
             const long long n0 = (long long)e * 24;
 #pragma unroll
             for (int c = 0; c < 6; ++c)
                 *reinterpret_cast<float4*>(G.dhA + tiled_off(row, n0 + 4 * c, G.Bp >> 3)) =
                     make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
+            float* sw = stage + (warp * kStageWarp);
+            __syncwarp();                                    // the previous element's tile has been read
 #pragma unroll
-            for (int i = 0; i < 24; ++i) G.dhT[tiled_off(n0 + i, row, G.Pp8)] = dp[i];
+            for (int i = 0; i < 24; ++i) sw[(i >> 3) * kStageBlk + (lane >> 2) * 36 + (i & 7) * 4 + (lane & 3)] = dp[i];
+            __syncwarp();
+            // rows of this warp: one 32-wide k-block of T(Pp, Bp); parameters n0 .. n0 + 23 = three 8-row groups
+            const long long kb = row >> 5;
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int f4 = u * 32 + lane;                // float4 slot 0 .. 191 of the 3 KB
+                const int blk = f4 >> 6, k4 = (f4 >> 3) & 7, n8 = f4 & 7;
+                const float4 v = *reinterpret_cast<const float4*>(sw + blk * kStageBlk + k4 * 36 + n8 * 4);
+                *reinterpret_cast<float4*>(G.dhT + ((size_t)kb * G.Pp8 + (size_t)(n0 >> 3) + blk) * 256 + k4 * 32 + n8 * 4) = v;
+            }
+            if (lane < 23) {                                 // dL/db2[e * 23 + lane] += sum over the warp's 32 rows
+                const float* col = sw + (lane >> 3) * kStageBlk + (lane & 7) * 4;
+                float a = 0.0f;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 v = *reinterpret_cast<const float4*>(col + k4 * 36);
+                    a += (v.x + v.y) + (v.z + v.w);
+                }
+                atomicAdd(G.gb2 + (size_t)e * 23 + lane, a);
+            }
         }
     }
     if constexpr (!BWD) G.ldp[(size_t)(nt * 2 + half) * G.Bp + row] = ldacc;
@@ -210,7 +240,9 @@ __global__ void __launch_bounds__(kThreads, 1) wide_gemm_kernel(const __grid_con
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int stage_bytes = kABytes + G.NT * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)G.stages * stage_bytes);
+    constexpr bool kBwd = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
+    float* stage = reinterpret_cast<float*>(smem_raw + (size_t)G.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)G.stages * stage_bytes + (kBwd ? kEpiWarps * kStageWarp * 4 : 0));
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + WB_COUNT);
 
     if (tid == 0) {
@@ -308,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) wide_gemm_kernel(const __grid_con
                 if (lane == 0) umma::mbar_arrive(&bars[WB_D_EMPTY]);
             };
             if constexpr (EPI == EPI_STORE) epi_store(G, mt, nt, ncols, tbase, warp, lane, release);
-            else epi_spline<EPI>(G, mt, nt, tbase, warp, lane, release);
+            else epi_spline<EPI>(G, mt, nt, tbase, warp, lane, stage, release);
         }
     }
     umma::tc_fence_before_sync();
@@ -386,28 +418,6 @@ __global__ void __launch_bounds__(256) pack_kernel(const PArgs P) {
     }
 }
 
-// per-row sums of a tiled matrix T(R, K) over k < K: out[(n / 24) * 23 + n % 24] for rows n < n_rows with n % 24 < 23
-// (dL/db2 = sum over the batch of dL/dh).  One block per 8-row group.
-__global__ void __launch_bounds__(256) rowsum_tiled_kernel(const float* __restrict__ T, long long R8, long long kb_total,
-                                                           long long n_rows, float* __restrict__ out) {
-    __shared__ float s[256];
-    const long long rg = blockIdx.x;
-    const int i = threadIdx.x;                 // [k4 (8)][row in group (8)][k % 4 (4)]
-    float a = 0.0f;
-    for (long long kb = 0; kb < kb_total; ++kb) a += __ldg(T + (kb * R8 + rg) * 256 + i);
-    s[i] = a;
-    __syncthreads();
-    if (i < 8) {
-        float t = 0.0f;
-        for (int k4 = 0; k4 < 8; ++k4)
-            for (int u = 0; u < 4; ++u) t += s[k4 * 32 + i * 4 + u];
-        const long long n = rg * 8 + i;
-        const long long e = n / 24;
-        const int k = (int)(n - e * 24);
-        if (n < n_rows && k < 23) out[e * 23 + k] = t;
-    }
-}
-
 // bias padded to 24 per element
 __global__ void pad_bias_kernel(const float* __restrict__ b2, float* __restrict__ b2p, int Dh) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,8 +464,11 @@ static Shapes shapes(long long B, int D, int H) {
     return s;
 }
 
+// Two buffers.  "keep": everything the backward can reuse from the forward of the same step (packed operands and hidden
+// activations; the T-forms only when the forward was told a backward follows).  "scratch": per-call temporaries.
 struct Workspace {           // offsets in floats
-    size_t xaA, xaT, W1t, W1T, W2p, W2pT, b2p, pre, hidA, hidT, ldp, dhA, dhT, dhid, dpreA, dpreT, total;
+    size_t xaA, W1t, W2p, b2p, pre, hidA, xaT, W1T, W2pT, hidT, keep_total;
+    size_t ldp, dhA, dhT, dhid, dpreA, dpreT, scratch_total;
 };
 
 static Workspace layout(const Shapes& s, bool backward) {
@@ -468,20 +481,25 @@ static Workspace layout(const Shapes& s, bool backward) {
     w.b2p = take((size_t)s.P);
     w.pre = take((size_t)s.Bp * s.H);
     w.hidA = take((size_t)s.Bp * s.H);
-    w.ldp = take((size_t)(s.P / 192) * 2 * s.Bp);
-    w.xaT = w.W1T = w.W2pT = w.hidT = w.dhA = w.dhT = w.dhid = w.dpreA = w.dpreT = 0;
+    w.xaT = w.W1T = w.W2pT = w.hidT = 0;
     if (backward) {
         w.xaT = take((size_t)s.Dhp * s.Bp);
         w.W1T = take((size_t)s.Dhp * s.H);
         w.W2pT = take((size_t)s.Hp * s.P);
         w.hidT = take((size_t)s.Hp * s.Bp);
+    }
+    w.keep_total = o;
+    o = 0;
+    w.ldp = take((size_t)(s.P / 192) * 2 * s.Bp);
+    w.dhA = w.dhT = w.dhid = w.dpreA = w.dpreT = 0;
+    if (backward) {
         w.dhA = take((size_t)s.Bp * s.P);
         w.dhT = take((size_t)s.Pp * s.Bp);
         w.dhid = take((size_t)s.Bp * s.H);
         w.dpreA = take((size_t)s.Bp * s.H);
         w.dpreT = take((size_t)s.Hp * s.Bp);
     }
-    w.total = o;
+    w.scratch_total = o;
     return w;
 }
 
@@ -508,8 +526,10 @@ static int pack(cudaStream_t st, const float* src, long long ld, long long R, lo
 
 template <int EPI>
 static int launch_gemm(cudaStream_t st, GArgs& G, const char* what) {
-    G.stages = std::min(kMaxStages, (int)((227 * 1024 - 256) / (kABytes + G.NT * 128)));
-    const size_t smem = (size_t)G.stages * (kABytes + G.NT * 128) + WB_COUNT * 8 + 16;
+    constexpr bool kBwd = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
+    const size_t extra = (kBwd ? (size_t)kEpiWarps * kStageWarp * 4 : 0) + WB_COUNT * 8 + 16;
+    G.stages = std::min(kMaxStages, (int)((227 * 1024 - extra) / (kABytes + G.NT * 128)));
+    const size_t smem = (size_t)G.stages * (kABytes + G.NT * 128) + extra;
     const int items = G.n_mt * G.n_nt * G.n_split;
     if (items <= 0) return B2F_OK;
     cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)wide_gemm_kernel<EPI>, smem);
@@ -533,15 +553,16 @@ static int gemm_store(cudaStream_t st, const float* A, long long RAp, const floa
     return launch_gemm<EPI_STORE>(st, G, "b2f_wide (gemm)");
 }
 
-// split factor that brings the item count close to a whole number of waves
+// k-split of a plain GEMM: minimise waves x (k-blocks per item + epilogue) -- a split adds one atomic pass over the output
+// per part, so short-K GEMMs stay unsplit and long-K ones fill the last wave
 static int pick_split(int items, int kb_total) {
     const int sms = n_sm();
     int best = 1;
-    double best_eff = 0.0;
+    double best_cost = 1e30;
     for (int s = 1; s <= 8 && s <= kb_total; ++s) {
-        const int n = items * s;
-        const double eff = (double)n / ((double)((n + sms - 1) / sms) * sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+        const double waves = (double)((items * s + sms - 1) / sms);
+        const double cost = waves * ((double)((kb_total + s - 1) / s) * 1400.0 + 8000.0);
+        if (cost < best_cost * 0.98) { best_cost = cost; best = s; }
     }
     return best;
 }
@@ -583,91 +604,100 @@ static void spline_gemm_args(GArgs& G, const b2f_wide_layer_t* L, const Shapes& 
 using namespace b2f;
 using namespace b2f::wide;
 
-extern "C" int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t backward) {
-    if (B < 0 || D < 2 || H < 1) return 0;
-    return (int64_t)(layout(shapes(B, D, H), backward != 0).total * sizeof(float));
+extern "C" int64_t b2f_wide_coupling_workspace(int64_t B, int32_t D, int32_t H, int32_t which) {
+    if (B < 0 || D < 2 || H < 1 || which < 0 || which > 3) return 0;
+    const Workspace w = layout(shapes(B, D, H), (which & 1) != 0);
+    return (int64_t)((which < 2 ? w.keep_total : w.scratch_total) * sizeof(float));
+}
+
+// packed weights + hidden activations into `keep` (with the transposed forms when a backward follows)
+static int prepare(cudaStream_t st, const b2f_wide_layer_t* L, const Shapes& s, const Workspace& w, float* kp, const float* x,
+                   bool backward) {
+    int rc;
+    if ((rc = hidden_layer(st, L, s, w, kp, x, backward)) != B2F_OK) return rc;
+    // output-layer weights T(Pp, H) for the GEMM whose epilogue is the spline; T(Hp, P) for dL/dhid
+    if ((rc = pack(st, L->W2, s.H, s.P, s.H, 1, PACK_COPY, nullptr, nullptr, 0, kp + w.W2p, s.Pp, backward ? kp + w.W2pT : nullptr,
+                   s.Hp, s.P, nullptr)) != B2F_OK) return rc;
+    pad_bias_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(L->b2, kp + w.b2p, s.Dh);
+    return check_launch("b2f_wide (bias)");
 }
 
 extern "C" int b2f_wide_coupling_forward(const b2f_wide_layer_t* L, const float* x, float* y, float* log_det, int64_t B,
-                                         void* workspace, int64_t workspace_bytes, void* stream) {
+                                         void* keep, int64_t keep_bytes, void* scratch, int64_t scratch_bytes, int32_t flags,
+                                         void* stream) {
     int rc = check_layer(L, B);
     if (rc != B2F_OK) return rc;
     if (B == 0) return B2F_OK;
-    if (!x || !y || !workspace) return fail(B2F_ERR_INVALID, "wide coupling: null buffer");
+    if (!x || !y || !keep || !scratch) return fail(B2F_ERR_INVALID, "wide coupling: null buffer");
+    const bool for_bwd = (flags & B2F_WIDE_FOR_BACKWARD) != 0;
     const Shapes s = shapes(B, L->D, L->H);
-    const Workspace w = layout(s, false);
-    if ((size_t)workspace_bytes < w.total * sizeof(float)) return fail(B2F_ERR_INVALID, "wide coupling: workspace too small");
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(workspace)) & 15)
+    const Workspace w = layout(s, for_bwd), wf = layout(s, false);
+    if ((size_t)keep_bytes < w.keep_total * sizeof(float) || (size_t)scratch_bytes < wf.scratch_total * sizeof(float))
+        return fail(B2F_ERR_INVALID, "wide coupling: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(keep) |
+         reinterpret_cast<uintptr_t>(scratch)) & 15)
         return fail(B2F_ERR_INVALID, "wide coupling: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    float* ws = (float*)workspace;
-    if ((rc = hidden_layer(st, L, s, w, ws, x, false)) != B2F_OK) return rc;
-    if ((rc = pack(st, L->W2, s.H, s.P, s.H, 1, PACK_COPY, nullptr, nullptr, 0, ws + w.W2p, s.Pp, nullptr, 0, 0, nullptr)) != B2F_OK) return rc;
-    pad_bias_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(L->b2, ws + w.b2p, s.Dh);
-    if ((rc = check_launch("b2f_wide (bias)")) != B2F_OK) return rc;
+    float *kp = (float*)keep, *sc = (float*)scratch;
+    if ((rc = prepare(st, L, s, w, kp, x, for_bwd)) != B2F_OK) return rc;
     GArgs G;
-    spline_gemm_args(G, L, s, w, ws, x);
-    G.y = y; G.ldp = ws + w.ldp;
+    spline_gemm_args(G, L, s, w, kp, x);
+    G.y = y; G.ldp = sc + w.ldp;
     rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
                                   : launch_gemm<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
     if (rc != B2F_OK) return rc;
-    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(x, y, B, s.D, s.Dh, ws + w.ldp, 2 * G.n_nt, s.Bp, log_det);
+    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(x, y, B, s.D, s.Dh, sc + w.ldp, 2 * G.n_nt, s.Bp, log_det);
     return check_launch("b2f_wide (finish)");
 }
 
 extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float* x, const float* gy, const float* glog_det,
-                                          float* gx, float* gW1, float* gb1, float* gW2, float* gb2, int64_t B, void* workspace,
-                                          int64_t workspace_bytes, void* stream) {
+                                          float* gx, float* gW1, float* gb1, float* gW2, float* gb2, int64_t B, void* keep,
+                                          int64_t keep_bytes, void* scratch, int64_t scratch_bytes, int32_t flags, void* stream) {
     int rc = check_layer(L, B);
     if (rc != B2F_OK) return rc;
-    if (!x || !gx || !gW1 || !gb1 || !gW2 || !gb2 || !workspace) return fail(B2F_ERR_INVALID, "wide coupling backward: null buffer");
+    if (!x || !gx || !gW1 || !gb1 || !gW2 || !gb2 || !keep || !scratch) return fail(B2F_ERR_INVALID, "wide coupling backward: null buffer");
     const Shapes s = shapes(B, L->D, L->H);
     const Workspace w = layout(s, true);
-    if ((size_t)workspace_bytes < w.total * sizeof(float)) return fail(B2F_ERR_INVALID, "wide coupling backward: workspace too small");
+    if ((size_t)keep_bytes < w.keep_total * sizeof(float) || (size_t)scratch_bytes < w.scratch_total * sizeof(float))
+        return fail(B2F_ERR_INVALID, "wide coupling backward: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    float* ws = (float*)workspace;
+    float *kp = (float*)keep, *sc = (float*)scratch;
     const size_t P23 = (size_t)s.Dh * 23;
     cudaMemsetAsync(gW1, 0, (size_t)s.H * s.Dh * 4, st);
     cudaMemsetAsync(gb1, 0, (size_t)s.H * 4, st);
     cudaMemsetAsync(gW2, 0, P23 * s.H * 4, st);
     cudaMemsetAsync(gb2, 0, P23 * 4, st);
     if (B == 0) return check_launch("b2f_wide_coupling_backward");
-    cudaMemsetAsync(ws + w.dhid, 0, (size_t)s.Bp * s.H * 4, st);
-    // rows beyond P of dhT (P is a multiple of 768, so there are none unless Pp > P) and the T-form pads stay zero
-    if (s.Pp > s.P) cudaMemsetAsync(ws + w.dhT, 0, (size_t)s.Pp * s.Bp * 4, st);
-    if ((rc = hidden_layer(st, L, s, w, ws, x, true)) != B2F_OK) return rc;
-    // output-layer weights in both orientations: T(Pp, H) for the recompute, T(Hp, P) for dL/dhid
-    if ((rc = pack(st, L->W2, s.H, s.P, s.H, 1, PACK_COPY, nullptr, nullptr, 0, ws + w.W2p, s.Pp, ws + w.W2pT, s.Hp, s.P, nullptr)) != B2F_OK) return rc;
-    pad_bias_kernel<<<(s.P + 255) / 256, 256, 0, st>>>(L->b2, ws + w.b2p, s.Dh);
-    if ((rc = check_launch("b2f_wide (bias)")) != B2F_OK) return rc;
-    // recompute h tile by tile, spline backward in the epilogue: gx (target half), dL/dh in both orientations
+    cudaMemsetAsync(sc + w.dhid, 0, (size_t)s.Bp * s.H * 4, st);
+    if (s.Pp > s.P) cudaMemsetAsync(sc + w.dhT, 0, (size_t)s.Pp * s.Bp * 4, st);
+    // packed operands and hidden activations: kept by the forward of this step, or rebuilt from x and the parameters
+    if (!(flags & B2F_WIDE_KEPT) && (rc = prepare(st, L, s, w, kp, x, true)) != B2F_OK) return rc;
+    // recompute h tile by tile, spline backward in the epilogue: gx (target half), dL/dh in both orientations, dL/db2
     GArgs G;
-    spline_gemm_args(G, L, s, w, ws, x);
-    G.gy = gy; G.gld = glog_det; G.gx = gx; G.dhA = ws + w.dhA; G.dhT = ws + w.dhT; G.Pp8 = s.Pp / 8;
+    spline_gemm_args(G, L, s, w, kp, x);
+    G.gy = gy; G.gld = glog_det; G.gx = gx; G.dhA = sc + w.dhA; G.dhT = sc + w.dhT; G.Pp8 = s.Pp / 8; G.gb2 = gb2;
     rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_BWD_INV>(st, G, "b2f_wide_coupling_backward (spline)")
                                   : launch_gemm<EPI_SPLINE_BWD_FWD>(st, G, "b2f_wide_coupling_backward (spline)");
     if (rc != B2F_OK) return rc;
-    rowsum_tiled_kernel<<<s.Pp / 8, 256, 0, st>>>(ws + w.dhT, s.Pp / 8, s.Bp / 32, s.P, gb2);
-    if ((rc = check_launch("b2f_wide (bias gradient)")) != B2F_OK) return rc;
     // dL/dW2[n, j] = sum_b dh[b, n] hid[b, j]
     {
         const int items = (s.Pp / 256) * ((s.H + 255) / 256);
-        if ((rc = gemm_store(st, ws + w.dhT, s.Pp, ws + w.hidT, s.Hp, s.H, s.Bp, gW2, s.H, s.P, s.H, 1, 1,
+        if ((rc = gemm_store(st, sc + w.dhT, s.Pp, kp + w.hidT, s.Hp, s.H, s.Bp, gW2, s.H, s.P, s.H, 1, 1,
                              pick_split(items, (int)(s.Bp / 32)), 256)) != B2F_OK) return rc;
     }
     // dL/dhid[b, j] = sum_n dh[b, n] W2[n, j]
     {
         const int items = (int)(s.Bp / 256) * ((s.H + 255) / 256);
-        if ((rc = gemm_store(st, ws + w.dhA, s.Bp, ws + w.W2pT, s.Hp, s.H, s.P, ws + w.dhid, s.H, s.Bp, s.H, 0, 1,
+        if ((rc = gemm_store(st, sc + w.dhA, s.Bp, kp + w.W2pT, s.Hp, s.H, s.P, sc + w.dhid, s.H, s.Bp, s.H, 0, 1,
                              pick_split(items, s.P / 32), 256)) != B2F_OK) return rc;
     }
     // through the tanh: dpre = dhid (1 - hid^2) in both orientations, dL/db1 = column sums
-    if ((rc = pack(st, ws + w.dhid, s.H, s.B, s.H, 0, PACK_DTANH, L->b1, ws + w.pre, s.H, ws + w.dpreA, s.Bp, ws + w.dpreT, s.Hp,
+    if ((rc = pack(st, sc + w.dhid, s.H, s.B, s.H, 0, PACK_DTANH, L->b1, kp + w.pre, s.H, sc + w.dpreA, s.Bp, sc + w.dpreT, s.Hp,
                    s.Bp, gb1)) != B2F_OK) return rc;
     // dL/dW1[j, i] = sum_b dpre[b, j] xa[b, i]
     {
         const int items = (s.Hp / 256) * ((s.Dh + 255) / 256);
-        if ((rc = gemm_store(st, ws + w.dpreT, s.Hp, ws + w.xaT, s.Dhp, s.Dh, s.Bp, gW1, s.Dh, s.H, s.Dh, 0, 1,
+        if ((rc = gemm_store(st, sc + w.dpreT, s.Hp, kp + w.xaT, s.Dhp, s.Dh, s.Bp, gW1, s.Dh, s.H, s.Dh, 0, 1,
                              pick_split(items, (int)(s.Bp / 32)), 256)) != B2F_OK) return rc;
     }
     // dL/dxa = gy[:, :Dh] + dpre W1
@@ -675,7 +705,7 @@ extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float
     if ((rc = check_launch("b2f_wide (finish)")) != B2F_OK) return rc;
     {
         const int items = (int)(s.Bp / 256) * ((s.Dh + 255) / 256);
-        if ((rc = gemm_store(st, ws + w.dpreA, s.Bp, ws + w.W1T, s.Dhp, s.Dh, s.H, gx, s.D, s.B, s.Dh, 0, 1,
+        if ((rc = gemm_store(st, sc + w.dpreA, s.Bp, kp + w.W1T, s.Dhp, s.Dh, s.H, gx, s.D, s.B, s.Dh, 0, 1,
                              pick_split(items, s.H / 32), 256)) != B2F_OK) return rc;
     }
     return B2F_OK;
