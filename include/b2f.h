@@ -197,6 +197,30 @@ int b2f_wide_coupling_backward(const b2f_wide_layer_t *layer, const float *x, co
                                float *gx, float *gW1, float *gb1, float *gW2, float *gb2, int64_t B, void *keep,
                                int64_t keep_bytes, void *scratch, int64_t scratch_bytes, int32_t flags, void *stream);
 
+/* ---- runs of per-column layers at any event size (csrc/b2f_colrun.cu) -----------------------------------------------
+ * ElementwiseAffine / ActNorm with global parameters (autoregressive/layers_base.py:300-318, transformers/linear/
+ * affine.py:33-59, layers.py:39-69) and ReversePermutationMatrix (matrix/permutation.py:19-37) in application order
+ * compose into y[r, c] = A[c] x[r, s(c)] + C[c]; one pass over the batch instead of one per layer.  Used between layers
+ * that are not part of a whole-flow program (the wide coupling layers above). */
+#define B2F_COL_AFFINE_FWD 0 /* z = alpha x + v1,  alpha = exp(log(1 - 1e-10) + v0 / 2) + 1e-10   (Affine.forward) */
+#define B2F_COL_AFFINE_INV 1 /* x = (z - v1) / alpha                                               (Affine.inverse) */
+#define B2F_COL_FLIP 2       /* y[:, c] = x[:, D - 1 - c] */
+#define B2F_COL_MAX_OPS 8
+typedef struct b2f_colop {
+    int32_t kind;
+    int32_t reserved;
+    const float *value; /* (D, 2): v0, v1 per column (null for FLIP) */
+    float *gvalue;      /* b2f_column_run_backward: gradient of `value`, overwritten (nullable: frozen parameters) */
+} b2f_colop_t;
+
+/* y:(B,D); log_det_sum: ONE float (nullable) = sum over columns of log A[c], the log-determinant of every row. */
+int b2f_column_run_apply(const b2f_colop_t *ops, int32_t n_ops, const float *x, float *y, float *log_det_sum, int64_t B,
+                         int32_t D, void *stream);
+/* x: the run's input; gy:(B,D); g_log_det_sum: one float (nullable) = sum over rows of dL/dlog_det.  gx:(B,D) and every
+ * op's gvalue; scratch: 2*D floats. */
+int b2f_column_run_backward(const b2f_colop_t *ops, int32_t n_ops, const float *x, const float *gy, const float *g_log_det_sum,
+                            float *gx, float *scratch, int64_t B, int32_t D, void *stream);
+
 /* Per-dimension batch statistics for ActNorm's data-dependent initialisation (layers.py:58-68):
  * sum:(D) and sumsq:(D) of x:(B,D), accumulated in fp64 (must be zeroed by the caller). */
 int b2f_column_stats(const float *x, double *sum, double *sumsq, int64_t B, int32_t D, void *stream);

@@ -46,6 +46,12 @@ class WideLayer(ctypes.Structure):
                 ('W2', ctypes.c_void_p), ('b2', ctypes.c_void_p)]
 
 
+class ColOp(ctypes.Structure):
+    """struct b2f_colop (include/b2f.h)."""
+    _fields_ = [('kind', ctypes.c_int32), ('reserved', ctypes.c_int32), ('value', ctypes.c_void_p), ('gvalue', ctypes.c_void_p)]
+
+
+COL_AFFINE_FWD, COL_AFFINE_INV, COL_FLIP, COL_MAX_OPS = 0, 1, 2, 8
 _lib = None
 
 
@@ -74,6 +80,8 @@ def lib():
         L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
         L.b2f_debug_umma_gemm.argtypes = [vp, vp, vp, i32, i32, vp]
+        L.b2f_column_run_apply.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, i64, i32, vp]
+        L.b2f_column_run_backward.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, vp, vp, i64, i32, vp]
         L.b2f_wide_coupling_workspace.argtypes = [i64, i32, i32, i32]
         L.b2f_wide_coupling_workspace.restype = i64
         L.b2f_wide_coupling_forward.argtypes = [ctypes.POINTER(WideLayer), vp, vp, vp, i64, vp, i64, vp, i64, i32, vp]
@@ -283,3 +291,38 @@ def wide_coupling_backward(tkind, x2, gy, gld, W1, b1, W2, b2, n_bins=8, boundar
                                            ptr(gW2), ptr(gb2), B, ptr(keep), keep.numel() * 4, ptr(scratch),
                                            scratch.numel() * 4, flags, stream_ptr(x2.device)))
     return gx, gW1, gb1, gW2, gb2
+
+
+# ---- runs of per-column layers (csrc/b2f_colrun.cu) --------------------------------------------------------------------------
+def _col_ops(kinds, values, gvalues=None):
+    arr = (ColOp * len(kinds))()
+    for i, (k, v) in enumerate(zip(kinds, values)):
+        arr[i].kind = k
+        arr[i].value = None if v is None else v.data_ptr()
+        g = None if gvalues is None else gvalues[i]
+        arr[i].gvalue = None if g is None else g.data_ptr()
+    return arr
+
+
+def column_run_apply(kinds, values, x2: torch.Tensor):
+    """kinds: COL_* per op; values: the (D, 2) parameter tensor per op (None for flips).  Returns (y, log_det_sum[1])."""
+    x2 = require_cuda_f32(x2, 'column run input')
+    B, D = x2.shape
+    y = torch.empty_like(x2)
+    lds = torch.empty(1, device=x2.device, dtype=torch.float32)
+    with torch.cuda.device(x2.device):
+        check(lib().b2f_column_run_apply(_col_ops(kinds, values), len(kinds), ptr(x2), ptr(y), ptr(lds), B, D, stream_ptr(x2.device)))
+    return y, lds
+
+
+def column_run_backward(kinds, values, need_grad, x2, gy, g_lds):
+    """Returns (gx, [gvalue or None per op])."""
+    x2, gy = require_cuda_f32(x2, 'column run input'), require_cuda_f32(gy, 'upstream gradient')
+    B, D = x2.shape
+    gx = torch.empty_like(x2)
+    gvalues = [torch.empty_like(v) if (v is not None and ng) else None for v, ng in zip(values, need_grad)]
+    scratch = torch.empty(2 * D, device=x2.device, dtype=torch.float32)
+    with torch.cuda.device(x2.device):
+        check(lib().b2f_column_run_backward(_col_ops(kinds, values, gvalues), len(kinds), ptr(x2), ptr(gy), ptr(g_lds), ptr(gx),
+                                            ptr(scratch), B, D, stream_ptr(x2.device)))
+    return gx, gvalues

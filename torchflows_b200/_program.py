@@ -348,3 +348,42 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan), x2.detach(), want_y, True, want_log_prob, base_loc,
                              base_log_scale, flags)
     return y, ld, lp
+
+
+# ---- runs of per-column layers outside whole-flow programs (csrc/b2f_colrun.cu) ---------------------------------------------
+class ColumnRunFunction(torch.autograd.Function):
+    """y = run(x), log_det_sum (one float, the same log-determinant for every row) of a run of ElementwiseAffine / ActNorm /
+    ReversePermutation layers at an event size the whole-flow kernels do not take; one pass over the batch each way."""
+
+    @staticmethod
+    def forward(ctx, x2, kinds, *values):
+        y, lds = N.column_run_apply(kinds, values, x2)
+        ctx.kinds = kinds
+        ctx.n_values = len(values)
+        ctx.save_for_backward(x2, *[v for v in values if v is not None])
+        ctx.present = [v is not None for v in values]
+        return y, lds
+
+    @staticmethod
+    def backward(ctx, gy, g_lds):
+        saved = ctx.saved_tensors
+        x2, it = saved[0], iter(saved[1:])
+        values = [next(it) if p else None for p in ctx.present]
+        need = [ctx.needs_input_grad[2 + i] for i in range(ctx.n_values)]
+        if gy is None:
+            gy = torch.zeros_like(x2)
+        gx, gvalues = N.column_run_backward(ctx.kinds, values, need, x2, gy.contiguous(), g_lds)
+        return (gx, None) + tuple(gvalues)
+
+
+def run_column_ops(col_ops, x2: torch.Tensor):
+    """col_ops: [(N.COL_* kind, value tensor or None)] in application order.  Returns (y, log_det:(B,))."""
+    x2 = N.require_cuda_f32(x2, 'input')
+    log_det = None
+    for i in range(0, len(col_ops), N.COL_MAX_OPS):
+        chunk = col_ops[i:i + N.COL_MAX_OPS]
+        kinds = tuple(k for k, _ in chunk)
+        values = [v for _, v in chunk]
+        x2, lds = ColumnRunFunction.apply(x2, kinds, *values)
+        log_det = lds if log_det is None else log_det + lds
+    return x2, log_det.expand(x2.shape[0])

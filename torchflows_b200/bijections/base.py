@@ -120,12 +120,25 @@ class BijectiveComposition(Bijection):
         for layer in order:
             ops = layer.lower(direction)
             needs_data = direction == 'forward' and getattr(layer, 'needs_data_init', lambda: False)()
-            if ops is None or needs_data:
+            # per-column layers the whole-flow kernels do not take (very wide events) still fuse with their neighbours
+            # into one pass over the batch (csrc/b2f_colrun.cu)
+            col = getattr(layer, 'column_op', lambda d: None)(direction) if ops is None else None
+            if col is not None and not needs_data:
                 if current:
                     segments.append(('ops', current))
                     current = []
-                if ops is None:
+                if segments and segments[-1][0] == 'cols':
+                    segments[-1][1].append(col)
+                else:
+                    segments.append(('cols', [col]))
+            elif ops is None or needs_data:
+                if current:
+                    segments.append(('ops', current))
+                    current = []
+                if ops is None and col is None and not needs_data:
                     segments.append(('layer', layer))
+                elif ops is None:
+                    segments.append(('layer_init', layer))   # initialised from its own input, then applied by itself
                 else:
                     segments.append(('init', layer))   # lowered after its initialisation, see _run_layers
             else:
@@ -159,6 +172,20 @@ class BijectiveComposition(Bijection):
             if kind == 'ops':
                 x2, ld, _ = prog.run_program(item, x2)
                 add(ld)
+            elif kind == 'cols':
+                x2, ld = prog.run_column_ops(item, x2)
+                add(ld)
+            elif kind == 'layer_init':
+                item.data_init(x2.reshape(*batch_shape, *self.event_shape),
+                               reduce_fn=getattr(self, '_stats_reduce_fn', None))
+                col = getattr(item, 'column_op', lambda d: None)(direction)
+                if col is not None:
+                    x2, ld = prog.run_column_ops([col], x2)
+                    add(ld)
+                else:
+                    y, ld = item.forward(x2.reshape(*batch_shape, *self.event_shape), context=context, **kwargs)[:2]
+                    x2 = y.reshape(-1, self.n_dim)
+                    add(ld.reshape(-1))
             elif kind == 'init':
                 item.data_init(x2.reshape(*batch_shape, *self.event_shape),
                                reduce_fn=getattr(self, '_stats_reduce_fn', None))

@@ -391,6 +391,15 @@ class ElementwiseBijection(AutoregressiveBijection):
             return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
         return None
 
+    def column_op(self, direction: str):
+        """(kind, value) of this layer as one op of a per-column run (csrc/b2f_colrun.cu), for event sizes the whole-flow
+        kernels do not take; None if the layer is not a global-parameter affine map."""
+        tk = self._tkind(direction)
+        if self.use_global_parameters and tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV) and self.n_dim % 4 == 0 \
+                and self.value.is_cuda and self.value.dtype == torch.float32:
+            return (N.COL_AFFINE_FWD if tk == N.T_AFFINE_FWD else N.COL_AFFINE_INV, self.value)
+        return None
+
     def _run_direction(self, x, direction, context=None):
         if self.lower(direction) is not None:
             return self._run_fused(x, direction)

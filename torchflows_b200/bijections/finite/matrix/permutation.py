@@ -47,6 +47,10 @@ class ReversePermutationMatrix(PermutationMatrix):
             return None          # very wide events: plain index flip (InvertibleMatrix.forward / inverse)
         return [prog.LoweredOp(kind=N.OP_FLIP, owner=self)]
 
+    def column_op(self, direction: str):
+        """As one op of a per-column run (csrc/b2f_colrun.cu) when the event is too wide for the whole-flow kernels."""
+        return (N.COL_FLIP, None) if self.n_dim % 4 == 0 else None
+
     def project_flat(self, x_flat: torch.Tensor, context_flat: torch.Tensor = None) -> torch.Tensor:
         return torch.flip(x_flat, dims=(-1,))       # same map as indexing with the reversed permutation, cheap backward
 
