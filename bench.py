@@ -471,6 +471,53 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def wide_tensor_roofline(torch, flow, x, dev, reps=5):
+    """Tensor-pipe roofline of the wide-conditioner layer (csrc/b2f_wide.cu), timed with CUDA events around the C-ABI calls
+    of ONE coupling layer on this workload's rows: forward = conditioner GEMMs + spline epilogue, backward = recompute +
+    spline backward + the four gradient GEMMs.  achieved = ALGORITHMIC flops (2 B (Dh H + H 23 Dh) forward, twice that
+    for the backward: the recompute GEMM is our choice, not the algorithm's) / duration; peak = the measured sustained bf16
+    rate / 2 (kind::tf32 runs at half the bf16 rate)."""
+    from torchflows_b200 import _native as N
+    layer = next(l for l in flow.bijection.layers if getattr(l, '_wide', False))
+    seq = layer.conditioner_transform.sequential
+    W1, b1, W2, b2 = (t.detach() for t in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias))
+    B, D = x.shape
+    Dh, H = D // 2, W1.shape[0]
+    gy, gld = torch.randn_like(x), torch.randn(B, device=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('bf16_tflops_sustained', 1400.0)) / 2
+    src = 'measured bf16_tflops_sustained / 2 (MEASURED_PEAKS.json)' if 'bf16_tflops_sustained' in peaks else \
+        'fallback 1400 / 2 (B200_PROFILING.md)'
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_f = timed(lambda: N.wide_coupling_forward(N.T_RQ_FWD, x, W1, b1, W2, b2))
+    ms_b = timed(lambda: N.wide_coupling_backward(N.T_RQ_FWD, x, gy, gld, W1, b1, W2, b2))
+    flops_f = 2.0 * B * (Dh * H + H * Dh * 23)
+    out = {'bound': 'tensor', 'unit': 'TFLOP/s', 'peak': peak, 'peak_source': src, 'dtype': 'tf32 (fp32 accumulate)',
+           'forward': {'kernel': 'b2f_wide_coupling_forward (wide_gemm_kernel: hidden GEMM, output GEMM + spline epilogue)',
+                       'launch_ms': ms_f, 'algorithmic_gflop': flops_f / 1e9, 'achieved': flops_f / (ms_f * 1e-3) / 1e12},
+           'backward': {'kernel': 'b2f_wide_coupling_backward (recompute GEMM + spline backward epilogue, wgrad, dgrad)',
+                        'launch_ms': ms_b, 'algorithmic_gflop': 2 * flops_f / 1e9, 'executed_gflop': 3 * flops_f / 1e9,
+                        'achieved': 2 * flops_f / (ms_b * 1e-3) / 1e12, 'executed': 3 * flops_f / (ms_b * 1e-3) / 1e12}}
+    out['achieved'] = 3 * flops_f / ((ms_f + ms_b) * 1e-3) / 1e12
+    out['frac'] = out['achieved'] / peak
+    return out
+
+
 def fit_path(flow):
     """Which kernels a Flow.fit step of this flow runs on, read off the layers' own dispatch flags."""
     layers = [l for l in flow.bijection.layers if hasattr(l, '_fusable') and hasattr(l, 'coupling')]
@@ -533,9 +580,14 @@ def fit_probe(torch, dist, dev, rank, world, workload, steps=5, warmup=3, rows=0
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step, ms_ar = float(ms[0]), float(ms[1])
     path = fit_path(flow)
+    tensor = None
+    if workload == 'w1024fit' and rank == 0:
+        tensor = wide_tensor_roofline(torch, flow, x, dev)
     out = {'workload': f'CouplingRQNSF n_dim={D} n_hidden={H}, {per_gpu} rows per GPU', 'ms_per_step': ms_step,
            'samples_per_s': world * per_gpu / (ms_step * 1e-3), 'trainable_parameters': n_params, 'path': path,
            'allreduce_bytes_per_step': nbytes, 'allreduce_alone_ms': ms_ar, 'final_loss': float(loss)}
+    if tensor is not None:
+        out['tensor_roofline'] = tensor
     del flow, x
     torch.cuda.empty_cache()
     return out

@@ -119,6 +119,20 @@ int b2f_flow_apply(const b2f_op_t *ops, int32_t n_ops, const float *x, float *y,
                    const float *base_loc, const float *base_log_scale, int64_t B, int32_t D, int32_t flags,
                    void *stream);
 
+/* Flow.sample with the base draws made by the library (flows.py:660-713, base_distributions/gaussian.py:41-44): the
+ * program `ops` (inverse direction) is applied to z = base_loc + exp(base_log_scale) * n, n = standard normals from a
+ * counter-based Philox4x32-10 stream (csrc/b2f_philox.cuh): flat element row * D + column is lane e % 4 of counter
+ * e / 4 + offset under the 64-bit key `seed`.  Programs of the spline tensor-core kernel (B2F_KERNEL_TCQ) draw their
+ * tiles in registers -- the noise is never written to or read from memory, a sample costs 4 D bytes of traffic --; every
+ * other program materialises the same stream into noise_scratch:(B,D) (required then) and runs as b2f_flow_apply.
+ * With B2F_FLOW_LOGP_OF_INPUT, log_prob = base density of z + log_det as Flow.sample(return_log_prob=True) returns. */
+int b2f_flow_sample(const b2f_op_t *ops, int32_t n_ops, float *y, float *log_det, float *log_prob, const float *base_loc,
+                    const float *base_log_scale, float *noise_scratch, int64_t B, int32_t D, int32_t flags, uint64_t seed,
+                    uint64_t offset, void *stream);
+/* The same stream materialised: out:(n_rows, D) = loc + exp(log_scale) * n  (DiagonalGaussian.sample). */
+int b2f_philox_normal(float *out, int64_t n_rows, int32_t D, const float *loc, const float *log_scale, uint64_t seed,
+                      uint64_t offset, void *stream);
+
 /* b2f_flow_apply for a training step: additionally writes, for every COUPLING / MADE / MADE_SEQ op in order, the
  * activations as they ENTER that layer into `workspace` ([layer][B][D] floats, b2f_flow_backward_workspace() bytes) --
  * exactly what b2f_flow_backward would otherwise recompute.  *saved = 1 if the kernel that took the program wrote them

@@ -80,6 +80,9 @@ def lib():
         L.b2f_transformer_backward.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, f32, i32, vp]
         L.b2f_column_stats.argtypes = [vp, vp, vp, i64, i32, vp]
         L.b2f_debug_umma_gemm.argtypes = [vp, vp, vp, i32, i32, vp]
+        u64 = ctypes.c_uint64
+        L.b2f_flow_sample.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, u64, u64, vp]
+        L.b2f_philox_normal.argtypes = [vp, i64, i32, vp, vp, u64, u64, vp]
         L.b2f_column_run_apply.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, i64, i32, vp]
         L.b2f_column_run_backward.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, vp, vp, i64, i32, vp]
         L.b2f_wide_coupling_workspace.argtypes = [i64, i32, i32, i32]
@@ -326,3 +329,33 @@ def column_run_backward(kinds, values, need_grad, x2, gy, g_lds):
         check(lib().b2f_column_run_backward(_col_ops(kinds, values, gvalues), len(kinds), ptr(x2), ptr(gy), ptr(g_lds), ptr(gx),
                                             ptr(scratch), B, D, stream_ptr(x2.device)))
     return gx, gvalues
+
+
+# ---- base draws made by the library (csrc/b2f_philox.cuh) -------------------------------------------------------------------
+def philox_normal(n_rows: int, D: int, device, seed: int, offset: int, loc=None, log_scale=None) -> torch.Tensor:
+    """(n_rows, D) draws loc + exp(log_scale) * n from the counter-based stream (seed, offset)."""
+    out = torch.empty((n_rows, D), device=device, dtype=torch.float32)
+    with torch.cuda.device(device):
+        check(lib().b2f_philox_normal(ptr(out), n_rows, D, ptr(loc), ptr(log_scale), seed, offset, stream_ptr(device)))
+    return out
+
+
+def flow_sample(ops: Sequence[dict], B: int, D: int, device, want_log_prob=False, base_loc=None, base_log_scale=None, flags=0,
+                seed=0, offset=0, in_kernel=False):
+    """b2f_flow_sample: (x:(B, D), log_prob | None).  in_kernel: the program is laid out for the spline tensor-core kernel,
+    which draws its tiles in registers; every other program gets a (B, D) scratch for the materialised stream."""
+    if not torch.device(device).type == 'cuda':
+        raise B2FError(f'sampling runs only as sm_100a kernels (no CPU fallback); got device {device}')
+    y = torch.empty((B, D), device=device, dtype=torch.float32)
+    lp = torch.empty(B, device=device, dtype=torch.float32) if want_log_prob else None
+    arr = make_ops(ops)
+    with torch.cuda.device(device):
+        scratch = None if in_kernel else torch.empty((B, D), device=device, dtype=torch.float32)
+        rc = lib().b2f_flow_sample(arr, len(ops), ptr(y), None, ptr(lp), ptr(base_loc), ptr(base_log_scale), ptr(scratch), B, D,
+                                   flags, seed, offset, stream_ptr(device))
+        if rc == -2 and scratch is None:        # B2F_ERR_UNSUPPORTED: the kernel declined the program after all
+            scratch = torch.empty((B, D), device=device, dtype=torch.float32)
+            rc = lib().b2f_flow_sample(arr, len(ops), ptr(y), None, ptr(lp), ptr(base_loc), ptr(base_log_scale), ptr(scratch), B,
+                                       D, flags, seed, offset, stream_ptr(device))
+        check(rc)
+    return y, lp

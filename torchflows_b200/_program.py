@@ -350,6 +350,30 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     return y, ld, lp
 
 
+# ---- Flow.sample with the library's own base draws (b2f_flow_sample, csrc/b2f_philox.cuh) -----------------------------------
+def next_noise_stream(device=None, n_elements: int = 0):
+    """(seed, offset) of the next base draws: a fresh 62-bit Philox key from torch's CPU generator per call -- the stream the
+    reference itself consumes (gaussian.py:42 draws torch.randn on the CPU) -- so torch.manual_seed makes sampling
+    reproducible and re-seeding restarts it; no device synchronisation."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item()), 0
+
+
+def run_sample_program(ops: Sequence[LoweredOp], B: int, D: int, device, want_log_prob=False, base_loc=None,
+                       base_log_scale=None, seed=None, offset=0):
+    """Inverse-direction program applied to base draws made by the library: returns (x:(B, D), log_prob or None) where
+    log_prob = base density of the draw + log_det (Flow.sample(return_log_prob=True), flows.py:710-712).  Inference only."""
+    ops = list(ops)
+    flags = _MODE_FLAGS[_mode] | N.FLOW_LOGP_OF_INPUT
+    if seed is None:
+        seed, offset = next_noise_stream(device, B * D)
+    plan = None
+    if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
+            and _tcq.eligible(ops, D)):
+        plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
+    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan), B, D, device, want_log_prob, base_loc, base_log_scale, flags,
+                         seed, offset, in_kernel=plan is not None)
+
+
 # ---- runs of per-column layers outside whole-flow programs (csrc/b2f_colrun.cu) ---------------------------------------------
 class ColumnRunFunction(torch.autograd.Function):
     """y = run(x), log_det_sum (one float, the same log-determinant for every row) of a run of ElementwiseAffine / ActNorm /

@@ -29,7 +29,23 @@ class DiagonalGaussian(torch.distributions.Distribution, nn.Module):
 
     def sample(self, sample_shape: torch.Size = torch.Size()) -> torch.Tensor:
         """Noise is drawn directly on the distribution's device (the reference draws on the CPU and copies,
-        gaussian.py:42; same distribution, different random stream)."""
+        gaussian.py:42; same distribution, different random stream): on a GPU by the library's Philox kernel, with trainable
+        base parameters under autograd (reparameterised draw) or on the CPU by torch.randn."""
+        if (self.loc.is_cuda and self.loc.dtype == torch.float32
+                and not (torch.is_grad_enabled() and (self.loc.requires_grad or self.log_scale.requires_grad))):
+            # the library's counter-based stream (csrc/b2f_philox.cuh, keyed by torch's seed): the same draws Flow.sample's
+            # fused kernels make in registers
+            from torchflows_b200 import _native as N
+            from torchflows_b200 import _program as prog
+            n, D = 1, 1
+            for d in sample_shape:
+                n *= int(d)
+            for d in self.event_shape:
+                D *= int(d)
+            seed, offset = prog.next_noise_stream(self.loc.device, n * D)
+            z = N.philox_normal(n, D, self.loc.device, seed, offset, self.loc.detach().reshape(-1).contiguous(),
+                                self.log_scale.detach().reshape(-1).contiguous())
+            return z.reshape(*sample_shape, *self.event_shape)
         noise = torch.randn(*sample_shape, *self.event_shape, device=self.loc.device, dtype=self.loc.dtype)
         return self.loc + noise * self.scale
 

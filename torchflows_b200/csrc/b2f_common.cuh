@@ -30,6 +30,13 @@ inline int check_launch(const char* what) {
 // the limit under it.  Per device; the attribute call is skipped when the limit is already high enough.
 int raise_smem_limit(const void* kernel, size_t bytes);   // b2f_api.cu; returns a cudaError_t value
 
+// in-kernel base draws of b2f_flow_sample (csrc/b2f_philox.cuh)
+struct TcqNoise {
+    unsigned long long seed, offset;
+    const float* base_loc;
+    const float* base_log_scale;
+};
+
 inline int params_per_element(int tkind, int n_bins) {
     switch (tkind) {
         case B2F_T_SHIFT_ADD: case B2F_T_SHIFT_SUB: return 1;

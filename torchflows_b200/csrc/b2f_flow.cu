@@ -202,7 +202,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
                        const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                        void* stream, float* ws);   // b2f_flow_tc.cu (ws: optional save area for the layer inputs)
 int try_launch_flow_tcq(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
-                        int64_t B, int32_t D, int32_t flags, void* stream);   // b2f_flow_tcq.cu
+                        int64_t B, int32_t D, int32_t flags, void* stream, const TcqNoise* noise);   // b2f_flow_tcq.cu
 int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                          const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                          void* stream);  // b2f_flow_rows.cu
@@ -225,7 +225,7 @@ static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, f
         for (int i = 0; i < n_ops; ++i)
             if (ops[i].kind >= B2F_OP_COUPLING && (ops[i].tkind == B2F_T_RQ_FWD || ops[i].tkind == B2F_T_RQ_INV)) has_rq = true;
         if (has_rq && !ws) {       // programs laid out for the second-generation spline kernel (B2F_FLAG_TCQ_OPERANDS)
-            const int rc = try_launch_flow_tcq(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream);
+            const int rc = try_launch_flow_tcq(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream, nullptr);
             if (rc == 1) last_flow_kernel() = B2F_KERNEL_TCQ;
             if (rc != 0) return rc == 1 ? B2F_OK : rc;
         }
@@ -317,4 +317,26 @@ extern "C" int b2f_flow_apply_saving(const b2f_op_t* ops, int32_t n_ops, const f
     *saved = 0;
     return flow_apply_impl(ops, n_ops, x, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream,
                            (float*)workspace, saved);
+}
+
+extern "C" int b2f_philox_normal(float* out, int64_t n_rows, int32_t D, const float* loc, const float* log_scale, uint64_t seed,
+                                 uint64_t offset, void* stream);
+
+extern "C" int b2f_flow_sample(const b2f_op_t* ops, int32_t n_ops, float* y, float* log_det, float* log_prob, const float* base_loc,
+                               const float* base_log_scale, float* noise_scratch, int64_t B, int32_t D, int32_t flags,
+                               uint64_t seed, uint64_t offset, void* stream) {
+    if (B == 0 && n_ops >= 0 && D > 0) return B2F_OK;
+    if (!ops || n_ops < 0 || D <= 0 || B < 0) return fail(B2F_ERR_INVALID, "b2f_flow_sample: bad arguments");
+    if (n_ops > B2F_MAX_OPS) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_sample: %d ops > B2F_MAX_OPS", n_ops);
+    if (D % 4 != 0 && !noise_scratch) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_sample: this shape needs a noise scratch buffer");
+    // programs of the spline tensor-core kernel draw their tiles in registers: the noise never exists in memory
+    TcqNoise nz;
+    nz.seed = seed; nz.offset = offset; nz.base_loc = base_loc; nz.base_log_scale = base_log_scale;
+    int rc = try_launch_flow_tcq(ops, n_ops, nullptr, y, log_det, log_prob, B, D, flags, stream, &nz);
+    if (rc == 1) { last_flow_kernel() = B2F_KERNEL_TCQ; return B2F_OK; }
+    if (rc != 0) return rc;
+    // every other program: the same stream, materialised once, then the ordinary launch
+    if (!noise_scratch) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_sample: this program needs a noise scratch buffer of B * D floats");
+    if ((rc = b2f_philox_normal(noise_scratch, B, D, base_loc, base_log_scale, seed, offset, stream)) != B2F_OK) return rc;
+    return flow_apply_impl(ops, n_ops, noise_scratch, y, log_det, log_prob, base_loc, base_log_scale, B, D, flags, stream, nullptr, nullptr);
 }

@@ -28,6 +28,7 @@
 #include <algorithm>
 
 #include "b2f_flow_device.cuh"
+#include "b2f_philox.cuh"
 #include "b2f_rqfast.cuh"
 #include "b2f_umma.cuh"
 
@@ -64,6 +65,11 @@ struct QArgs {
     float* log_det;
     float* log_prob;
     const float* prog;      // program blob: [4 ints][4 consts][D x (fin_a, fin_b)][D x (in_a, in_b)]
+    // Flow.sample with in-kernel noise (b2f_flow_sample): the input tile is drawn from the Philox stream instead of loaded
+    int philox;
+    unsigned long long seed, offset;
+    const float* base_loc;          // nullable: standard normal
+    const float* base_log_scale;
 };
 
 enum { QB_XA_FULL = 0, QB_XB_FULL, QB_EARLY_FREE, QB_TILE_DONE, QB_W1_FULL, QB_W1_EMPTY, QB_A1_READY, QB_D1_FULL, QB_A2_FULL,
@@ -260,7 +266,7 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
         if (lane == 0) {
             auto is_full = [&](int t) { return A.use_tma && ((long long)t * 128 + 128 <= A.B); };
             auto load_half = [&](int t, int h, uint32_t buf, uint64_t* bar) {
-                if (is_full(t)) {
+                if (is_full(t) && !A.philox) {
                     umma::mbar_arrive_expect_tx(bar, 128u * Dh * 4);
                     q_tma_load4(reinterpret_cast<uint8_t*>(s.xt[0]) + buf * half_bytes, &map_x, 0, 0, h * (Dh / 4), t * 16, bar);
                 } else {
@@ -392,17 +398,40 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
         for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++tc) {
             const long long row0 = (long long)tile * 128;
             const int rows = (int)min(128LL, A.B - row0);
-            const bool full = A.use_tma && rows == 128;
+            const bool full = A.use_tma && rows == 128;      // the tile leaves through the TMA engine
+            const bool tma_in = full && !A.philox;           // ... and arrived through it
             bool have_b = false;                           // waited for the second half of this tile yet?
             umma::mbar_wait(&s.bars[QB_XA_FULL], tc & 1);
-            if (!full || lp_in) { umma::mbar_wait(&s.bars[QB_XB_FULL], tc & 1); have_b = true; }
-            if (!full) {
+            if (!tma_in || lp_in) { umma::mbar_wait(&s.bars[QB_XB_FULL], tc & 1); have_b = true; }
+            if (!tma_in) {
                 const bool live = m8 < rows;
-                const float4* src = reinterpret_cast<const float4*>(A.x + (row0 + m8) * D);
-                for (int kc = kq; kc < D / 4; kc += 4) {
-                    const float4 v = live ? __ldg(src + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
-                    q_sts128((xt0 + (hf ^ swap) * half_bytes) + row_off + k4 * 128, v);
+                if (A.philox) {
+                    // base draws of this tile: z = loc + exp(log_scale) n, n = counter-based normals (b2f_philox.cuh); the
+                    // noise matrix never exists in memory (gaussian.py:41-44 + flows.py:693 of the reference)
+                    const unsigned long long g0 = (unsigned long long)(row0 + m8) * (unsigned long long)(D / 4);
+                    for (int kc = kq; kc < D / 4; kc += 4) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) {
+                            v = philox::normal4(g0 + kc, A.seed, A.offset);
+                            if (A.base_log_scale) {
+                                const float4 ls = __ldg(reinterpret_cast<const float4*>(A.base_log_scale) + kc);
+                                v.x *= __expf(ls.x); v.y *= __expf(ls.y); v.z *= __expf(ls.z); v.w *= __expf(ls.w);
+                            }
+                            if (A.base_loc) {
+                                const float4 lc = __ldg(reinterpret_cast<const float4*>(A.base_loc) + kc);
+                                v.x += lc.x; v.y += lc.y; v.z += lc.z; v.w += lc.w;
+                            }
+                        }
+                        const uint32_t hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
+                        q_sts128((xt0 + (hf ^ swap) * half_bytes) + row_off + k4 * 128, v);
+                    }
+                } else {
+                    const float4* src = reinterpret_cast<const float4*>(A.x + (row0 + m8) * D);
+                    for (int kc = kq; kc < D / 4; kc += 4) {
+                        const float4 v = live ? __ldg(src + kc) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const uint32_t hf = (4 * kc) >= Dh, k4 = kc - hf * (Dh / 4);
+                        q_sts128((xt0 + (hf ^ swap) * half_bytes) + row_off + k4 * 128, v);
+                    }
                 }
                 q_epi_sync();
             }
@@ -563,10 +592,11 @@ static bool make_tile_map(CUtensorMap* map, const float* base, long long B, int 
 
 // Returns 1 if the kernel was launched, 0 if the program is not for this kernel (caller falls through), < 0 on error.
 int try_launch_flow_tcq(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
-                        int64_t B, int32_t D, int32_t flags, void* stream) {
+                        int64_t B, int32_t D, int32_t flags, void* stream, const TcqNoise* noise) {
     if (getenv("B2F_DISABLE_TCQ") || getenv("B2F_DISABLE_TC") || (flags & B2F_FLOW_MODE_PRECISE)) return 0;
     if (D % 32 != 0 || D < 32 || D > 256) return 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) || (y && (reinterpret_cast<uintptr_t>(y) & 15))) return 0;
+    if ((!noise && (reinterpret_cast<uintptr_t>(x) & 15)) || (y && (reinterpret_cast<uintptr_t>(y) & 15))) return 0;
+    if (noise && ((reinterpret_cast<uintptr_t>(noise->base_loc) | reinterpret_cast<uintptr_t>(noise->base_log_scale)) & 15)) return 0;
     QArgs A;
     memset(&A, 0, sizeof(A));
     int flip = 0, K2max = 8;
@@ -607,7 +637,11 @@ int try_launch_flow_tcq(const b2f_op_t* ops, int32_t n_ops, const float* x, floa
     memset(&map_x, 0, sizeof(map_x));
     memset(&map_y, 0, sizeof(map_y));
     A.use_tma = getenv("B2F_TCQ_NO_TMA") ? 0 : 1;
-    if (A.use_tma && !make_tile_map(&map_x, x, B, D)) A.use_tma = 0;
+    if (noise) {
+        A.philox = 1; A.seed = noise->seed; A.offset = noise->offset;
+        A.base_loc = noise->base_loc; A.base_log_scale = noise->base_log_scale;
+    }
+    if (A.use_tma && !noise && !make_tile_map(&map_x, x, B, D)) A.use_tma = 0;
     if (A.use_tma && y && !make_tile_map(&map_y, y, B, D)) A.use_tma = 0;
     int dev = 0, n_sm = 148;
     cudaGetDevice(&dev);

@@ -663,6 +663,21 @@ class Flow(BaseFlow):
             sample_shape = (sample_shape,)
         sample_shape = tuple(sample_shape)
         if context is None:
+            grad_needed = (not no_grad) and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+            dev = self.get_device()
+            if not grad_needed and dev.type == 'cuda' and self._fusable_base():
+                # inference: the base draws are made by the library (counter-based Philox stream keyed by torch's seed);
+                # spline coupling programs draw them inside the kernel, the noise never touches memory
+                ops = self.bijection.lower('inverse')
+                if ops is not None and len(ops) <= N.MAX_OPS:
+                    n = 1
+                    for d in sample_shape:
+                        n *= int(d)
+                    with torch.no_grad():
+                        x2, lp = prog.run_sample_program(ops, n, self.event_size, dev, want_log_prob=return_log_prob,
+                                                         base_loc=self.base.loc, base_log_scale=self.base.log_scale)
+                    x = x2.reshape(*sample_shape, *self.event_shape)
+                    return (x, lp.reshape(sample_shape)) if return_log_prob else x
             z = self.base_sample(sample_shape=sample_shape)
             return self._sample_from_base(z, no_grad, return_log_prob)
         # context-conditioned (flows.py:680-692): either one context per sampled element, or one context tensor per
