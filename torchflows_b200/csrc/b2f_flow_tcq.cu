@@ -409,6 +409,8 @@ flow_tcq_kernel(const __grid_constant__ QArgs A, const __grid_constant__ CUtenso
                     // base draws of this tile: z = loc + exp(log_scale) n, n = counter-based normals (b2f_philox.cuh); the
                     // noise matrix never exists in memory (gaussian.py:41-44 + flows.py:693 of the reference)
                     const unsigned long long g0 = (unsigned long long)(row0 + m8) * (unsigned long long)(D / 4);
+                    // D / 16 >= 2 independent Philox chains per thread: unrolled so that their 10 dependent rounds overlap
+#pragma unroll 4
                     for (int kc = kq; kc < D / 4; kc += 4) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (live) {

@@ -32,9 +32,12 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint64_t counter, uint64_
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u1 = fmaf((float)(a >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);     // (k + 0.5) 2^-24
     const float th = (float)(b >> 8) * (6.283185307179586f * 5.9604644775390625e-08f);
-    const float r = sqrtf(-2.0f * __logf(u1));
-    float s, c;
-    __sincosf(th, &s, &c);
+    // SFU forms: lg2 / sqrt / sin / cos .approx (theta in [0, 2 pi): the range the approximations are specified for)
+    float l2, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l2 * -1.3862943611198906f));      // -2 ln u1 = -2 ln2 * lg2 u1
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(th));
     n0 = r * c;
     n1 = r * s;
 }
