@@ -34,10 +34,10 @@ WORKLOADS = {
 
 
 # the kernel each workload's log_prob launch dispatches to (b2f_flow_apply: csrc/b2f_flow.cu)
-KERNELS = {'q256': 'b2f::flow_tcq_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_rows_kernel',
+KERNELS = {'q256': 'b2f::flow_tcq_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_tca_kernel',
            'm128': 'b2f::flow_rows_kernel'}
 KERNEL_IDS = {0: 'none', 1: 'generic (b2f_flow.cu)', 2: 'tc (b2f_flow_tc.cu)', 3: 'rows (b2f_flow_rows.cu)',
-              4: 'tcq (b2f_flow_tcq.cu)'}
+              4: 'tcq (b2f_flow_tcq.cu)', 5: 'tca (b2f_flow_tca.cu)'}
 
 
 def algorithmic_bytes(D):
@@ -434,7 +434,7 @@ def run_ours(args):
                 'note': 'pinned host memory <-> HBM over PCIe, both directions concurrently; copies_only_ms is the same '
                         'traffic without any kernel (max over ranks): the end-to-end step is bound by the host side of the '
                         'box (one NUMA node shared by all ranks), not by the GPU'},
-        'gpu_launches': (2 if k_s == N_.KERNEL_TCQ else 3) * args.steps,       # log_prob; sample (+ the noise kernel when the
+        'gpu_launches': (2 if k_s in (N_.KERNEL_TCQ, N_.KERNEL_TCA) else 3) * args.steps,       # log_prob; sample (+ the noise kernel when the
                                                                                 # program's kernel does not draw in registers)
         'dispatch': {'log_prob': KERNEL_IDS.get(k_lp_full, str(k_lp_full)), 'sample': KERNEL_IDS.get(k_s, str(k_s)),
                      'note': 'kernel each call of the timed loop ran on (b2f_last_flow_kernel): 100 % on the fused path'},

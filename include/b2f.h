@@ -88,6 +88,20 @@ enum b2f_op_kind {
                                          {sum of elementwise log-dets, base-density constant, 0, 0}, [D][2] final affine per physical
                                          column, [D][2] (exp(-log_scale), -loc*exp(-log_scale)) of the base density per column */
 
+#define B2F_FLAG_TCA_OPERANDS 16    /* op flag (COUPLING, affine or shift), set on EVERY coupling op of a program made of
+                                       ELEMENTWISE / FLIP / COUPLING ops: the program is laid out for the multi-tile affine kernel
+                                       (csrc/b2f_flow_tca.cu; layout produced by torchflows_b200/_tca.py):
+                                       p[4] = layer blob (fp32 words, 16-byte aligned), Dh = D/2, N1 = roundup(H, 16),
+                                              K2 = roundup(H + 1, 8), N2 = roundup(Dh * P, 16), P = 2 (affine) or 1 (shift):
+                                         [0,8)  int32 header: magic 'BTCA', physical source half, 1 if the source half must be
+                                                materialised, H, N1, K2, Dh, P | inverse << 8
+                                         W1hi, W1lo  canonical [N1 x Dh] each: tf32 hi / lo parts, columns in PHYSICAL order
+                                         b1     32 floats (zero padded)
+                                         W2hi, W2lo  canonical [N2 x K2] each: row = element * P + parameter (elements in PHYSICAL
+                                                order of the target half), K column H = the bias
+                                         tgt    [Dh][8] and src [Dh][2] as for B2F_FLAG_TCQ_OPERANDS
+                                       p[5] (first coupling op) = program blob, as for B2F_FLAG_TCQ_OPERANDS */
+
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
     int32_t tkind;    /* enum b2f_transformer */
@@ -258,6 +272,7 @@ int32_t b2f_abi_version(void);
 #define B2F_KERNEL_TC 2
 #define B2F_KERNEL_ROWS 3
 #define B2F_KERNEL_TCQ 4 /* csrc/b2f_flow_tcq.cu: spline coupling programs laid out with B2F_FLAG_TCQ_OPERANDS */
+#define B2F_KERNEL_TCA 5 /* csrc/b2f_flow_tca.cu: affine / shift coupling programs laid out with B2F_FLAG_TCA_OPERANDS */
 int32_t b2f_last_flow_kernel(void);
 
 #ifdef __cplusplus

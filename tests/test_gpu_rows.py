@@ -9,6 +9,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+@pytest.fixture(autouse=True)
+def _without_the_multi_tile_affine_kernel():
+    """These tests pin the dispatch of the older kernels; affine / shift coupling programs would otherwise go to the
+    multi-tile tensor-core kernel (csrc/b2f_flow_tca.cu, covered by tests/test_gpu_tca.py)."""
+    os.environ['B2F_DISABLE_TCA'] = '1'
+    yield
+    os.environ.pop('B2F_DISABLE_TCA', None)
+
+
 
 def _run(flow, x, z):
     with torch.no_grad():

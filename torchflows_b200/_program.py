@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _native as N
-from . import _tcq
+from . import _tca, _tcq
 
 
 @dataclass
@@ -173,7 +173,7 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
 
 
 def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None,
-             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None):
+             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None, tca_plan=None):
     """b2f_op descriptors of a program.  ``tcq_plan``: the program is laid out for the second-generation spline kernel
     (csrc/b2f_flow_tcq.cu): every coupling op carries its blob in p[4], the first one the program blob in p[5]."""
     out = []
@@ -186,6 +186,10 @@ def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.
         elif tcq_plan is not None and op.kind == N.OP_COUPLING:
             p = p[:4] + [tcq_plan.layer_blobs[n_coupling], tcq_plan.program_blob if n_coupling == 0 else None]
             flags |= N.FLAG_TCQ_OPERANDS
+            n_coupling += 1
+        elif tca_plan is not None and op.kind == N.OP_COUPLING:       # multi-tile affine kernel (csrc/b2f_flow_tca.cu)
+            p = p[:4] + [tca_plan.layer_blobs[n_coupling], tca_plan.program_blob if n_coupling == 0 else None]
+            flags |= N.FLAG_TCA_OPERANDS
             n_coupling += 1
         elif D is not None and grads is None and tc_eligible(op, D):
             w1c, w2c = tc_operands(op, flipped, D)
@@ -345,9 +349,17 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
             and _tcq.eligible(ops, D)):
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
-    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan), x2.detach(), want_y, True, want_log_prob, base_loc,
-                             base_log_scale, flags)
+    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=_tca_plan(ops, D, base_loc, base_log_scale, flags)),
+                             x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
     return y, ld, lp
+
+
+def _tca_plan(ops, D, base_loc, base_log_scale, flags):
+    """Operand plan of the multi-tile affine kernel if the program is one it takes, else None."""
+    if (flags & N.FLOW_MODE_PRECISE) or os.environ.get('B2F_DISABLE_TCA') or os.environ.get('B2F_DISABLE_TC') \
+            or not _tca.eligible(ops, D):
+        return None
+    return _tca.cached_plan(ops, D, base_loc, base_log_scale)
 
 
 # ---- Flow.sample with the library's own base draws (b2f_flow_sample, csrc/b2f_philox.cuh) -----------------------------------
@@ -370,8 +382,9 @@ def run_sample_program(ops: Sequence[LoweredOp], B: int, D: int, device, want_lo
     if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
             and _tcq.eligible(ops, D)):
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
-    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan), B, D, device, want_log_prob, base_loc, base_log_scale, flags,
-                         seed, offset, in_kernel=plan is not None)
+    tca = _tca_plan(ops, D, base_loc, base_log_scale, flags) if plan is None else None
+    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=tca), B, D, device, want_log_prob, base_loc, base_log_scale,
+                         flags, seed, offset, in_kernel=plan is not None or tca is not None)
 
 
 # ---- runs of per-column layers outside whole-flow programs (csrc/b2f_colrun.cu) ---------------------------------------------
