@@ -7,6 +7,7 @@ per-column affine maps applied where a column is touched anyway, the permutation
 conditioner layers as UMMA operands -- here split into tf32 hi / lo parts, because affine flows need fp32-faithful
 conditioners: every product is evaluated as hi*hi + lo*hi + hi*lo on the tensor cores.
 """
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -19,9 +20,11 @@ HDR = 8
 
 
 def eligible(ops: Sequence, D: int) -> bool:
-    """Mirror of try_launch_flow_tca's conditions: affine / shift coupling programs, D a multiple of 16 in [32, 128],
+    """Mirror of try_launch_flow_tca's conditions: affine / shift coupling programs, D a multiple of 32 in [32, 128],
     hidden width <= 31, both halves transformed, even number of flips."""
-    if D % 16 != 0 or D < 32 or D > 128 or len(ops) > N.MAX_OPS:
+    if D % 32 != 0 or D < 32 or D > 128 or len(ops) > N.MAX_OPS:
+        return False
+    if D > 64 and not os.environ.get('B2F_TCA_ANY'):      # fewer than four tile pipelines fit: the rows kernel is faster
         return False
     flip, written, n_c = False, set(), 0
     for op in ops:
@@ -93,7 +96,7 @@ def build_plan(ops: Sequence, D: int, base_loc: Optional[torch.Tensor], base_log
                 bb = b2.reshape(Dh, P)
                 if flip:                      # physical order of the source / target columns is the reverse of the logical one
                     W1, w2, bb = W1.flip(1), w2.flip(0), bb.flip(0)
-                layer = dict(src_half=s, tgt_half=t, src_pass=pending[s], H=H, P=P, tkind=op.tkind,
+                layer = dict(src_half=s, tgt_half=t, src_pass=pending[s], has_pre=pending[t], H=H, P=P, tkind=op.tkind,
                              src_a=A[half[s]].clone(), src_b=B[half[s]].clone(),
                              pre_a=A[half[t]].clone(), pre_b=B[half[t]].clone(),
                              post_a=torch.ones(Dh, **f32), post_b=torch.zeros(Dh, **f32), W1=W1, b1=b1, w2=w2, bb=bb)
@@ -119,13 +122,34 @@ def build_plan(ops: Sequence, D: int, base_loc: Optional[torch.Tensor], base_log
             else:
                 layer['fin_a'] = torch.zeros(Dh, **f32)
                 layer['fin_b'] = torch.zeros(Dh, **f32)
-        for layer in layers:
+        for i, layer in enumerate(layers):
             H, P = layer['H'], layer['P']
             N1 = (H + 15) // 16 * 16
             K2 = (H + 1 + 7) // 8 * 8
             N2 = (Dh * P + 15) // 16 * 16
             inverse = layer['tkind'] in (N.T_AFFINE_INV, N.T_SHIFT_SUB)
-            hdr = torch.tensor([MAGIC, layer['src_half'], int(layer['src_pass']), H, N1, K2, Dh, P | (int(inverse) << 8)],
+            w2, bb = layer['w2'].clone(), layer['bb'].clone()
+            post_a, post_b = layer['post_a'], layer['post_b']
+            folded = 0
+            if P == 2:
+                # the elementwise layers that follow ride on the conditioner's own output layer: with alpha = exp(c0 + u0 / 2),
+                #   forward:  post_a (alpha v + u1) + post_b = (post_a alpha) v + (post_a u1 + post_b)
+                #   inverse:  post_a (v - u1) / alpha + post_b = (v - u1) / (alpha / post_a) + post_b
+                # i.e. u0 is shifted by +-2 log post_a (post_a > 0: a product of exp(.) scales) and, forward, u1 is mapped
+                # affinely -- both linear in the output layer, so they go into its weights; the layer's log-det is then
+                # +-(c0 + u0' / 2) -+ log post_a, the second term a constant of the program.
+                folded = 1
+                lpa = torch.log(post_a)
+                const_ld = const_ld - lpa.sum()
+                if inverse:
+                    bb[:, 0] = bb[:, 0] - 2.0 * lpa
+                else:
+                    bb[:, 0] = bb[:, 0] + 2.0 * lpa
+                    w2[:, 1, :] = w2[:, 1, :] * post_a[:, None]
+                    bb[:, 1] = bb[:, 1] * post_a + post_b
+            fin_mode = 2 if last_writer[layer['tgt_half']] == i else 0
+            bits = P | (int(inverse) << 8) | (int(layer['has_pre']) << 9) | (fin_mode << 10) | (folded << 12)
+            hdr = torch.tensor([MAGIC, layer['src_half'], int(layer['src_pass']), H, N1, K2, Dh, bits],
                                dtype=torch.int32, device=dev).view(torch.float32)
             W1p = torch.zeros(N1, Dh, **f32)
             W1p[:H] = layer['W1']
@@ -133,10 +157,10 @@ def build_plan(ops: Sequence, D: int, base_loc: Optional[torch.Tensor], base_log
             b1p = torch.zeros(32, **f32)
             b1p[:H] = layer['b1']
             M = torch.zeros(N2, K2, **f32)                     # row = element * P + parameter; column H = bias (times the 1 in A2)
-            M[:Dh * P, :H] = layer['w2'].reshape(Dh * P, H)
-            M[:Dh * P, H] = layer['bb'].reshape(Dh * P)
+            M[:Dh * P, :H] = w2.reshape(Dh * P, H)
+            M[:Dh * P, H] = bb.reshape(Dh * P)
             w2h, w2l = _split(M)
-            tp = torch.stack([layer['pre_a'], layer['pre_b'], layer['post_a'], layer['post_b'], layer['fin_a'],
+            tp = torch.stack([layer['pre_a'], layer['pre_b'], post_a, post_b, layer['fin_a'],
                               layer['fin_b'], torch.zeros(Dh, **f32), torch.zeros(Dh, **f32)], dim=1).reshape(-1)
             sp = torch.stack([layer['src_a'], layer['src_b']], dim=1).reshape(-1)
             blob = torch.cat([hdr, canonical(w1h), canonical(w1l), b1p, canonical(w2h), canonical(w2l), tp, sp]).contiguous()
