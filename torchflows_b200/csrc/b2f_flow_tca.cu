@@ -35,7 +35,7 @@
 namespace b2f {
 
 constexpr int kAMaxGroups = 4;
-constexpr int kAThreads = (4 * kAMaxGroups + 2) * 32;
+constexpr int kAThreads = 4 * kAMaxGroups * 32;
 constexpr int kAHdr = 8;
 constexpr int kAMaxLayers = 8;
 constexpr float kALog2e = 1.4426950408889634f;
@@ -134,7 +134,7 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
         umma::mbar_init(w_full, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 4 * kAMaxGroups) umma::tmem_alloc(tmem_ptr, A.tmem_cols);
+    if (warp == 0) umma::tmem_alloc(tmem_ptr, A.tmem_cols);
     umma::tc_fence_before_sync();
     __syncthreads();
     umma::tc_fence_after_sync();
@@ -148,116 +148,19 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
         return first >= A.n_tiles ? 0 : (int)((A.n_tiles - 1 - first) / step + 1);
     };
 
-    if (warp == 4 * kAMaxGroups + 1) {
-        // ===================== tile IO + weights (one thread) =====================
-        if (lane == 0) {
-            // every layer's operands, once
-            uint32_t wbytes = 0;
-            for (int li = 0; li < L; ++li) wbytes += (uint32_t)(2 * A.layers[li].N1 * Dh + 2 * A.layers[li].N2 * A.layers[li].K2) * 4;
-            umma::mbar_arrive_expect_tx(w_full, wbytes);
-            for (int li = 0; li < L; ++li) {
-                const ALayer& Ly = A.layers[li];
-                const uint32_t w1b = (uint32_t)(2 * Ly.N1 * Dh) * 4, w2b = (uint32_t)(2 * Ly.N2 * Ly.K2) * 4;
-                umma::bulk_g2s(wreg + Ly.w_off, Ly.blob + kAHdr, w1b, w_full);
-                umma::bulk_g2s(wreg + Ly.w_off + 2 * Ly.N1 * Dh, Ly.blob + kAHdr + 2 * Ly.N1 * Dh + 32, w2b, w_full);
-            }
-            auto is_full = [&](long long t) { return A.use_tma && (t * 128 + 128 <= A.B); };
-            auto load_tile = [&](long long t, int g) {
-                uint64_t* bar = &bars[g * AB_PER_GROUP + AB_X_FULL];
-                if (is_full(t) && !A.philox) {
-                    umma::mbar_arrive_expect_tx(bar, 2 * half_bytes);
-                    const uint32_t base = g_base0 + g * group_bytes;
-                    a_tma_load4(base, &map_x, 0, 0, 0, (int)(t * 16), bar);
-                    a_tma_load4(base + half_bytes, &map_x, 0, 0, Dh / 4, (int)(t * 16), bar);
-                } else {
-                    umma::mbar_arrive(bar);          // ragged tile / in-kernel noise: the group's warps fill the tile themselves
-                }
-            };
-            int it[kAMaxGroups], nt[kAMaxGroups], remaining = 0;
-            for (int g = 0; g < NG; ++g) {
-                it[g] = 0; nt[g] = tiles_of(g); remaining += nt[g];
-                if (nt[g] > 0) load_tile(a_tile(0, g, NG), g);
-            }
-            uint32_t idle = 0;
-            while (remaining > 0) {
-                bool any = false;
-                for (int g = 0; g < NG; ++g) {
-                    if (it[g] >= nt[g]) continue;
-                    if (!a_test(&bars[g * AB_PER_GROUP + AB_TILE_DONE], it[g] & 1)) continue;
-                    any = true;
-                    const long long t = a_tile(it[g], g, NG);
-                    if (A.y && is_full(t)) {
-                        const uint32_t base = g_base0 + g * group_bytes;
-                        a_tma_store4(&map_y, 0, 0, 0, (int)(t * 16), base);
-                        a_tma_store4(&map_y, 0, 0, Dh / 4, (int)(t * 16), base + half_bytes);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    }
-                    ++it[g];
-                    --remaining;
-                    if (it[g] < nt[g]) load_tile(a_tile(it[g], g, NG), g);
-                }
-                if (!any) { __nanosleep(40); if (++idle > (1u << 26)) __trap(); } else idle = 0;
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // every layer's operands, once per CTA
+    if (tid == 0) {
+        uint32_t wbytes = 0;
+        for (int li = 0; li < L; ++li) wbytes += (uint32_t)(2 * A.layers[li].N1 * Dh + 2 * A.layers[li].N2 * A.layers[li].K2) * 4;
+        umma::mbar_arrive_expect_tx(w_full, wbytes);
+        for (int li = 0; li < L; ++li) {
+            const ALayer& Ly = A.layers[li];
+            const uint32_t w1b = (uint32_t)(2 * Ly.N1 * Dh) * 4, w2b = (uint32_t)(2 * Ly.N2 * Ly.K2) * 4;
+            umma::bulk_g2s(wreg + Ly.w_off, Ly.blob + kAHdr, w1b, w_full);
+            umma::bulk_g2s(wreg + Ly.w_off + 2 * Ly.N1 * Dh, Ly.blob + kAHdr + 2 * Ly.N1 * Dh + 32, w2b, w_full);
         }
-        __syncwarp();
-    } else if (warp == 4 * kAMaxGroups) {
-        // ===================== MMA issuer: serves whichever group has an operand ready =====================
-        const uint32_t leader = umma::elect_one();
-        umma::mbar_wait(w_full, 0);
-        const uint64_t d1c = umma::make_smem_desc(0, 128, Dh * 32);
-        const uint32_t d1_lo = (uint32_t)d1c, d1_hi = (uint32_t)(d1c >> 32);
-        const uint32_t w0 = umma::smem_u32(wreg);
-        int step[kAMaxGroups], total[kAMaxGroups], remaining = 0;      // step = 2 * (tile * L + layer) + (0: GEMM1, 1: GEMM2)
-        for (int g = 0; g < NG; ++g) { step[g] = 0; total[g] = tiles_of(g) * L * 2; remaining += total[g]; }
-        uint32_t idle = 0;
-        while (remaining > 0) {
-            bool any = false;
-            for (int g = 0; g < NG; ++g) {
-                if (step[g] >= total[g]) continue;
-                const int which = step[g] & 1, k = step[g] >> 1;       // k-th (tile, layer) of this group
-                uint64_t* ready = &bars[g * AB_PER_GROUP + (which ? AB_A2_READY : AB_A1_READY)];
-                if (!a_test(ready, k & 1)) continue;
-                any = true;
-                umma::tc_fence_after_sync();
-                const ALayer& Ly = A.layers[k % L];
-                const uint32_t gb = g_base0 + g * group_bytes;
-                const uint32_t scratch = gb + 2 * half_bytes;
-                const uint32_t dcol = tbase + (uint32_t)g * (uint32_t)A.tmem_stride;
-                if (leader) {
-                    if (!which) {
-                        // D1 = x_hi W1hi^T + x_lo W1hi^T + x_hi W1lo^T   (x_hi = the tile itself, truncated by the tensor core)
-                        const uint32_t idesc = umma::make_idesc_tf32(128, Ly.N1);
-                        const uint32_t xh = d1_lo + ((gb + (uint32_t)Ly.src_half * half_bytes) >> 4), xl = d1_lo + (scratch >> 4);
-                        const uint32_t wh = d1_lo + ((w0 + Ly.w_off * 4) >> 4), wl = wh + ((Ly.N1 * Dh * 4) >> 4);
-                        for (int ks = 0; ks < Dh / 8; ++ks) {
-                            umma::mma_tf32_ss_parts(dcol, xh + ks * 16, d1_hi, wh + ks * 16, d1_hi, idesc, ks > 0);
-                            umma::mma_tf32_ss_parts(dcol, xl + ks * 16, d1_hi, wh + ks * 16, d1_hi, idesc, 1);
-                            umma::mma_tf32_ss_parts(dcol, xh + ks * 16, d1_hi, wl + ks * 16, d1_hi, idesc, 1);
-                        }
-                        umma::mma_commit(&bars[g * AB_PER_GROUP + AB_D1_FULL]);
-                    } else {
-                        const uint64_t d2c = umma::make_smem_desc(0, 128, Ly.K2 * 32);
-                        const uint32_t d2_lo = (uint32_t)d2c, d2_hi = (uint32_t)(d2c >> 32);
-                        const uint32_t idesc = umma::make_idesc_tf32(128, Ly.N2);
-                        const uint32_t ah = d2_lo + (scratch >> 4), al = ah + ((128 * Ly.K2 * 4) >> 4);
-                        const uint32_t wh = d2_lo + ((w0 + (Ly.w_off + 2 * Ly.N1 * Dh) * 4) >> 4), wl = wh + ((Ly.N2 * Ly.K2 * 4) >> 4);
-                        for (int ks = 0; ks < Ly.K2 / 8; ++ks) {
-                            umma::mma_tf32_ss_parts(dcol + A.d2_col, ah + ks * 16, d2_hi, wh + ks * 16, d2_hi, idesc, ks > 0);
-                            umma::mma_tf32_ss_parts(dcol + A.d2_col, al + ks * 16, d2_hi, wh + ks * 16, d2_hi, idesc, 1);
-                            umma::mma_tf32_ss_parts(dcol + A.d2_col, ah + ks * 16, d2_hi, wl + ks * 16, d2_hi, idesc, 1);
-                        }
-                        umma::mma_commit(&bars[g * AB_PER_GROUP + AB_D2_FULL]);
-                    }
-                }
-                __syncwarp();
-                ++step[g];
-                --remaining;
-            }
-            if (!any) { __nanosleep(20); if (++idle > (1u << 26)) __trap(); } else idle = 0;
-        }
-    } else if ((warp >> 2) < NG) {
+    }
+    if ((warp >> 2) < NG) {
         // ===================== epilogue warps: group g = one tile pipeline, thread = one row =====================
         const int g = warp >> 2, q = warp & 3;
         const int m = q * 32 + lane;
@@ -273,6 +176,21 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
         const bool want_lp = A.log_prob != nullptr;
         const bool lp_in = want_lp && (A.flags & B2F_FLOW_LOGP_OF_INPUT);
         const int n_my = tiles_of(g);
+        const bool driver = q == 0 && lane == 0;          // the group's thread that talks to the TMA engine and the tensor core
+        const uint64_t d1c = umma::make_smem_desc(0, 128, Dh * 32);
+        const uint32_t d1_lo = (uint32_t)d1c, d1_hi = (uint32_t)(d1c >> 32);
+        const uint32_t w0 = umma::smem_u32(wreg);
+        auto is_full = [&](long long t) { return A.use_tma && (t * 128 + 128 <= A.B); };
+        auto load_tile = [&](long long t) {               // driver only
+            if (is_full(t) && !A.philox) {
+                umma::mbar_arrive_expect_tx(&gb_bars[AB_X_FULL], 2 * half_bytes);
+                a_tma_load4(gb, &map_x, 0, 0, 0, (int)(t * 16), &gb_bars[AB_X_FULL]);
+                a_tma_load4(gb + half_bytes, &map_x, 0, 0, Dh / 4, (int)(t * 16), &gb_bars[AB_X_FULL]);
+            } else {
+                umma::mbar_arrive(&gb_bars[AB_X_FULL]);   // ragged tile / in-kernel noise: the group fills the tile itself
+            }
+        };
+        if (driver && n_my > 0) load_tile(a_tile(0, g, NG));
         umma::mbar_wait(w_full, 0);
         uint32_t k = 0;                 // (tile, layer) counter of this group: barrier phases
         for (int it = 0; it < n_my; ++it) {
@@ -354,8 +272,22 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
                     a_sts128(lo_addr + kc * 128, r);
                 }
                 umma::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&gb_bars[AB_A1_READY]);
+                umma::tc_fence_before_sync();
+                a_group_sync(g);                         // all 128 rows of both operands are in shared memory
+                if (driver) {
+                    // D1 = x_hi W1hi^T + x_lo W1hi^T + x_hi W1lo^T   (x_hi = the tile itself, truncated by the tensor core)
+                    umma::tc_fence_after_sync();
+                    const uint32_t idesc = umma::make_idesc_tf32(128, Ly.N1);
+                    const uint32_t xh = d1_lo + ((gb + (uint32_t)Ly.src_half * half_bytes) >> 4), xl = d1_lo + (scratch >> 4);
+                    const uint32_t wh = d1_lo + ((w0 + Ly.w_off * 4) >> 4), wl = wh + ((Ly.N1 * Dh * 4) >> 4);
+                    const uint32_t dc = dcol - lane_addr;
+                    for (int ks = 0; ks < Dh / 8; ++ks) {
+                        umma::mma_tf32_ss_parts(dc, xh + ks * 16, d1_hi, wh + ks * 16, d1_hi, idesc, ks > 0);
+                        umma::mma_tf32_ss_parts(dc, xl + ks * 16, d1_hi, wh + ks * 16, d1_hi, idesc, 1);
+                        umma::mma_tf32_ss_parts(dc, xh + ks * 16, d1_hi, wl + ks * 16, d1_hi, idesc, 1);
+                    }
+                    umma::mma_commit(&gb_bars[AB_D1_FULL]);
+                }
                 // ---- hidden layer: D1 + b1 -> tanh -> hi / lo operands of GEMM2 (column H is the 1 that multiplies the bias) ----
                 umma::mbar_wait(&gb_bars[AB_D1_FULL], k & 1);
                 umma::tc_fence_after_sync();
@@ -390,8 +322,22 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
                 }
                 umma::tc_fence_before_sync();
                 umma::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&gb_bars[AB_A2_READY]);
+                a_group_sync(g);
+                if (driver) {
+                    umma::tc_fence_after_sync();
+                    const uint64_t d2c = umma::make_smem_desc(0, 128, Ly.K2 * 32);
+                    const uint32_t d2_lo = (uint32_t)d2c, d2_hi = (uint32_t)(d2c >> 32);
+                    const uint32_t idesc = umma::make_idesc_tf32(128, Ly.N2);
+                    const uint32_t ah = d2_lo + (scratch >> 4), al = ah + ((128 * Ly.K2 * 4) >> 4);
+                    const uint32_t wh = d2_lo + ((w0 + (Ly.w_off + 2 * Ly.N1 * Dh) * 4) >> 4), wl = wh + ((Ly.N2 * Ly.K2 * 4) >> 4);
+                    const uint32_t dc = dcol - lane_addr + A.d2_col;
+                    for (int ks = 0; ks < Ly.K2 / 8; ++ks) {
+                        umma::mma_tf32_ss_parts(dc, ah + ks * 16, d2_hi, wh + ks * 16, d2_hi, idesc, ks > 0);
+                        umma::mma_tf32_ss_parts(dc, al + ks * 16, d2_hi, wh + ks * 16, d2_hi, idesc, 1);
+                        umma::mma_tf32_ss_parts(dc, ah + ks * 16, d2_hi, wl + ks * 16, d2_hi, idesc, 1);
+                    }
+                    umma::mma_commit(&gb_bars[AB_D2_FULL]);
+                }
                 // ---- transformer: this row's Dh elements ----
                 umma::mbar_wait(&gb_bars[AB_D2_FULL], k & 1);
                 umma::tc_fence_after_sync();
@@ -498,13 +444,22 @@ flow_tca_kernel(const __grid_constant__ AArgs A, const __grid_constant__ CUtenso
                 }
             }
             umma::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&gb_bars[AB_TILE_DONE]);
+            a_group_sync(g);                             // the whole tile is final
+            if (driver) {
+                if (A.y && full) {
+                    a_tma_store4(&map_y, 0, 0, 0, (int)(tile * 16), gb);
+                    a_tma_store4(&map_y, 0, 0, Dh / 4, (int)(tile * 16), gb + half_bytes);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                if (it + 1 < n_my) load_tile(a_tile(it + 1, g, NG));
+            }
         }
+        if (driver) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     umma::tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4 * kAMaxGroups) umma::tmem_dealloc(tbase, A.tmem_cols);
+    if (warp == 0) umma::tmem_dealloc(tbase, A.tmem_cols);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------------
