@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "b2f_flow_device.cuh"
+#include "b2f_rqfast.cuh"
 
 namespace b2f {
 
@@ -66,9 +67,15 @@ __device__ __forceinline__ void transformer_backward_element(float v, const floa
     else if constexpr (TK == B2F_T_AFFINE_FWD) affine_fwd_backward<MODE>(v, acc[0], GZ, GL, dv, dh[0], dh[1]);
     else if constexpr (TK == B2F_T_AFFINE_INV) affine_inv_backward<MODE>(v, acc[0], acc[1], GZ, GL, dv, dh[0], dh[1]);
     else if constexpr (TK == B2F_T_RQ_FWD) {
-        auto h = [&](int i) { return acc[i]; };
-        auto g = [&](int i, float val) { dh[i] = val; };
-        rq_backward_fwd<8, MODE>(v, h, 8, boundary, GZ, GL, dv, g);
+        if constexpr (MODE >= 1 && PP == 24) {
+            // default mode: the restructured backward (one evaluation of the two softmaxes shared by the knots and by their
+            // gradients, SFU exponentials, reciprocals): ~2.5x fewer instructions, tolerance-checked against rq_backward_fwd
+            rqf::backward_fwd(v, acc, boundary, GZ, GL, dv, dh);
+        } else {
+            auto h = [&](int i) { return acc[i]; };
+            auto g = [&](int i, float val) { dh[i] = val; };
+            rq_backward_fwd<8, MODE>(v, h, 8, boundary, GZ, GL, dv, g);
+        }
     } else {
         auto h = [&](int i) { return acc[i]; };
         auto g = [&](int i, float val) { dh[i] = val; };
