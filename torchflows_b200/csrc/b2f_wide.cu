@@ -151,27 +151,24 @@ constexpr int kStageBlk = 8 * 36;                    // floats per staged block 
 constexpr int kStageWarp = 3 * kStageBlk;
 
 template <int EPI, class Release>
-__device__ __forceinline__ void epi_spline(const GArgs& G, int mt, int nt, uint32_t tbase, int warp, int lane,
-                                           float* stage, const Release& release) {
+__device__ __forceinline__ void epi_spline(const GArgs& G, long long row, uint32_t taddr, int e0, int n_el, int ldp_slot,
+                                           int warp, int lane, float* stage, const Release& release) {
+    // row: this thread's sample; taddr: TMEM address of its first parameter column; e0, n_el: its elements of the target half
     constexpr bool BWD = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
     constexpr bool INV = EPI == EPI_SPLINE_INV || EPI == EPI_SPLINE_BWD_INV;
-    const int q = warp & 3, t = warp >> 3, half = (warp >> 2) & 1;
-    const long long row = (long long)mt * 256 + t * 128 + q * 32 + lane;
     const bool live = row < G.B;
-    const uint32_t taddr = tbase + ((uint32_t)(q * 32) << 16) + t * 192 + half * 96;
-    const int e0 = nt * 8 + half * 4;                        // first of this thread's 4 elements of the target half
     const float* xrow = G.x + row * G.ldx + G.Dh;
     float ldacc = 0.0f;
     float GL = 0.0f;
     if (BWD) GL = (live && G.gld) ? __ldg(G.gld + row) : 0.0f;
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < n_el; ++j) {
         float p[24];
         umma::tmem_ld8_nowait<0>(taddr + j * 24, p);
         umma::tmem_ld8_nowait<8>(taddr + j * 24 + 8, p);
         umma::tmem_ld8_nowait<16>(taddr + j * 24 + 16, p);
         umma::tmem_ld_wait();
-        if (j == 3) release();
+        if (j == n_el - 1) release();
         const int e = e0 + j;
         const float4* bp = reinterpret_cast<const float4*>(G.b2p + (size_t)e * 24);
 #pragma unroll
@@ -230,7 +227,7 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, int mt, int nt, uint3
             }
         }
     }
-    if constexpr (!BWD) G.ldp[(size_t)(nt * 2 + half) * G.Bp + row] = ldacc;
+    if constexpr (!BWD) G.ldp[(size_t)ldp_slot * G.Bp + row] = ldacc;
 }
 
 // ---- the GEMM kernel -------------------------------------------------------------------------------------------------------
@@ -340,12 +337,179 @@ __global__ void __launch_bounds__(kThreads, 1) wide_gemm_kernel(const __grid_con
                 if (lane == 0) umma::mbar_arrive(&bars[WB_D_EMPTY]);
             };
             if constexpr (EPI == EPI_STORE) epi_store(G, mt, nt, ncols, tbase, warp, lane, release);
-            else epi_spline<EPI>(G, mt, nt, tbase, warp, lane, stage, release);
+            else {
+                const int q = warp & 3, t = warp >> 3, half = (warp >> 2) & 1;
+                epi_spline<EPI>(G, (long long)mt * 256 + t * 128 + q * 32 + lane, tbase + ((uint32_t)(q * 32) << 16) + t * 192 + half * 96,
+                                nt * 8 + half * 4, 4, nt * 2 + half, warp, lane, stage, release);
+            }
         }
     }
     umma::tc_fence_before_sync();
     __syncthreads();
     if (warp == kEpiWarps) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+// ---- the spline GEMMs as a 2-CTA cluster ----------------------------------------------------------------------------------------
+// The spline epilogues (above all the backward one) are long; with two M tiles per CTA the accumulators fill 384 of the 512
+// TMEM columns and the epilogue cannot overlap the next item's MMAs.  Here a CTA owns ONE 128-row tile and double-buffers
+// its [128 x 192] accumulator; the B operand (the element chunk's weights) is shared by the two CTAs of a cluster, each
+// loading half of every stage and multicasting it to both -- the same L2 -> SM bytes per flop as the two-tile kernel.
+// A stage may be refilled once BOTH CTAs have consumed it: every MMA issuer commits its stage release to both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(umma::smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(umma::smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(umma::smem_u32(bar)), "h"(mask) : "memory");
+}
+
+enum { CB_FULL = 0, CB_EMPTY = kMaxStages, CB_D_FULL = 2 * kMaxStages, CB_D_EMPTY = 2 * kMaxStages + 2, CB_COUNT = 2 * kMaxStages + 4 };
+constexpr int kCABytes = 128 * 128;       // one k-block of this CTA's M tile
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) wide_spline_kernel(const __grid_constant__ GArgs G) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr bool kBwd = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const uint32_t rank = cluster_rank();
+    const int stage_bytes = kCABytes + 192 * 128;
+    float* stage = reinterpret_cast<float*>(smem_raw + (size_t)G.stages * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)G.stages * stage_bytes + (kBwd ? kEpiWarps * kStageWarp * 4 : 0));
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + CB_COUNT);
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            umma::mbar_init(&bars[CB_FULL + i], 1);
+            umma::mbar_init(&bars[CB_EMPTY + i], 2);          // this CTA's issuer and the peer's
+        }
+        for (int i = 0; i < 2; ++i) {
+            umma::mbar_init(&bars[CB_D_FULL + i], 1);
+            umma::mbar_init(&bars[CB_D_EMPTY + i], kEpiWarps);
+        }
+        umma::fence_barrier_init();
+    }
+    if (warp == kEpiWarps) umma::tmem_alloc(tmem_ptr, kTmemCols);
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync();                                           // the peer's barriers exist before anything is sent to them
+    umma::tc_fence_after_sync();
+    const uint32_t tbase = *tmem_ptr;
+    const int n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const int n_items = G.n_mt * G.n_nt;                      // (pair of M tiles, element chunk); nt fastest
+
+    if (warp == kEpiWarps + 1) {
+        if (lane == 0) {
+            uint32_t st = 0, ph = 0;
+            for (int item = cid; item < n_items; item += n_clusters) {
+                const int nt = item % G.n_nt, tile = 2 * (item / G.n_nt) + (int)rank;
+                for (int kb = 0; kb < G.kb_total; ++kb) {
+                    umma::mbar_wait(&bars[CB_EMPTY + st], ph ^ 1);
+                    uint8_t* sa = smem_raw + (size_t)st * stage_bytes;
+                    umma::mbar_arrive_expect_tx(&bars[CB_FULL + st], kCABytes + 192 * 128);
+                    umma::bulk_g2s(sa, G.A + ((size_t)kb * G.RA8 + (size_t)tile * 16) * 256, kCABytes, &bars[CB_FULL + st]);
+                    if (G.atomic) {        // debug: no multicast, every CTA loads the whole chunk itself
+                        umma::bulk_g2s(sa + kCABytes, G.Bm + ((size_t)kb * G.RB8 + (size_t)nt * 24) * 256, 192 * 128, &bars[CB_FULL + st]);
+                    } else
+                    // this CTA's half of the chunk's weights (96 of 192 rows), to both CTAs of the cluster
+                    bulk_g2s_multicast(sa + kCABytes + rank * (96 * 128), G.Bm + ((size_t)kb * G.RB8 + (size_t)nt * 24 + rank * 12) * 256,
+                                       96 * 128, &bars[CB_FULL + st], (uint16_t)3);
+                    if (++st == (uint32_t)G.stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == kEpiWarps) {
+        const uint32_t leader = umma::elect_one();
+        const uint64_t dc = umma::make_smem_desc(0, 128, 1024);
+        const uint32_t d_lo = (uint32_t)dc, d_hi = (uint32_t)(dc >> 32);
+        // in a cluster launch the shared::cta address carries the CTA's rank above bit 18 (0x1000400 for rank 1): the matrix
+        // descriptor wants the 14-bit (address >> 4) of the CTA-local window, anything above would spill into its LBO field
+        const uint32_t s0 = (umma::smem_u32(smem_raw) >> 4) & 0x3FFFu;
+        const uint32_t idesc = umma::make_idesc_tf32(128, 192);
+        uint32_t st = 0, ph = 0, it = 0;
+        for (int item = cid; item < n_items; item += n_clusters, ++it) {
+            const uint32_t set = it & 1;
+            umma::mbar_wait(&bars[CB_D_EMPTY + set], ((it >> 1) & 1) ^ 1);
+            umma::tc_fence_after_sync();
+            for (int kb = 0; kb < G.kb_total; ++kb) {
+                umma::mbar_wait(&bars[CB_FULL + st], ph);
+                umma::tc_fence_after_sync();
+                if (leader) {
+                    const uint32_t a_lo = d_lo + s0 + st * (stage_bytes >> 4);
+                    const uint32_t b_lo = a_lo + (kCABytes >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma::mma_tf32_ss_parts(tbase + set * 192, a_lo + ks * 16, d_hi, b_lo + ks * 16, d_hi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                    if (G.atomic) { umma::mma_commit(&bars[CB_EMPTY + st]); umma::mma_commit(&bars[CB_EMPTY + st]); }
+                    else mma_commit_multicast(&bars[CB_EMPTY + st], (uint16_t)3);
+                    if (kb == G.kb_total - 1) umma::mma_commit(&bars[CB_D_FULL + set]);
+                }
+                __syncwarp();
+                if (++st == (uint32_t)G.stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        const int q = warp & 3, cg = warp >> 2;               // lane quarter; column group: 2 of the chunk's 8 elements
+        uint32_t it = 0;
+        for (int item = cid; item < n_items; item += n_clusters, ++it) {
+            const int nt = item % G.n_nt, tile = 2 * (item / G.n_nt) + (int)rank;
+            const uint32_t set = it & 1;
+            umma::mbar_wait_backoff(&bars[CB_D_FULL + set], (it >> 1) & 1);
+            umma::tc_fence_after_sync();
+            auto release = [&]() {
+                umma::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&bars[CB_D_EMPTY + set]);
+            };
+            epi_spline<EPI>(G, (long long)tile * 128 + q * 32 + lane, tbase + ((uint32_t)(q * 32) << 16) + set * 192 + cg * 48,
+                            nt * 8 + cg * 2, 2, nt * 4 + cg, warp, lane, stage, release);
+        }
+    }
+    umma::tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync();                                           // nothing of the peer's is still on its way to this CTA
+    if (warp == kEpiWarps) umma::tmem_dealloc(tbase, kTmemCols);
+}
+
+static int n_sm();
+
+template <int EPI>
+static int launch_spline(cudaStream_t st, GArgs& G, const char* what) {
+    constexpr bool kBwd = EPI == EPI_SPLINE_BWD_FWD || EPI == EPI_SPLINE_BWD_INV;
+    const size_t stage_bytes = kCABytes + 192 * 128;
+    const size_t extra = (kBwd ? (size_t)kEpiWarps * kStageWarp * 4 : 0) + CB_COUNT * 8 + 16;
+    G.stages = std::min(kMaxStages, (int)((227 * 1024 - extra) / stage_bytes));
+    const size_t smem = (size_t)G.stages * stage_bytes + extra;
+    const int items = G.n_mt * G.n_nt;
+    if (items <= 0) return B2F_OK;
+    cudaError_t ce = (cudaError_t)raise_smem_limit((const void*)wide_spline_kernel<EPI>, smem);
+    if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "cudaFuncSetAttribute(wide spline): %s", cudaGetErrorString(ce));
+    // persistent clusters: as many as can be resident at once (GPCs with an odd number of free SMs leave one SM out)
+    int max_clusters = n_sm() / 2;
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * (n_sm() / 2));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, (const void*)wide_spline_kernel<EPI>, &cfg) == cudaSuccess && n > 0) max_clusters = std::min(max_clusters, n);
+        else (void)cudaGetLastError();
+    }
+    const int grid = 2 * std::max(1, std::min(items, max_clusters));
+    wide_spline_kernel<EPI><<<grid, kThreads, smem, st>>>(G);
+    return check_launch(what);
 }
 
 // ---- pack kernel: row-major -> tiled operands -------------------------------------------------------------------------------
@@ -490,7 +654,7 @@ static Workspace layout(const Shapes& s, bool backward) {
     }
     w.keep_total = o;
     o = 0;
-    w.ldp = take((size_t)(s.P / 192) * 2 * s.Bp);
+    w.ldp = take((size_t)(s.P / 192) * 4 * s.Bp);
     w.dhA = w.dhT = w.dhid = w.dpreA = w.dpreT = 0;
     if (backward) {
         w.dhA = take((size_t)s.Bp * s.P);
@@ -643,10 +807,18 @@ extern "C" int b2f_wide_coupling_forward(const b2f_wide_layer_t* L, const float*
     GArgs G;
     spline_gemm_args(G, L, s, w, kp, x);
     G.y = y; G.ldp = sc + w.ldp;
-    rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
-                                  : launch_gemm<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
+    // 2-CTA cluster kernel (one M tile per CTA, double-buffered accumulators, B multicast); B2F_WIDE_NO_CLUSTER=1 keeps the
+    // two-tile single-CTA kernel
+    const bool cluster = !getenv("B2F_WIDE_NO_CLUSTER");
+    G.atomic = getenv("B2F_WIDE_NO_MULTICAST") ? 1 : 0;
+    if (cluster)
+        rc = L->tkind == B2F_T_RQ_INV ? launch_spline<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
+                                      : launch_spline<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
+    else
+        rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
+                                      : launch_gemm<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
     if (rc != B2F_OK) return rc;
-    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(x, y, B, s.D, s.Dh, sc + w.ldp, 2 * G.n_nt, s.Bp, log_det);
+    finish_kernel<<<(unsigned)std::min<long long>(4096, (B * (s.Dh / 4) + 255) / 256), 256, 0, st>>>(x, y, B, s.D, s.Dh, sc + w.ldp, (cluster ? 4 : 2) * G.n_nt, s.Bp, log_det);
     return check_launch("b2f_wide (finish)");
 }
 
@@ -676,8 +848,12 @@ extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float
     GArgs G;
     spline_gemm_args(G, L, s, w, kp, x);
     G.gy = gy; G.gld = glog_det; G.gx = gx; G.dhA = sc + w.dhA; G.dhT = sc + w.dhT; G.Pp8 = s.Pp / 8; G.gb2 = gb2;
-    rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_BWD_INV>(st, G, "b2f_wide_coupling_backward (spline)")
-                                  : launch_gemm<EPI_SPLINE_BWD_FWD>(st, G, "b2f_wide_coupling_backward (spline)");
+    if (!getenv("B2F_WIDE_NO_CLUSTER"))
+        rc = L->tkind == B2F_T_RQ_INV ? launch_spline<EPI_SPLINE_BWD_INV>(st, G, "b2f_wide_coupling_backward (spline)")
+                                      : launch_spline<EPI_SPLINE_BWD_FWD>(st, G, "b2f_wide_coupling_backward (spline)");
+    else
+        rc = L->tkind == B2F_T_RQ_INV ? launch_gemm<EPI_SPLINE_BWD_INV>(st, G, "b2f_wide_coupling_backward (spline)")
+                                      : launch_gemm<EPI_SPLINE_BWD_FWD>(st, G, "b2f_wide_coupling_backward (spline)");
     if (rc != B2F_OK) return rc;
     // dL/dW2[n, j] = sum_b dh[b, n] hid[b, j]
     {
