@@ -53,7 +53,8 @@ def _oracle_layer(x, W1, b1, W2, b2, direction, boundary, dtype, tf32_operands=F
 
 
 @pytest.mark.parametrize('B,D,H,direction', [(300, 64, 32, 'forward'), (300, 64, 32, 'inverse'), (1000, 128, 96, 'forward'),
-                                             (513, 192, 256, 'inverse'), (2048, 256, 320, 'forward'), (1, 64, 64, 'forward')])
+                                             (513, 192, 256, 'inverse'), (2048, 256, 320, 'forward'), (1, 64, 64, 'forward'),
+                                             (700, 256, 17, 'forward'), (300, 64, 5, 'inverse'), (400, 128, 40, 'forward')])
 def test_wide_layer_forward_vs_oracle(B, D, H, direction):
     from torchflows_b200 import _native as N
     dev = torch.device('cuda:0')
@@ -75,7 +76,7 @@ def test_wide_layer_forward_vs_oracle(B, D, H, direction):
 
 
 @pytest.mark.parametrize('B,D,H,direction', [(300, 64, 32, 'forward'), (700, 128, 96, 'forward'), (515, 128, 64, 'inverse'),
-                                             (1024, 256, 288, 'forward')])
+                                             (1024, 256, 288, 'forward'), (600, 256, 17, 'forward'), (300, 64, 9, 'inverse')])
 def test_wide_layer_backward_vs_oracle_autograd(B, D, H, direction):
     from torchflows_b200 import _native as N
     dev = torch.device('cuda:0')

@@ -225,7 +225,7 @@ def debug_umma_gemm(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
 # ---- wide-conditioner spline coupling layer (csrc/b2f_wide.cu) -------------------------------------------------------------
 def wide_eligible(D: int, H: int, n_bins: int) -> bool:
     """Mirror of check_layer in csrc/b2f_wide.cu."""
-    return D >= 64 and D % 64 == 0 and H >= 32 and H % 32 == 0 and n_bins == 8
+    return D >= 64 and D % 64 == 0 and H >= 1 and n_bins == 8
 
 
 WIDE_FOR_BACKWARD, WIDE_KEPT = 1, 2

@@ -5,6 +5,7 @@ description of the layer as one op of a fused libb2f flow program (conditioner G
 in one kernel, ``h`` never written to HBM).  Configurations outside the fused path (non-default conditioner
 depth / nonlinearity, globally learned parameter subsets, n_bins != 8) are detected at construction time and run
 as a *composite*: conditioner as library GEMMs, transformer as the stand-alone transformer kernel."""
+import os
 from typing import Any, List, Optional, Tuple, Type, Union
 
 import torch
@@ -147,10 +148,22 @@ class CouplingBijection(AutoregressiveBijection):
                                                 self._spline_args()[0]))
         # too wide for the whole-flow kernels (e.g. n_dim = 1024, n_hidden = 1024): the layer runs on the tcgen05 GEMM
         # pipeline of csrc/b2f_wide.cu (spline as the output-layer GEMM's epilogue, h never in memory)
-        self._wide = (not self._fusable and context_shape is None and isinstance(coupling, HalfSplit)
-                      and type(ct) is FeedForward and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
-                      and isinstance(transformer, RationalQuadratic)
-                      and N.wide_eligible(self.n_dim, ct.n_hidden, transformer.n_bins))
+        wide_ok = (context_shape is None and isinstance(coupling, HalfSplit)
+                   and type(ct) is FeedForward and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
+                   and isinstance(transformer, RationalQuadratic)
+                   and N.wide_eligible(self.n_dim, ct.n_hidden, transformer.n_bins))
+        self._wide = not self._fusable and wide_ok
+        # Spline couplings that DO fit the whole-flow kernels can also train through the per-layer GEMM pipeline
+        # (B2F_WIDE_TRAINING=1): measured on CouplingRQNSF(256), 131072 rows, it is a tie with the whole-flow backward kernel
+        # (7.56 vs 7.50 ms per step: both are bound by the latency of the spline backward arithmetic), so it is off by
+        # default and the fp32-faithful recompute of the whole-flow kernel keeps the gradients of the default widths.
+        self._wide_training = False
+        self._wide_ok = wide_ok
+
+    def _trains_wide(self) -> bool:
+        if os.environ.get('B2F_WIDE_TRAINING') != '1' or not (self._fusable and self._wide_ok):
+            return False
+        return torch.is_grad_enabled() and any(p.requires_grad and p.is_cuda for p in self.conditioner_transform.parameters())
 
     # -- reference API ---------------------------------------------------------------------------------------
     def get_constant_part(self, x: torch.Tensor) -> torch.Tensor:
@@ -174,7 +187,7 @@ class CouplingBijection(AutoregressiveBijection):
 
     # -- fused path ------------------------------------------------------------------------------------------
     def lower(self, direction: str) -> Optional[List[prog.LoweredOp]]:
-        if not self._fusable:
+        if not self._fusable or self._trains_wide():
             return None
         seq = self.conditioner_transform.sequential
         n_bins, boundary = self._spline_args()
@@ -213,7 +226,7 @@ class CouplingBijection(AutoregressiveBijection):
 
     def _composite(self, x: torch.Tensor, context, direction: str):
         """Conditioner as library GEMMs, transformer as the stand-alone kernel (non-default configurations)."""
-        if self._wide and context is None and x.is_cuda and x.dtype == torch.float32:
+        if (self._wide or self._trains_wide()) and context is None and x.is_cuda and x.dtype == torch.float32:
             return self._run_wide(x, direction)
         batch_shape = get_batch_shape(x, self.event_shape)
         xf = flatten_event(x, self.event_shape)
@@ -235,10 +248,12 @@ class CouplingBijection(AutoregressiveBijection):
         return unflatten_event(out, self.event_shape), log_det
 
     def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_fused(x, 'forward') if self._fusable else self._composite(x, context, 'forward')
+        fused = self._fusable and not self._trains_wide()
+        return self._run_fused(x, 'forward') if fused else self._composite(x, context, 'forward')
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        return self._run_fused(z, 'inverse') if self._fusable else self._composite(z, context, 'inverse')
+        fused = self._fusable and not self._trains_wide()
+        return self._run_fused(z, 'inverse') if fused else self._composite(z, context, 'inverse')
 
 
 class MaskedAutoregressiveBijection(AutoregressiveBijection):

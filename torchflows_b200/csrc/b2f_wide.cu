@@ -617,13 +617,13 @@ static inline long long up(long long v, long long m) { return (v + m - 1) / m * 
 
 struct Shapes {
     long long B, Bp;
-    int D, Dh, H, P, Pp, Hp, Dhp;
+    int D, Dh, H, Hk, P, Pp, Hp, Dhp;      // Hk: H rounded up to the 32-wide k-block (the padded hidden units are exact zeros)
 };
 
 static Shapes shapes(long long B, int D, int H) {
     Shapes s;
     s.B = B; s.Bp = up(std::max<long long>(B, 1), 256);
-    s.D = D; s.Dh = D / 2; s.H = H;
+    s.D = D; s.Dh = D / 2; s.H = H; s.Hk = (int)up(H, 32);
     s.P = s.Dh * 24; s.Pp = (int)up(s.P, 256); s.Hp = (int)up(H, 256); s.Dhp = (int)up(s.Dh, 256);
     return s;
 }
@@ -641,14 +641,14 @@ static Workspace layout(const Shapes& s, bool backward) {
     auto take = [&](size_t n) { size_t at = o; o += (n + 63) / 64 * 64; return at; };
     w.xaA = take((size_t)s.Bp * s.Dh);
     w.W1t = take((size_t)s.Hp * s.Dh);
-    w.W2p = take((size_t)s.Pp * s.H);
+    w.W2p = take((size_t)s.Pp * s.Hk);
     w.b2p = take((size_t)s.P);
-    w.pre = take((size_t)s.Bp * s.H);
-    w.hidA = take((size_t)s.Bp * s.H);
+    w.pre = take((size_t)s.Bp * s.Hk);
+    w.hidA = take((size_t)s.Bp * s.Hk);
     w.xaT = w.W1T = w.W2pT = w.hidT = 0;
     if (backward) {
         w.xaT = take((size_t)s.Dhp * s.Bp);
-        w.W1T = take((size_t)s.Dhp * s.H);
+        w.W1T = take((size_t)s.Dhp * s.Hk);
         w.W2pT = take((size_t)s.Hp * s.P);
         w.hidT = take((size_t)s.Hp * s.Bp);
     }
@@ -659,8 +659,8 @@ static Workspace layout(const Shapes& s, bool backward) {
     if (backward) {
         w.dhA = take((size_t)s.Bp * s.P);
         w.dhT = take((size_t)s.Pp * s.Bp);
-        w.dhid = take((size_t)s.Bp * s.H);
-        w.dpreA = take((size_t)s.Bp * s.H);
+        w.dhid = take((size_t)s.Bp * s.Hk);
+        w.dpreA = take((size_t)s.Bp * s.Hk);
         w.dpreT = take((size_t)s.Hp * s.Bp);
     }
     w.scratch_total = o;
@@ -736,7 +736,7 @@ static int check_layer(const b2f_wide_layer_t* L, long long B) {
     if (L->tkind != B2F_T_RQ_FWD && L->tkind != B2F_T_RQ_INV) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: spline transformers only");
     if (L->n_bins != 8) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_bins must be 8");
     if (L->D < 64 || L->D % 64 != 0) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_dim must be a multiple of 64");
-    if (L->H < 32 || L->H % 32 != 0) return fail(B2F_ERR_UNSUPPORTED, "wide coupling: n_hidden must be a multiple of 32");
+    if (L->H < 1) return fail(B2F_ERR_INVALID, "wide coupling: n_hidden");
     if (!(L->boundary > 0.0f)) return fail(B2F_ERR_INVALID, "wide coupling: boundary");
     if (B < 0 || B > (1LL << 30)) return fail(B2F_ERR_INVALID, "wide coupling: batch size");
     return B2F_OK;
@@ -749,16 +749,17 @@ static int hidden_layer(cudaStream_t st, const b2f_wide_layer_t* L, const Shapes
     if ((rc = pack(st, x, s.D, s.B, s.Dh, 0, PACK_COPY, nullptr, nullptr, 0, ws + w.xaA, s.Bp, backward ? ws + w.xaT : nullptr,
                    s.Dhp, s.Bp, nullptr)) != B2F_OK) return rc;
     if ((rc = pack(st, L->W1, s.Dh, s.H, s.Dh, 0, PACK_COPY, nullptr, nullptr, 0, ws + w.W1t, s.Hp, backward ? ws + w.W1T : nullptr,
-                   s.Dhp, s.H, nullptr)) != B2F_OK) return rc;
-    if ((rc = gemm_store(st, ws + w.xaA, s.Bp, ws + w.W1t, s.Hp, s.H, s.Dh, ws + w.pre, s.H, s.Bp, s.H, 0, 0, 1, 256)) != B2F_OK) return rc;
-    return pack(st, ws + w.pre, s.H, s.B, s.H, 0, PACK_TANH_BIAS, L->b1, nullptr, 0, ws + w.hidA, s.Bp, backward ? ws + w.hidT : nullptr,
+                   s.Dhp, s.Hk, nullptr)) != B2F_OK) return rc;
+    if ((rc = gemm_store(st, ws + w.xaA, s.Bp, ws + w.W1t, s.Hp, s.Hk, s.Dh, ws + w.pre, s.Hk, s.Bp, s.Hk, 0, 0, 1, 256)) != B2F_OK) return rc;
+    // columns >= H (padding of the k-block) are written as exact zeros: tanh is applied to the real hidden units only
+    return pack(st, ws + w.pre, s.Hk, s.B, s.H, 0, PACK_TANH_BIAS, L->b1, nullptr, 0, ws + w.hidA, s.Bp, backward ? ws + w.hidT : nullptr,
                 s.Hp, s.Bp, nullptr);
 }
 
 static void spline_gemm_args(GArgs& G, const b2f_wide_layer_t* L, const Shapes& s, const Workspace& w, float* ws, const float* x) {
     memset(&G, 0, sizeof(G));
     G.A = ws + w.hidA; G.Bm = ws + w.W2p; G.RA8 = (int)(s.Bp / 8); G.RB8 = s.Pp / 8; G.RB = s.P; G.NT = 192;
-    G.n_mt = (int)(s.Bp / 256); G.n_nt = s.P / 192; G.n_split = 1; G.kb_total = s.H / 32;
+    G.n_mt = (int)(s.Bp / 256); G.n_nt = s.P / 192; G.n_split = 1; G.kb_total = s.Hk / 32;
     G.x = x; G.ldx = s.D; G.Dh = s.Dh; G.B = s.B; G.Bp = s.Bp; G.b2p = ws + w.b2p; G.boundary = L->boundary;
 }
 
@@ -840,7 +841,7 @@ extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float
     cudaMemsetAsync(gW2, 0, P23 * s.H * 4, st);
     cudaMemsetAsync(gb2, 0, P23 * 4, st);
     if (B == 0) return check_launch("b2f_wide_coupling_backward");
-    cudaMemsetAsync(sc + w.dhid, 0, (size_t)s.Bp * s.H * 4, st);
+    cudaMemsetAsync(sc + w.dhid, 0, (size_t)s.Bp * s.Hk * 4, st);
     if (s.Pp > s.P) cudaMemsetAsync(sc + w.dhT, 0, (size_t)s.Pp * s.Bp * 4, st);
     // packed operands and hidden activations: kept by the forward of this step, or rebuilt from x and the parameters
     if (!(flags & B2F_WIDE_KEPT) && (rc = prepare(st, L, s, w, kp, x, true)) != B2F_OK) return rc;
@@ -857,18 +858,18 @@ extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float
     if (rc != B2F_OK) return rc;
     // dL/dW2[n, j] = sum_b dh[b, n] hid[b, j]
     {
-        const int items = (s.Pp / 256) * ((s.H + 255) / 256);
-        if ((rc = gemm_store(st, sc + w.dhT, s.Pp, kp + w.hidT, s.Hp, s.H, s.Bp, gW2, s.H, s.P, s.H, 1, 1,
+        const int items = (s.Pp / 256) * ((s.Hk + 255) / 256);
+        if ((rc = gemm_store(st, sc + w.dhT, s.Pp, kp + w.hidT, s.Hp, s.Hk, s.Bp, gW2, s.H, s.P, s.H, 1, 1,
                              pick_split(items, (int)(s.Bp / 32)), 256)) != B2F_OK) return rc;
     }
     // dL/dhid[b, j] = sum_n dh[b, n] W2[n, j]
     {
-        const int items = (int)(s.Bp / 256) * ((s.H + 255) / 256);
-        if ((rc = gemm_store(st, sc + w.dhA, s.Bp, kp + w.W2pT, s.Hp, s.H, s.P, sc + w.dhid, s.H, s.Bp, s.H, 0, 1,
+        const int items = (int)(s.Bp / 256) * ((s.Hk + 255) / 256);
+        if ((rc = gemm_store(st, sc + w.dhA, s.Bp, kp + w.W2pT, s.Hp, s.Hk, s.P, sc + w.dhid, s.Hk, s.Bp, s.Hk, 0, 1,
                              pick_split(items, s.P / 32), 256)) != B2F_OK) return rc;
     }
     // through the tanh: dpre = dhid (1 - hid^2) in both orientations, dL/db1 = column sums
-    if ((rc = pack(st, sc + w.dhid, s.H, s.B, s.H, 0, PACK_DTANH, L->b1, kp + w.pre, s.H, sc + w.dpreA, s.Bp, sc + w.dpreT, s.Hp,
+    if ((rc = pack(st, sc + w.dhid, s.Hk, s.B, s.H, 0, PACK_DTANH, L->b1, kp + w.pre, s.Hk, sc + w.dpreA, s.Bp, sc + w.dpreT, s.Hp,
                    s.Bp, gb1)) != B2F_OK) return rc;
     // dL/dW1[j, i] = sum_b dpre[b, j] xa[b, i]
     {
@@ -881,8 +882,8 @@ extern "C" int b2f_wide_coupling_backward(const b2f_wide_layer_t* L, const float
     if ((rc = check_launch("b2f_wide (finish)")) != B2F_OK) return rc;
     {
         const int items = (int)(s.Bp / 256) * ((s.Dh + 255) / 256);
-        if ((rc = gemm_store(st, sc + w.dpreA, s.Bp, kp + w.W1T, s.Dhp, s.Dh, s.H, gx, s.D, s.B, s.Dh, 0, 1,
-                             pick_split(items, s.H / 32), 256)) != B2F_OK) return rc;
+        if ((rc = gemm_store(st, sc + w.dpreA, s.Bp, kp + w.W1T, s.Dhp, s.Dh, s.Hk, gx, s.D, s.B, s.Dh, 0, 1,
+                             pick_split(items, s.Hk / 32), 256)) != B2F_OK) return rc;
     }
     return B2F_OK;
 }
