@@ -403,11 +403,13 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
     achieved = by_lp * B / (lp_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of the log_prob launch from the committed ncu capture
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
         if args.workload in tr and not args.rows:
             traffic = tr[args.workload]['log_prob_launch_dram_bytes']
+            traffic_src = 'committed ncu capture, not this run: ' + tr[args.workload].get('source', '') + ' @ ' + \
+                str(tr[args.workload].get('captured_at_commit', '?'))
     except Exception:
         pass
 
@@ -422,6 +424,7 @@ def run_ours(args):
         'log_prob_samples_per_s': world * B / (lp_avg_ms * 1e-3), 'sample_samples_per_s': world * B / (s_avg_ms * 1e-3),
         'roofline': {'bound': 'hbm', 'kernel': KERNELS[args.workload] + ' (log_prob launch)', 'achieved': achieved,
                      'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
+                     'traffic_source': traffic_src,
                      'peak_source': peak_src, 'algorithmic_bytes_per_row': by_lp, 'launch_ms': lp_avg_ms,
                      'sample_launch': {'achieved': by_s * B / (s_avg_ms * 1e-3) / 1e9, 'algorithmic_bytes_per_row': by_s,
                                        'launch_ms': s_avg_ms,
@@ -466,9 +469,24 @@ def run_ours(args):
         line['cpu_baseline'] = {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'{cpu_rows} rows in chunks of {chunk} (log_prob + sample), same weights as the '
                                           f'repo arm (state T), median of 3'}
+    if args.workload == 'q256' and not args.rows and not args.no_fit:
+        # the other single-GPU configurations of BASELINE.json, briefly (their own bench lines: --workload r64|m128|mq128)
+        del x
+        torch.cuda.empty_cache()
+        others = {}
+        for wl in ('r64', 'm128', 'mq128'):
+            try:
+                others[wl] = quick_probe(torch, dev, rank, wl, hbm_peak)
+            except Exception as e:
+                others[wl] = {'error': str(e)[:200]}
+        if world > 1:
+            dist.barrier()
+        line['other_workloads'] = others
+        x = None
     if not args.no_fit:
         # Flow.fit, data-parallel over the same ranks: the path of this repo that has a collective in it
-        del x, x_host, xs_host, lp_host
+        del x_host, xs_host, lp_host
+        x = None
         in_flight.clear()
         torch.cuda.empty_cache()
         fit = {}
@@ -482,6 +500,37 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def quick_probe(torch, dev, rank, workload, hbm_peak, reps=10):
+    """Flow.log_prob / Flow.sample launch times of one of the other BASELINE configurations on this rank's GPU (device
+    events, 3 warm-up calls, `reps` timed calls each): the numbers their own bench lines report at length."""
+    from torchflows_b200 import _native as N_
+    preset, D, B, _, _ = WORKLOADS[workload]
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    x = torch.randn(B, D, device=dev, generator=g)
+    flow = build_flow(preset, D, dev, init_rows=x[:65536])
+    by_lp, by_s = algorithmic_bytes(D)
+    out = {'workload': f'{preset} n_dim={D}, {B} rows'}
+    with torch.no_grad():
+        for name, fn in (('log_prob', lambda: flow.log_prob(x)), ('sample', lambda: flow.sample(B, no_grad=True))):
+            for _ in range(3):
+                fn()
+            kernel = N_.last_flow_kernel()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            nbytes = by_lp if name == 'log_prob' else by_s
+            out[name] = {'launch_ms': ms, 'samples_per_s': B / (ms * 1e-3), 'kernel': KERNEL_IDS.get(kernel, str(kernel)),
+                         'hbm_frac': nbytes * B / (ms * 1e-3) / 1e9 / hbm_peak}
+    del flow, x
+    torch.cuda.empty_cache()
+    return out
 
 
 def wide_tensor_roofline(torch, flow, x, dev, reps=5):
