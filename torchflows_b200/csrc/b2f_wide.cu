@@ -161,22 +161,33 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, long long row, uint32
     float ldacc = 0.0f;
     float GL = 0.0f;
     if (BWD) GL = (live && G.gld) ? __ldg(G.gld + row) : 0.0f;
+    // this thread's inputs of element j are requested one element ahead, the bias before the wait on tensor memory: the
+    // epilogue is a long dependent chain per element and every exposed L2 round trip is paid n_el times per item
+    float v_next = live ? __ldg(xrow + e0) : 0.0f;
+    float gz_next = 0.0f;
+    if (BWD) gz_next = (live && G.gy) ? __ldg(G.gy + row * G.ldx + G.Dh + e0) : 0.0f;
 #pragma unroll 1
     for (int j = 0; j < n_el; ++j) {
         float p[24];
         umma::tmem_ld8_nowait<0>(taddr + j * 24, p);
         umma::tmem_ld8_nowait<8>(taddr + j * 24 + 8, p);
         umma::tmem_ld8_nowait<16>(taddr + j * 24 + 16, p);
-        umma::tmem_ld_wait();
-        if (j == n_el - 1) release();
         const int e = e0 + j;
         const float4* bp = reinterpret_cast<const float4*>(G.b2p + (size_t)e * 24);
+        float4 bv[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) bv[c] = __ldg(bp + c);
+        const float v = v_next, GZ_cur = gz_next;
+        if (j + 1 < n_el) {
+            v_next = live ? __ldg(xrow + e + 1) : 0.0f;
+            if (BWD) gz_next = (live && G.gy) ? __ldg(G.gy + row * G.ldx + G.Dh + e + 1) : 0.0f;
+        }
+        umma::tmem_ld_wait();
+        if (j == n_el - 1) release();
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
-            const float4 bv = __ldg(bp + c);
-            p[4 * c] += bv.x; p[4 * c + 1] += bv.y; p[4 * c + 2] += bv.z; p[4 * c + 3] += bv.w;
+            p[4 * c] += bv[c].x; p[4 * c + 1] += bv[c].y; p[4 * c + 2] += bv[c].z; p[4 * c + 3] += bv[c].w;
         }
-        const float v = live ? __ldg(xrow + e) : 0.0f;
         auto h = [&](int i) { return p[i]; };
         if constexpr (!BWD) {
             float out, ld;
@@ -185,7 +196,7 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, long long row, uint32
             if (live) G.y[row * G.ldx + G.Dh + e] = out;
             ldacc += ld;
         } else {
-            const float GZ = (live && G.gy) ? __ldg(G.gy + row * G.ldx + G.Dh + e) : 0.0f;
+            const float GZ = GZ_cur;
             float dp[24];
             dp[23] = 0.0f;
             auto g = [&](int i, float val) { dp[i] = val; };
@@ -198,9 +209,9 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, long long row, uint32
             // dL/dh in both operand orientations: (row, k = parameter) directly, (parameter, k = row) through the staging tile
             const long long n0 = (long long)e * 24;
 #pragma unroll
-            for (int c = 0; c < 6; ++c)
-                *reinterpret_cast<float4*>(G.dhA + tiled_off(row, n0 + 4 * c, G.Bp >> 3)) =
-                    make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]);
+            for (int c = 0; c < 6; ++c)           // streaming stores: 1.6 GB of dL/dh per call must not evict the GEMM operands from L2
+                __stcs(reinterpret_cast<float4*>(G.dhA + tiled_off(row, n0 + 4 * c, G.Bp >> 3)),
+                       make_float4(dp[4 * c], dp[4 * c + 1], dp[4 * c + 2], dp[4 * c + 3]));
             float* sw = stage + (warp * kStageWarp);
             __syncwarp();                                    // the previous element's tile has been read
 #pragma unroll
@@ -213,7 +224,7 @@ __device__ __forceinline__ void epi_spline(const GArgs& G, long long row, uint32
                 const int f4 = u * 32 + lane;                // float4 slot 0 .. 191 of the 3 KB
                 const int blk = f4 >> 6, k4 = (f4 >> 3) & 7, n8 = f4 & 7;
                 const float4 v = *reinterpret_cast<const float4*>(sw + blk * kStageBlk + k4 * 36 + n8 * 4);
-                *reinterpret_cast<float4*>(G.dhT + ((size_t)kb * G.Pp8 + (size_t)(n0 >> 3) + blk) * 256 + k4 * 32 + n8 * 4) = v;
+                __stcs(reinterpret_cast<float4*>(G.dhT + ((size_t)kb * G.Pp8 + (size_t)(n0 >> 3) + blk) * 256 + k4 * 32 + n8 * 4), v);
             }
             if (lane < 23) {                                 // dL/db2[e * 23 + lane] += sum over the warp's 32 rows
                 const float* col = sw + (lane >> 3) * kStageBlk + (lane & 7) * 4;
