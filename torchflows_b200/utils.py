@@ -12,8 +12,11 @@ def get_batch_shape(x: torch.Tensor, event_shape: Shape) -> torch.Size:
 
 
 def flatten_event(x: torch.Tensor, event_shape: Shape) -> torch.Tensor:
-    """(*batch, *event) -> (*batch, prod(event))."""
-    return x.reshape(*get_batch_shape(x, event_shape), -1)
+    """(*batch, *event) -> (*batch, prod(event)).  The event size is spelled out (a -1 is ambiguous for an empty batch)."""
+    n = 1
+    for s in event_shape:
+        n *= int(s)
+    return x.reshape(*get_batch_shape(x, event_shape), n)
 
 
 def unflatten_event(x: torch.Tensor, event_shape: Shape) -> torch.Tensor:
