@@ -218,3 +218,30 @@ def test_wide_flow_edge_batches_and_training_modes():
     xg = x.clone().requires_grad_(True)
     flow.log_prob(xg).sum().backward()
     assert torch.isfinite(xg.grad).all() and float(xg.grad.abs().max()) > 0
+
+
+def test_cluster_and_single_cta_spline_gemms_agree():
+    """The 2-CTA cluster kernel (default) and the single-CTA two-tile kernel (B2F_WIDE_NO_CLUSTER=1) run the same arithmetic
+    per output: forward results are identical, gradients agree to the order of the atomics."""
+    import os
+    from torchflows_b200 import _native as N
+    dev = torch.device('cuda:0')
+    W1, b1, W2, b2 = (t.to(dev) for t in _params(128, 160, seed=4))
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(777, 128, generator=g) * 2).to(dev)
+    gy, gld = torch.randn(777, 128, generator=g).to(dev), torch.randn(777, generator=g).to(dev)
+    outs = []
+    for single in (False, True):
+        if single:
+            os.environ['B2F_WIDE_NO_CLUSTER'] = '1'
+        try:
+            y, ld, _ = N.wide_coupling_forward(N.T_RQ_FWD, x, W1, b1, W2, b2, boundary=5.0)
+            grads = N.wide_coupling_backward(N.T_RQ_FWD, x, gy, gld, W1, b1, W2, b2, boundary=5.0)
+            torch.cuda.synchronize()
+            outs.append((y, ld) + tuple(grads))
+        finally:
+            os.environ.pop('B2F_WIDE_NO_CLUSTER', None)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert float((outs[0][1] - outs[1][1]).abs().max()) < 1e-5
+    for a, b_ in zip(outs[0][2:], outs[1][2:]):
+        assert rel(a, b_) < 1e-4

@@ -424,9 +424,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) wide_sp
                     uint8_t* sa = smem_raw + (size_t)st * stage_bytes;
                     umma::mbar_arrive_expect_tx(&bars[CB_FULL + st], kCABytes + 192 * 128);
                     umma::bulk_g2s(sa, G.A + ((size_t)kb * G.RA8 + (size_t)tile * 16) * 256, kCABytes, &bars[CB_FULL + st]);
-                    if (G.atomic) {        // debug: no multicast, every CTA loads the whole chunk itself
-                        umma::bulk_g2s(sa + kCABytes, G.Bm + ((size_t)kb * G.RB8 + (size_t)nt * 24) * 256, 192 * 128, &bars[CB_FULL + st]);
-                    } else
                     // this CTA's half of the chunk's weights (96 of 192 rows), to both CTAs of the cluster
                     bulk_g2s_multicast(sa + kCABytes + rank * (96 * 128), G.Bm + ((size_t)kb * G.RB8 + (size_t)nt * 24 + rank * 12) * 256,
                                        96 * 128, &bars[CB_FULL + st], (uint16_t)3);
@@ -457,8 +454,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) wide_sp
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
                         umma::mma_tf32_ss_parts(tbase + set * 192, a_lo + ks * 16, d_hi, b_lo + ks * 16, d_hi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                    if (G.atomic) { umma::mma_commit(&bars[CB_EMPTY + st]); umma::mma_commit(&bars[CB_EMPTY + st]); }
-                    else mma_commit_multicast(&bars[CB_EMPTY + st], (uint16_t)3);
+                    mma_commit_multicast(&bars[CB_EMPTY + st], (uint16_t)3);
                     if (kb == G.kb_total - 1) umma::mma_commit(&bars[CB_D_FULL + set]);
                 }
                 __syncwarp();
@@ -822,7 +818,6 @@ extern "C" int b2f_wide_coupling_forward(const b2f_wide_layer_t* L, const float*
     // 2-CTA cluster kernel (one M tile per CTA, double-buffered accumulators, B multicast); B2F_WIDE_NO_CLUSTER=1 keeps the
     // two-tile single-CTA kernel
     const bool cluster = !getenv("B2F_WIDE_NO_CLUSTER");
-    G.atomic = getenv("B2F_WIDE_NO_MULTICAST") ? 1 : 0;
     if (cluster)
         rc = L->tkind == B2F_T_RQ_INV ? launch_spline<EPI_SPLINE_INV>(st, G, "b2f_wide_coupling_forward")
                                       : launch_spline<EPI_SPLINE_FWD>(st, G, "b2f_wide_coupling_forward");
