@@ -207,54 +207,61 @@ B2F_HD float f_rcpn(float x) {            // reciprocal + one Newton step (~1 ul
     return fmaf(y, fmaf(-x, y, 1.0f), y);
 }
 
-B2F_HD void backward_fwd(float v, const float (&p)[24], float b, float GZ, float GL, float& dv, float (&dp)[24]) {
+B2F_HD void backward_fwd(float v, const float (&p)[24], float b, float GZ_in, float GL_in, float& dv, float (&dp)[24]) {
+    // Out of bounds (identity tail): dL/dv = GZ and zero parameter gradients.  The arithmetic below runs on v clamped into
+    // the spline's range with the upstream gradients zeroed, so it stays finite and every product with them is an exact 0.
     const bool inb = v > -b && v < b;
     const float lo = -b, span = b + b;
-    // softmaxes (rational_quadratic.py:75-76, 46-47)
-    float px[8], py[8];
+    const float vc = fminf(fmaxf(v, lo), b);
+    const float GZ = inb ? GZ_in : 0.0f, GL = inb ? GL_in : 0.0f;
+    // softmaxes (rational_quadratic.py:75-76, 46-47); cx = c1 * softmax (c1 = 1 - 8e-3), the form both the bin sizes and the
+    // softmax backward use
+    float cx[8], cy[8];
     float mx = p[0], my = fmaf(p[8], 1e-3f, p[0]);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        px[j] = p[j];
-        py[j] = fmaf(p[8 + j], 1e-3f, p[j]);
-        mx = fmaxf(mx, px[j]);
-        my = fmaxf(my, py[j]);
+        cx[j] = p[j];
+        cy[j] = fmaf(p[8 + j], 1e-3f, p[j]);
+        mx = fmaxf(mx, cx[j]);
+        my = fmaxf(my, cy[j]);
     }
     float sx = 0.0f, sy = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        px[j] = f_ex2((px[j] - mx) * kLog2e);
-        py[j] = f_ex2((py[j] - my) * kLog2e);
-        sx += px[j];
-        sy += py[j];
+        cx[j] = f_ex2((cx[j] - mx) * kLog2e);
+        cy[j] = f_ex2((cy[j] - my) * kLog2e);
+        sx += cx[j];
+        sy += cy[j];
     }
-    const float isx = f_rcpn(sx), isy = f_rcpn(sy);
-    // knots, search (searchsorted right=False: knots strictly below v), selection of the bin's quantities
-    float cx = 0.0f, cy = 0.0f;
-    float xk = lo, yk = lo, xk1 = b, yk1 = b, ud0 = kRqEdgeU, ud1 = kRqEdgeU;
-    int k = 0;
-    bool prev_below = true;
+    const float isx = kSizeScale * f_rcpn(sx), isy = kSizeScale * f_rcpn(sy);
+    // Search with the predicates as numbers.  m_j = [knot_{j+1} < v] (searchsorted right=False), M_j = [knot_j < v] = m_{j-1}
+    // (M_0 = 1), d_j = M_j - m_j = [bin j is the one].  Monotone predicates make the predicated prefix sums EXACTLY the
+    // cumulative sums of the selected knots, in the reference's summation order; knot = span * cumsum + lo.
+    float m[8], d[8];
+    float Cx = 0.0f, Cx1 = 0.0f, Cy = 0.0f, Cy1 = 0.0f, ud0 = 0.0f, ud1 = 0.0f, c = 0.0f, Mj = 1.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        px[j] *= isx;
-        py[j] *= isy;
-        cx += fmaf(px[j], kSizeScale, kRqMinBin);
-        cy += fmaf(py[j], kSizeScale, kRqMinBin);
-        const bool last = j == 7;
-        const float kx = last ? b : fmaf(span, cx, lo);
-        const float ky = last ? b : fmaf(span, cy, lo);
-        const float ud = last ? kRqEdgeU : p[16 + (last ? 0 : j)];
-        const bool below = kx < v;
-        const bool take = prev_below && !below;
-        if (below) { xk = kx; yk = ky; ud0 = ud; k = j + 1; }
-        if (take) { xk1 = kx; yk1 = ky; ud1 = ud; }
-        prev_below = below;
+        cx[j] *= isx;
+        cy[j] *= isy;
+        const float wx = cx[j] + kRqMinBin, wy = cy[j] + kRqMinBin;      // bin sizes in units of the range
+        c += wx;
+        m[j] = (j < 7 && fmaf(span, c, lo) < vc) ? 1.0f : 0.0f;          // knot 8 = +b is never below v
+        d[j] = Mj - m[j];
+        Cx = fmaf(m[j], wx, Cx);  Cx1 = fmaf(Mj, wx, Cx1);
+        Cy = fmaf(m[j], wy, Cy);  Cy1 = fmaf(Mj, wy, Cy1);
+        const float aj = j == 0 ? kRqEdgeU : p[16 + (j == 0 ? 0 : j - 1)];       // derivative logit of knot j
+        const float aj1 = j == 7 ? kRqEdgeU : p[16 + (j == 7 ? 0 : j)];          // ... of knot j + 1
+        ud0 = fmaf(d[j], aj, ud0);
+        ud1 = fmaf(d[j], aj1, ud1);
+        Mj = m[j];
     }
+    const float xk = fmaf(span, Cx, lo), yk = fmaf(span, Cy, lo);
+    const float xk1 = d[7] != 0.0f ? b : fmaf(span, Cx1, lo), yk1 = d[7] != 0.0f ? b : fmaf(span, Cy1, lo);    // knot 8 is pinned
     // evaluation inside the bin (rational_quadratic.py:88-109)
     const float w = xk1 - xk, hgt = yk1 - yk;
     const float iw = f_rcpn(w);
     const float sk = hgt * iw;
-    const float xr = (v - xk) * iw;
+    const float xr = (vc - xk) * iw;
     const float a0 = fmaf(ud0, 1e-3f, kRqEdgeU), a1 = fmaf(ud1, 1e-3f, kRqEdgeU);
     const float e0 = f_ex2(a0 * kLog2e), e1 = f_ex2(a1 * kLog2e);
     const float d0 = fmaf(f_lg2(1.0f + e0), kLn2, kRqMinDelta), d1 = fmaf(f_lg2(1.0f + e1), kLn2, kRqMinDelta);
@@ -282,34 +289,35 @@ B2F_HD void backward_fwd(float v, const float (&p)[24], float b, float GZ, float
     if (clipped) Gxi = 0.0f;
     const float Gs = fmaf(GZ, out_s, GL * ld_s);
     const float dvi = Gxi * iw;
-    const float Gxk = -dvi;
     const float Gw = -(fmaf(Gxi, xi, Gs * sk)) * iw;
     const float Ghgt = fmaf(GZ * A, iDn, Gs * iw);
     const float Gd0 = fmaf(GZ, out_d0, GL * ld_d0), Gd1 = fmaf(GZ, out_d1, GL * ld_d1);
-    // softmax backward: knot gradients g_j = span ([j < k] G_below + [j == k] G_at); J(p, g)_j = c1 p_j (g_j - sum_i p_i g_i)
-    float gxv[8], gyv[8];
+    // softmax backward: knot gradients g_j = span (m_j G_below + d_j G_at); J(p, g)_j = c1 p_j (g_j - sum_i p_i g_i)
+    const float sGxk = -span * dvi, sGw = span * Gw, sGyk = span * GZ, sGh = span * Ghgt;
+    float gx[8], gy[8];
     float dotx = 0.0f, doty = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        gxv[j] = span * (j < k ? Gxk : (j == k ? Gw : 0.0f));
-        gyv[j] = span * (j < k ? GZ : (j == k ? Ghgt : 0.0f));
-        dotx = fmaf(px[j], gxv[j], dotx);
-        doty = fmaf(py[j], gyv[j], doty);
+        gx[j] = fmaf(m[j], sGxk, d[j] * sGw);
+        gy[j] = fmaf(m[j], sGyk, d[j] * sGh);
+        dotx = fmaf(cx[j], gx[j], dotx);
+        doty = fmaf(cy[j], gy[j], doty);
     }
-    // out of bounds (identity tail): zero parameter gradient -- selected, not multiplied (w = 0 there, the values are NaN)
+    dotx *= 1.0f / kSizeScale;                    // cx carries c1: sum_i p_i g_i = dot / c1
+    doty *= 1.0f / kSizeScale;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float jx = kSizeScale * px[j] * (gxv[j] - dotx);
-        const float jy = kSizeScale * py[j] * (gyv[j] - doty);
-        dp[j] = inb ? jx + jy : 0.0f;
-        dp[8 + j] = inb ? jy * 1e-3f : 0.0f;
+        const float jx = cx[j] * (gx[j] - dotx);
+        const float jy = cy[j] * (gy[j] - doty);
+        dp[j] = jx + jy;
+        dp[8 + j] = jy * 1e-3f;
     }
     // derivative logits: softplus' = sigmoid = e / (1 + e); only knots k (lower) and k + 1 (upper) receive anything
     const float g0 = Gd0 * e0 * f_rcpn(1.0f + e0) * 1e-3f, g1 = Gd1 * e1 * f_rcpn(1.0f + e1) * 1e-3f;
 #pragma unroll
-    for (int jj = 1; jj < 8; ++jj) dp[16 + jj - 1] = inb ? (jj == k ? g0 : 0.0f) + (jj == k + 1 ? g1 : 0.0f) : 0.0f;
+    for (int jj = 1; jj < 8; ++jj) dp[16 + jj - 1] = fmaf(d[jj], g0, d[jj - 1] * g1);
     dp[23] = 0.0f;
-    dv = inb ? dvi : GZ;
+    dv = inb ? dvi : GZ_in;
 }
 
 }  // namespace rqf
