@@ -249,6 +249,14 @@ int b2f_column_run_apply(const b2f_colop_t *ops, int32_t n_ops, const float *x, 
 int b2f_column_run_backward(const b2f_colop_t *ops, int32_t n_ops, const float *x, const float *gy, const float *g_log_det_sum,
                             float *gx, float *scratch, int64_t B, int32_t D, void *stream);
 
+/* DiagonalGaussian.log_prob over rows (base_distributions/gaussian.py:46-54) for flows whose layers are not one program
+ * (z:(B,D) comes back from the last layer): log_prob:(B); loc / log_scale:(D) nullable = standard normal.  Backward:
+ * gz:(B,D) = dL/dz given g_log_prob:(B) (the base parameters are not differentiated: trainable bases stay on torch ops). */
+int b2f_gauss_log_prob(const float *z, const float *loc, const float *log_scale, float *log_prob, int64_t B, int32_t D,
+                       void *stream);
+int b2f_gauss_log_prob_backward(const float *z, const float *loc, const float *log_scale, const float *g_log_prob, float *gz,
+                                int64_t B, int32_t D, void *stream);
+
 /* Per-dimension batch statistics for ActNorm's data-dependent initialisation (layers.py:58-68):
  * sum:(D) and sumsq:(D) of x:(B,D), accumulated in fp64 (must be zeroed by the caller). */
 int b2f_column_stats(const float *x, double *sum, double *sumsq, int64_t B, int32_t D, void *stream);

@@ -245,3 +245,28 @@ def test_cluster_and_single_cta_spline_gemms_agree():
     assert float((outs[0][1] - outs[1][1]).abs().max()) < 1e-5
     for a, b_ in zip(outs[0][2:], outs[1][2:]):
         assert rel(a, b_) < 1e-4
+
+
+def test_base_log_prob_kernel_matches_torch_ops():
+    """b2f_gauss_log_prob / _backward (base density of flows whose layers are not one program) against
+    DiagonalGaussian.log_prob (base_distributions/gaussian.py:46-54) and its autograd."""
+    from torchflows_b200 import Flow
+    from torchflows_b200.architectures import CouplingRQNSF
+    dev = torch.device('cuda:0')
+    torch.manual_seed(8)
+    flow = Flow(CouplingRQNSF(64)).to(dev)
+    with torch.no_grad():
+        flow.base.loc.copy_(torch.randn(64, device=dev))
+        flow.base.log_scale.copy_(0.3 * torch.randn(64, device=dev))
+    for B in (1, 33, 1000):
+        z = torch.randn(B, 64, device=dev, requires_grad=True)
+        lp = flow.base_log_prob(z)
+        g = torch.randn(B, device=dev)
+        (lp * g).sum().backward()
+        z64 = z.detach().double().requires_grad_(True)
+        ref = flow.base.double().log_prob(z64) if False else None
+        loc, ls = flow.base.loc.double(), flow.base.log_scale.double()
+        ref = (-(0.5 * ((z64 - loc) / ls.exp()) ** 2 + 0.5 * torch.log(torch.tensor(2 * torch.pi, dtype=torch.float64)) + ls)).sum(-1)
+        (ref * g.double()).sum().backward()
+        assert float((lp.double() - ref).abs().max()) < 1e-4 * (1 + float(ref.abs().max()))
+        assert rel(z.grad, z64.grad) < 1e-6

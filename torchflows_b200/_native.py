@@ -84,6 +84,8 @@ def lib():
         u64 = ctypes.c_uint64
         L.b2f_flow_sample.argtypes = [ctypes.POINTER(Op), i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, u64, u64, vp]
         L.b2f_philox_normal.argtypes = [vp, i64, i32, vp, vp, u64, u64, vp]
+        L.b2f_gauss_log_prob.argtypes = [vp, vp, vp, vp, i64, i32, vp]
+        L.b2f_gauss_log_prob_backward.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp]
         L.b2f_column_run_apply.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, i64, i32, vp]
         L.b2f_column_run_backward.argtypes = [ctypes.POINTER(ColOp), i32, vp, vp, vp, vp, vp, i64, i32, vp]
         L.b2f_wide_coupling_workspace.argtypes = [i64, i32, i32, i32]
@@ -360,3 +362,22 @@ def flow_sample(ops: Sequence[dict], B: int, D: int, device, want_log_prob=False
                                        D, flags, seed, offset, stream_ptr(device))
         check(rc)
     return y, lp
+
+
+# ---- base density over rows (csrc/b2f_colrun.cu) ------------------------------------------------------------------------------
+def gauss_log_prob(z2: torch.Tensor, loc, log_scale) -> torch.Tensor:
+    z2 = require_cuda_f32(z2, 'base density input')
+    B, D = z2.shape
+    lp = torch.empty(B, device=z2.device, dtype=torch.float32)
+    with torch.cuda.device(z2.device):
+        check(lib().b2f_gauss_log_prob(ptr(z2), ptr(loc), ptr(log_scale), ptr(lp), B, D, stream_ptr(z2.device)))
+    return lp
+
+
+def gauss_log_prob_backward(z2: torch.Tensor, loc, log_scale, g: torch.Tensor) -> torch.Tensor:
+    g = require_cuda_f32(g, 'upstream gradient')
+    B, D = z2.shape
+    gz = torch.empty_like(z2)
+    with torch.cuda.device(z2.device):
+        check(lib().b2f_gauss_log_prob_backward(ptr(z2), ptr(loc), ptr(log_scale), ptr(g), ptr(gz), B, D, stream_ptr(z2.device)))
+    return gz

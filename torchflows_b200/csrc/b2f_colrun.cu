@@ -9,6 +9,8 @@
 // matrix/permutation.py:19-37 (ReversePermutationMatrix), and their autograd backward.
 #include <string.h>
 
+#include <algorithm>
+
 #include "b2f_common.cuh"
 #include "b2f_math.cuh"
 
@@ -195,6 +197,34 @@ __global__ void __launch_bounds__(256) finalize_kernel(const Ops P, const float*
     }
 }
 
+// DiagonalGaussian.log_prob of rows (base_distributions/gaussian.py:46-54): lp[r] = sum_c -(t^2 / 2 + log(2 pi) / 2 + ls_c),
+// t = (z - loc_c) exp(-ls_c); one warp per row.  Backward: gz[r, c] = -g[r] t exp(-ls_c).
+__global__ void __launch_bounds__(256) gauss_logp_kernel(const float* __restrict__ z, const float* __restrict__ loc,
+                                                         const float* __restrict__ ls, float* __restrict__ lp, long long B, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < B; r += n_warps) {
+        float acc = 0.0f;
+        for (int c = lane; c < D; c += 32) acc += gauss_logp(__ldg(z + r * D + c), loc ? __ldg(loc + c) : 0.0f, ls ? __ldg(ls + c) : 0.0f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) lp[r] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) gauss_logp_backward_kernel(const float* __restrict__ z, const float* __restrict__ loc,
+                                                                  const float* __restrict__ ls, const float* __restrict__ g,
+                                                                  float* __restrict__ gz, long long B, int D) {
+    const long long n = B * D, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long r = i / D;
+        const int c = (int)(i - r * D);
+        const float is = ls ? expf(-__ldg(ls + c)) : 1.0f;
+        const float t = (__ldg(z + i) - (loc ? __ldg(loc + c) : 0.0f)) * is;
+        gz[i] = -__ldg(g + r) * t * is;
+    }
+}
+
 static int make_ops(Ops& P, const b2f_colop_t* ops, int32_t n_ops, int32_t D, bool backward) {
     if (!ops || n_ops < 1 || n_ops > kMaxOps) return fail(B2F_ERR_INVALID, "column run: 1..%d ops", kMaxOps);
     if (D < 4 || D % 4 != 0) return fail(B2F_ERR_UNSUPPORTED, "column run: n_dim must be a multiple of 4");
@@ -249,4 +279,24 @@ extern "C" int b2f_column_run_backward(const b2f_colop_t* ops, int32_t n_ops, co
     }
     finalize_kernel<<<(D + 255) / 256, 256, 0, st>>>(P, scratch, g_log_det_sum, D);
     return check_launch("b2f_column_run_backward");
+}
+
+extern "C" int b2f_gauss_log_prob(const float* z, const float* loc, const float* log_scale, float* log_prob, int64_t B, int32_t D,
+                                  void* stream) {
+    if (B < 0 || D < 1) return fail(B2F_ERR_INVALID, "b2f_gauss_log_prob: shape");
+    if (B == 0) return B2F_OK;
+    if (!z || !log_prob) return fail(B2F_ERR_INVALID, "b2f_gauss_log_prob: null buffer");
+    const unsigned grid = (unsigned)std::min<long long>((B + 7) / 8, 148 * 8);
+    gauss_logp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, loc, log_scale, log_prob, B, D);
+    return check_launch("b2f_gauss_log_prob");
+}
+
+extern "C" int b2f_gauss_log_prob_backward(const float* z, const float* loc, const float* log_scale, const float* g_log_prob, float* gz,
+                                           int64_t B, int32_t D, void* stream) {
+    if (B < 0 || D < 1) return fail(B2F_ERR_INVALID, "b2f_gauss_log_prob_backward: shape");
+    if (B == 0) return B2F_OK;
+    if (!z || !g_log_prob || !gz) return fail(B2F_ERR_INVALID, "b2f_gauss_log_prob_backward: null buffer");
+    const unsigned grid = (unsigned)std::min<long long>((B * D + 255) / 256, 148 * 16);
+    gauss_logp_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, loc, log_scale, g_log_prob, gz, B, D);
+    return check_launch("b2f_gauss_log_prob_backward");
 }

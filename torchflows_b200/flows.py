@@ -52,6 +52,20 @@ def allreduce_gradients(parameters, world: int) -> None:
         offset += n
 
 
+class _GaussLogProb(torch.autograd.Function):
+    """DiagonalGaussian.log_prob over rows with fixed parameters (gaussian.py:46-54): b2f_gauss_log_prob / _backward."""
+
+    @staticmethod
+    def forward(ctx, z2, loc, log_scale):
+        ctx.save_for_backward(z2, loc, log_scale)
+        return N.gauss_log_prob(z2, loc, log_scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        z2, loc, log_scale = ctx.saved_tensors
+        return N.gauss_log_prob_backward(z2, loc, log_scale, g.contiguous()), None, None
+
+
 class GradBuckets:
     """Data-parallel gradient exchange of ``Flow.fit``: one bucket per layer of the bijection, gradients
     LIVING in the bucket (every ``p.grad`` is a view into its bucket's flat buffer, so nothing is packed or copied back),
@@ -213,7 +227,14 @@ class BaseFlow(nn.Module):
         return self.device_buffer.device
 
     def base_log_prob(self, z: torch.Tensor):
-        return self.base.log_prob(flatten_event(z, self.event_shape))
+        zf = flatten_event(z, self.event_shape)
+        if zf.is_cuda and zf.dtype == torch.float32 and self._fusable_base():
+            # one kernel each way instead of six elementwise passes (flows whose layers are not a single program)
+            batch_shape = zf.shape[:-1]
+            lp = _GaussLogProb.apply(zf.reshape(-1, zf.shape[-1]), self.base.loc.detach().reshape(-1).contiguous(),
+                                     self.base.log_scale.detach().reshape(-1).contiguous())
+            return lp.reshape(batch_shape)
+        return self.base.log_prob(zf)
 
     def base_sample(self, sample_shape: Union[torch.Size, Tuple[int, ...]]):
         return unflatten_event(self.base.sample(sample_shape), self.event_shape)
