@@ -264,7 +264,6 @@ def test_base_log_prob_kernel_matches_torch_ops():
         g = torch.randn(B, device=dev)
         (lp * g).sum().backward()
         z64 = z.detach().double().requires_grad_(True)
-        ref = flow.base.double().log_prob(z64) if False else None
         loc, ls = flow.base.loc.double(), flow.base.log_scale.double()
         ref = (-(0.5 * ((z64 - loc) / ls.exp()) ** 2 + 0.5 * torch.log(torch.tensor(2 * torch.pi, dtype=torch.float64)) + ls)).sum(-1)
         (ref * g.double()).sum().backward()

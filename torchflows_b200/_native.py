@@ -237,7 +237,8 @@ _wide_ws = {}
 def _wide_buffer(device, role: str, need: int) -> torch.Tensor:
     """Shared buffers of the wide layer kernels, one per (device, role) that only grows: the layers of a flow run one
     after the other on one stream and nothing in them outlives a call (what must survive until the backward is allocated
-    per call instead, see wide_coupling_forward)."""
+    per call instead, see wide_coupling_forward).  Callers that drive wide layers from SEVERAL streams or threads at once
+    must give each its own buffers (the C ABI takes them as arguments; this cache is a convenience of the Python side)."""
     key = (device.type, device.index, role)
     buf = _wide_ws.get(key)
     if buf is None or buf.numel() * 4 < need:
