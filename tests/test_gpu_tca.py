@@ -125,3 +125,23 @@ def test_tca_sample_draws_noise_in_the_kernel():
         x2, lp2 = flow._sample_from_base(z, no_grad=True, return_log_prob=True)
     assert float((x1 - x2).abs().max()) <= 1e-5 * (1 + float(x2.abs().max()))
     assert float((lp1 - lp2).abs().max()) <= 1e-4 * (1 + float(lp2.abs().max()))
+
+
+def test_tca_sample_with_a_non_standard_base():
+    from torchflows_b200 import Flow, _native as N, _program as prog
+    from torchflows_b200.architectures import RealNVP
+    dev = torch.device('cuda:0')
+    torch.manual_seed(6)
+    flow = Flow(RealNVP(32)).to(dev).eval()
+    with torch.no_grad():
+        flow.base.loc.copy_(torch.randn(32, device=dev))
+        flow.base.log_scale.copy_(torch.randn(32, device=dev) * 0.2)
+        torch.manual_seed(9)
+        x, lp = flow.sample((3000,), no_grad=True, return_log_prob=True)
+        assert N.last_flow_kernel() == N.KERNEL_TCA
+        torch.manual_seed(9)
+        seed, offset = prog.next_noise_stream()
+        z = N.philox_normal(3000, 32, dev, seed, offset, flow.base.loc.reshape(-1), flow.base.log_scale.reshape(-1))
+        x2, lp2 = flow._sample_from_base(z, no_grad=True, return_log_prob=True)
+    assert float((x - x2).abs().max()) <= 1e-5 * (1 + float(x2.abs().max()))
+    assert float((lp - lp2).abs().max()) <= 1e-4 * (1 + float(lp2.abs().max()))

@@ -269,3 +269,42 @@ def test_base_log_prob_kernel_matches_torch_ops():
         (ref * g.double()).sum().backward()
         assert float((lp.double() - ref).abs().max()) < 1e-4 * (1 + float(ref.abs().max()))
         assert rel(z.grad, z64.grad) < 1e-6
+
+
+def test_default_width_couplings_can_train_through_the_wide_pipeline():
+    """B2F_WIDE_TRAINING=1: spline couplings that fit the whole-flow kernels take the per-layer GEMM pipeline when gradients
+    are needed (hidden width padded to the k-block with exact zeros).  Same loss, gradients within the TF32-conditioner
+    tolerance of the default (fp32-faithful recompute) path."""
+    import os
+    from torchflows_b200 import Flow, _native as N
+    from torchflows_b200.architectures import CouplingRQNSF
+    dev = torch.device('cuda:0')
+    torch.manual_seed(12)
+    flow = Flow(CouplingRQNSF(128)).to(dev)
+    x = torch.randn(2000, 128, device=dev)
+    out = []
+    for wide in (False, True):
+        if wide:
+            os.environ['B2F_WIDE_TRAINING'] = '1'
+        try:
+            flow.zero_grad()
+            calls = {'n': 0}
+            orig = N.wide_coupling_backward
+
+            def spy(*a, **k):
+                calls['n'] += 1
+                return orig(*a, **k)
+            N.wide_coupling_backward = spy
+            try:
+                loss = flow._base_batch_loss((x, torch.ones(len(x), device=dev)))
+                loss.backward()
+            finally:
+                N.wide_coupling_backward = orig
+            assert (calls['n'] > 0) == wide
+            out.append((float(loss.detach()), {k: p.grad.clone() for k, p in flow.named_parameters() if p.grad is not None}))
+        finally:
+            os.environ.pop('B2F_WIDE_TRAINING', None)
+    assert abs(out[0][0] - out[1][0]) <= 1e-4 * (1 + abs(out[0][0]))
+    for k, g in out[0][1].items():
+        if g.norm() > 0:
+            assert rel(out[1][1][k], g) < 2e-2, (k, rel(out[1][1][k], g))
