@@ -34,10 +34,10 @@ WORKLOADS = {
 
 
 # the kernel each workload's log_prob launch dispatches to (b2f_flow_apply: csrc/b2f_flow.cu)
-KERNELS = {'q256': 'b2f::flow_tcq_kernel', 'mq128': 'b2f::flow_tc_kernel', 'r64': 'b2f::flow_tca_kernel',
+KERNELS = {'q256': 'b2f::flow_tcq_kernel', 'mq128': 'b2f::flow_tcm_kernel', 'r64': 'b2f::flow_tca_kernel',
            'm128': 'b2f::flow_rows_kernel'}
 KERNEL_IDS = {0: 'none', 1: 'generic (b2f_flow.cu)', 2: 'tc (b2f_flow_tc.cu)', 3: 'rows (b2f_flow_rows.cu)',
-              4: 'tcq (b2f_flow_tcq.cu)', 5: 'tca (b2f_flow_tca.cu)'}
+              4: 'tcq (b2f_flow_tcq.cu)', 5: 'tca (b2f_flow_tca.cu)', 6: 'tcm (b2f_flow_tcm.cu)'}
 
 
 def algorithmic_bytes(D):

@@ -102,6 +102,20 @@ enum b2f_op_kind {
                                          tgt    [Dh][8] and src [Dh][2] as for B2F_FLAG_TCQ_OPERANDS
                                        p[5] (first coupling op) = program blob, as for B2F_FLAG_TCQ_OPERANDS */
 
+#define B2F_FLAG_TCM_OPERANDS 32    /* op flag (MADE, RQ, n_bins 8, one-pass direction), set on EVERY MADE op of a program made of
+                                       ELEMENTWISE / FLIP / MADE ops: the program is laid out for the masked-autoregressive spline
+                                       kernel (csrc/b2f_flow_tcm.cu; layout produced by torchflows_b200/_tcm.py):
+                                       p[4] = layer blob (fp32 words, 16-byte aligned), K2 = roundup(H+2, 8):
+                                         [0,8)  int32 header: magic 'BTCM', 0, 1 if the tile must be materialised first (src affine
+                                                below), H, K2, D/2 chunks, D, 0
+                                         W1c    canonical [32 x D] tf32 of W1 * mask1, columns in PHYSICAL order
+                                         b1     32 floats (zero padded)
+                                         W2c    D/2 chunks, each canonical [48 x K2]: folded columns of (W2 * mask2, b2) as for
+                                                B2F_FLAG_TCQ_OPERANDS, elements in PHYSICAL order
+                                         tgt    [D][8], src [D][2], misc [4] as for B2F_FLAG_TCQ_OPERANDS
+                                       p[5] (first MADE op) = program blob: int32 {magic, final pass, 0, layers}, then as for
+                                         B2F_FLAG_TCQ_OPERANDS */
+
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
     int32_t tkind;    /* enum b2f_transformer */
@@ -281,6 +295,7 @@ int32_t b2f_abi_version(void);
 #define B2F_KERNEL_ROWS 3
 #define B2F_KERNEL_TCQ 4 /* csrc/b2f_flow_tcq.cu: spline coupling programs laid out with B2F_FLAG_TCQ_OPERANDS */
 #define B2F_KERNEL_TCA 5 /* csrc/b2f_flow_tca.cu: affine / shift coupling programs laid out with B2F_FLAG_TCA_OPERANDS */
+#define B2F_KERNEL_TCM 6 /* csrc/b2f_flow_tcm.cu: one-pass MADE spline programs laid out with B2F_FLAG_TCM_OPERANDS */
 int32_t b2f_last_flow_kernel(void);
 
 #ifdef __cplusplus

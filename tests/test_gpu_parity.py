@@ -280,6 +280,6 @@ def test_mq128_many_tiles_vs_oracle(dev, state):
     o = fo.OracleFlow('MaskedAutoregressiveRQNSF', (D,), {k: v.cpu() for k, v in flow.state_dict().items()})
     with torch.no_grad():
         lp = flow.log_prob(x.to(dev))
-    assert N.last_flow_kernel() == N.KERNEL_TC
+    assert N.last_flow_kernel() == N.KERNEL_TCM
     ref = torch.cat([o.log_prob(x[i:i + 4096]) for i in range(0, B, 4096)])
     close(lp, ref, f'MQ128 log_prob state {state}', LP_TOL, LP_TOL)

@@ -77,6 +77,7 @@ def test_tensor_core_flow_matches_generic_kernel_and_oracle(preset, D, B):
     os.environ.pop('B2F_DISABLE_TC', None)
     os.environ['B2F_DISABLE_ROWS'] = '1'       # affine / shift presets would otherwise take the row-per-thread kernel
     os.environ['B2F_DISABLE_TCQ'] = '1'        # spline coupling presets would otherwise take the second-generation kernel
+    os.environ['B2F_DISABLE_TCM'] = '1'        # ... and one-pass MADE spline programs the masked-autoregressive one
     try:
         from torchflows_b200 import _native as N_
         tc = _lp_and_sample(flow, x.to(dev), z.to(dev))
@@ -89,6 +90,7 @@ def test_tensor_core_flow_matches_generic_kernel_and_oracle(preset, D, B):
         os.environ.pop('B2F_DISABLE_TC', None)
         os.environ.pop('B2F_DISABLE_ROWS', None)
         os.environ.pop('B2F_DISABLE_TCQ', None)
+        os.environ.pop('B2F_DISABLE_TCM', None)
     names = ('log_prob', 'z', 'log_det', 'sample', 'sample log_prob')
     for a, b, n in zip(tc, gen, names):
         a, b = a.double().cpu(), b.double().cpu()

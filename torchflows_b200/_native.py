@@ -19,11 +19,12 @@ FLAG_TC_OPERANDS = 2
 FLAG_TC_FLIPPED = 4
 FLAG_TCQ_OPERANDS = 8
 FLAG_TCA_OPERANDS = 16
+FLAG_TCM_OPERANDS = 32
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 FLOW_MODE_FAST_KNOTS = 4
 FLOW_WS_FILLED = 8
-KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS, KERNEL_TCQ, KERNEL_TCA = range(6)
+KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS, KERNEL_TCQ, KERNEL_TCA, KERNEL_TCM = range(7)
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
                 T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}

@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _native as N
-from . import _tca, _tcq
+from . import _tca, _tcm, _tcq
 
 
 @dataclass
@@ -173,7 +173,7 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
 
 
 def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None,
-             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None, tca_plan=None):
+             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None, tca_plan=None, tcm_plan=None):
     """b2f_op descriptors of a program.  ``tcq_plan``: the program is laid out for the second-generation spline kernel
     (csrc/b2f_flow_tcq.cu): every coupling op carries its blob in p[4], the first one the program blob in p[5]."""
     out = []
@@ -183,6 +183,10 @@ def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.
         p, flags = list(kernel_params(op)), op.flags
         if op.kind == N.OP_FLIP:
             flipped = not flipped
+        elif tcm_plan is not None and op.kind == N.OP_MADE:           # one-pass MADE spline kernel (csrc/b2f_flow_tcm.cu)
+            p = p[:4] + [tcm_plan.layer_blobs[n_coupling], tcm_plan.program_blob if n_coupling == 0 else None]
+            flags |= N.FLAG_TCM_OPERANDS
+            n_coupling += 1
         elif tcq_plan is not None and op.kind == N.OP_COUPLING:
             p = p[:4] + [tcq_plan.layer_blobs[n_coupling], tcq_plan.program_blob if n_coupling == 0 else None]
             flags |= N.FLAG_TCQ_OPERANDS
@@ -349,9 +353,18 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
             and _tcq.eligible(ops, D)):
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
-    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=_tca_plan(ops, D, base_loc, base_log_scale, flags)),
+    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=_tca_plan(ops, D, base_loc, base_log_scale, flags),
+                                      tcm_plan=_tcm_plan(ops, D, base_loc, base_log_scale, flags)),
                              x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
     return y, ld, lp
+
+
+def _tcm_plan(ops, D, base_loc, base_log_scale, flags):
+    """Operand plan of the one-pass MADE spline kernel if the program is one it takes, else None."""
+    if (flags & N.FLOW_MODE_PRECISE) or os.environ.get('B2F_DISABLE_TCM') or os.environ.get('B2F_DISABLE_TC') \
+            or not _tcm.eligible(ops, D):
+        return None
+    return _tcm.cached_plan(ops, D, base_loc, base_log_scale)
 
 
 def _tca_plan(ops, D, base_loc, base_log_scale, flags):
@@ -383,8 +396,9 @@ def run_sample_program(ops: Sequence[LoweredOp], B: int, D: int, device, want_lo
             and _tcq.eligible(ops, D)):
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
     tca = _tca_plan(ops, D, base_loc, base_log_scale, flags) if plan is None else None
-    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=tca), B, D, device, want_log_prob, base_loc, base_log_scale,
-                         flags, seed, offset, in_kernel=plan is not None or tca is not None)
+    tcm = _tcm_plan(ops, D, base_loc, base_log_scale, flags) if plan is None and tca is None else None
+    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=tca, tcm_plan=tcm), B, D, device, want_log_prob, base_loc,
+                         base_log_scale, flags, seed, offset, in_kernel=plan is not None or tca is not None or tcm is not None)
 
 
 # ---- runs of per-column layers outside whole-flow programs (csrc/b2f_colrun.cu) ---------------------------------------------

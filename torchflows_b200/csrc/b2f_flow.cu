@@ -205,6 +205,8 @@ int try_launch_flow_tcq(const b2f_op_t* ops, int32_t n_ops, const float* x, floa
                         int64_t B, int32_t D, int32_t flags, void* stream, const TcqNoise* noise);   // b2f_flow_tcq.cu
 int try_launch_flow_tca(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                         int64_t B, int32_t D, int32_t flags, void* stream, const TcqNoise* noise);   // b2f_flow_tca.cu
+int try_launch_flow_tcm(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
+                        int64_t B, int32_t D, int32_t flags, void* stream, const TcqNoise* noise);   // b2f_flow_tcm.cu
 int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, float* y, float* log_det, float* log_prob,
                          const float* base_loc, const float* base_log_scale, int64_t B, int32_t D, int32_t flags,
                          void* stream);  // b2f_flow_rows.cu
@@ -230,6 +232,9 @@ static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, f
             const int rc = try_launch_flow_tcq(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream, nullptr);
             if (rc == 1) last_flow_kernel() = B2F_KERNEL_TCQ;
             if (rc != 0) return rc == 1 ? B2F_OK : rc;
+            const int rm = try_launch_flow_tcm(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream, nullptr);
+            if (rm == 1) last_flow_kernel() = B2F_KERNEL_TCM;
+            if (rm != 0) return rm == 1 ? B2F_OK : rm;
         }
         if (!has_rq && !ws) {      // affine / shift coupling programs laid out for the multi-tile tensor-core kernel
             const int rc = try_launch_flow_tca(ops, n_ops, x, y, log_det, log_prob, B, D, flags, stream, nullptr);
@@ -344,6 +349,9 @@ extern "C" int b2f_flow_sample(const b2f_op_t* ops, int32_t n_ops, float* y, flo
     if (rc != 0) return rc;
     rc = try_launch_flow_tca(ops, n_ops, nullptr, y, log_det, log_prob, B, D, flags, stream, &nz);
     if (rc == 1) { last_flow_kernel() = B2F_KERNEL_TCA; return B2F_OK; }
+    if (rc != 0) return rc;
+    rc = try_launch_flow_tcm(ops, n_ops, nullptr, y, log_det, log_prob, B, D, flags, stream, &nz);
+    if (rc == 1) { last_flow_kernel() = B2F_KERNEL_TCM; return B2F_OK; }
     if (rc != 0) return rc;
     // every other program: the same stream, materialised once, then the ordinary launch
     if (!noise_scratch) return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_sample: this program needs a noise scratch buffer of B * D floats");
