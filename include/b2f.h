@@ -33,7 +33,12 @@ enum b2f_transformer {
     B2F_T_AFFINE_FWD = 2, /* Affine.forward / InverseAffine.inverse  z = a*x + u1, ld = +log a   affine.py:39-48 */
     B2F_T_AFFINE_INV = 3, /* Affine.inverse / InverseAffine.forward  x = (z-u1)/a, ld = -log a   affine.py:50-59 */
     B2F_T_RQ_FWD = 4,     /* RationalQuadratic.forward   spline/base.py:53-60, rational_quadratic.py:65-128 */
-    B2F_T_RQ_INV = 5      /* RationalQuadratic.inverse   spline/base.py:65-72, rational_quadratic.py:130-200 */
+    B2F_T_RQ_INV = 5,     /* RationalQuadratic.inverse   spline/base.py:65-72, rational_quadratic.py:130-200 */
+    /* stand-alone transformer entry points only (b2f_transformer_apply / _backward), not flow programs: */
+    B2F_T_LRS_FWD = 6,    /* LinearRational.forward      spline/linear_rational.py:92-135; 4 * n_bins parameters per element */
+    B2F_T_LRS_INV = 7,    /* LinearRational.inverse      spline/linear_rational.py:137-182 */
+    B2F_T_SCALE_FWD = 8,  /* Scale.forward               z = a*x, ld = +log a    affine.py:186-193 */
+    B2F_T_SCALE_INV = 9   /* Scale.inverse               x = z/a, ld = -log a    affine.py:195-202 */
 };
 
 /* One step of a flow program = one layer of BijectiveComposition (bijections/base.py:203-232) applied

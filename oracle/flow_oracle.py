@@ -190,25 +190,134 @@ def rq_inverse(z: Tensor, h: Tensor, n_bins: int = 8, boundary: float = 50.0, n_
     return (x, ld, kk) if return_bins else (x, ld)
 
 
+# ---- linear rational spline (transformers/spline/linear_rational.py:9-182) ---------------------------------
+LRS_MIN_BIN = 1e-2                                        # linear_rational.py:19-20
+LRS_MIN_D = 1e-5                                          # linear_rational.py:21
+LRS_CONST = math.log(math.exp(1 - LRS_MIN_D) - 1)         # linear_rational.py:22
+LRS_EPS = 5e-10                                           # linear_rational.py:23
+
+
+def lrs_bins(u: Tensor, lo: float, hi: float, n_bins: int) -> Tensor:
+    """linear_rational.py:67-75 (compute_bins)."""
+    sizes = torch.softmax(u, dim=-1)
+    sizes = LRS_MIN_BIN + (1 - LRS_MIN_BIN * n_bins) * sizes
+    bins = torch.cumsum(sizes, dim=-1)
+    bins = F.pad(bins, pad=(1, 0), mode='constant', value=0.0)
+    bins = (hi - lo) * bins + lo
+    bins[..., 0] = lo
+    bins[..., -1] = hi
+    return bins
+
+
+def _lrs_knots(h: Tensor, n_bins: int, boundary: float):
+    """linear_rational.py:82-90 (compute_knots) and the parameter split of :96-100."""
+    K = n_bins
+    u_x, u_y, u_l, u_d, u_w0 = h[:, :K], h[:, K:2 * K], h[:, 2 * K:3 * K], h[:, 3 * K:4 * K - 1], h[:, 4 * K - 1]
+    knots_x = lrs_bins(u_x, -boundary, boundary, K)
+    knots_y = lrs_bins(u_x + u_y / 100, -boundary, boundary, K)
+    knots_lambda = torch.sigmoid(u_l)
+    knots_d = F.pad(F.softplus(LRS_CONST + u_d / 100) + LRS_MIN_D, pad=(1, 1), mode='constant', value=1.0)
+    return knots_x, knots_y, knots_d, knots_lambda, u_w0
+
+
+def _lrs_parameters(idx, knots_x, knots_y, knots_d, knots_lambda, u_w0):
+    """linear_rational.py:30-65 (compute_parameters)."""
+    w0 = F.softplus(u_w0)
+    w = w0[:, None] * torch.sqrt(knots_d[:, 0][:, None] / knots_d)
+    w_k, w_kp1 = w.gather(1, idx), w.gather(1, idx + 1)
+    lambda_k = knots_lambda.gather(1, idx)
+    x_k, x_kp1 = knots_x.gather(1, idx), knots_x.gather(1, idx + 1)
+    y_k, y_kp1 = knots_y.gather(1, idx), knots_y.gather(1, idx + 1)
+    d_k, d_kp1 = knots_d.gather(1, idx), knots_d.gather(1, idx + 1)
+    y_m = torch.divide((1 - lambda_k) * w_k * y_k + lambda_k * w_kp1 * y_kp1, (1 - lambda_k) * w_k + lambda_k * w_kp1)
+    w_m = torch.multiply(lambda_k * w_k * d_k + (1 - lambda_k) * w_kp1 * d_kp1, torch.divide(x_kp1 - x_k, y_kp1 - y_k))
+    return lambda_k, w_k, w_m, w_kp1, x_k, x_kp1, y_k, y_m, y_kp1
+
+
+def lrs_forward_1d(x: Tensor, h: Tensor, n_bins: int, boundary: float):
+    """linear_rational.py:92-135."""
+    knots_x, knots_y, knots_d, knots_lambda, u_w0 = _lrs_knots(h, n_bins, boundary)
+    idx = torch.searchsorted(knots_x, x[:, None]) - 1
+    lam, w_k, w_m, w_kp1, x_k, x_kp1, y_k, y_m, y_kp1 = _lrs_parameters(idx, knots_x, knots_y, knots_d, knots_lambda, u_w0)
+    phi = (x[:, None] - x_k) / (x_kp1 - x_k)
+    mask = phi > lam
+    out_lt = torch.divide(w_k * y_k * (lam - phi) + w_m * y_m * phi, w_k * (lam - phi) + w_m * phi)
+    ld_lt = (torch.log(lam * w_k * w_m * (y_m - y_k)) - torch.log((w_k * (lam - phi) + w_m * phi) ** 2 + LRS_EPS)
+             - torch.log(x_kp1 - x_k))
+    out_gt = torch.divide(w_m * y_m * (1 - phi) + w_kp1 * y_kp1 * (phi - lam), w_m * (1 - phi) + w_kp1 * (phi - lam))
+    ld_gt = (torch.log((1 - lam) * w_m * w_kp1 * (y_kp1 - y_m))
+             - torch.log((w_m * (1 - phi) + w_kp1 * (phi - lam)) ** 2 + LRS_EPS) - torch.log(x_kp1 - x_k))
+    return torch.where(mask, out_gt, out_lt).flatten(), torch.where(mask, ld_gt, ld_lt).flatten()
+
+
+def lrs_inverse_1d(z: Tensor, h: Tensor, n_bins: int, boundary: float):
+    """linear_rational.py:137-182."""
+    knots_x, knots_y, knots_d, knots_lambda, u_w0 = _lrs_knots(h, n_bins, boundary)
+    idx = torch.searchsorted(knots_y, z[:, None]) - 1
+    lam, w_k, w_m, w_kp1, x_k, x_kp1, y_k, y_m, y_kp1 = _lrs_parameters(idx, knots_x, knots_y, knots_d, knots_lambda, u_w0)
+    z = z[:, None]
+    mask = z > y_m
+    out_lt = torch.divide(lam * w_k * (y_k - z), w_k * (y_k - z) + w_m * (z - y_m)) * (x_kp1 - x_k) + x_k
+    ld_lt = (torch.log(lam * w_k * w_m * (y_m - y_k)) - torch.log((w_k * (y_k - z) + w_m * (z - y_m)) ** 2 + LRS_EPS)
+             + torch.log(x_kp1 - x_k))
+    out_gt = torch.divide(lam * w_kp1 * (y_kp1 - z) + w_m * (z - y_m), w_kp1 * (y_kp1 - z) + w_m * (z - y_m)) * (x_kp1 - x_k) + x_k
+    ld_gt = (torch.log((1 - lam) * w_m * w_kp1 * (y_kp1 - y_m))
+             - torch.log((w_kp1 * (y_kp1 - z) + w_m * (z - y_m)) ** 2 + LRS_EPS) + torch.log(x_kp1 - x_k))
+    return torch.where(mask, out_gt, out_lt).flatten(), torch.where(mask, ld_gt, ld_lt).flatten()
+
+
+def _lrs_apply(fn, v: Tensor, h: Tensor, n_bins: int, boundary: float, n_event_dims: int):
+    """MonotonicSpline.forward / inverse (spline/base.py:53-72): strict in-bounds mask, identity tails."""
+    out = torch.clone(v)
+    ld = torch.zeros_like(out)
+    mask = (v > -boundary) & (v < boundary)
+    if torch.any(mask):
+        o, l = fn(v[mask], h[mask], n_bins, boundary)
+        out = out.masked_scatter(mask, o)
+        ld = ld.masked_scatter(mask, l)
+    return out, _sum_event(ld, n_event_dims)
+
+
+def lrs_forward(x: Tensor, h: Tensor, n_bins: int = 8, boundary: float = 50.0, n_event_dims: int = 1):
+    return _lrs_apply(lrs_forward_1d, x, h, n_bins, boundary, n_event_dims)
+
+
+def lrs_inverse(z: Tensor, h: Tensor, n_bins: int = 8, boundary: float = 50.0, n_event_dims: int = 1):
+    return _lrs_apply(lrs_inverse_1d, z, h, n_bins, boundary, n_event_dims)
+
+
+# ---- Scale (transformers/linear/affine.py:160-200): z = alpha * x, alpha as for Affine with its own constant ----------
+def scale_forward(x: Tensor, h: Tensor, n_event_dims: int = 1) -> Tuple[Tensor, Tensor]:
+    alpha = torch.exp(math.log(1 - AFFINE_MIN_SCALE) + h[..., 0] / 2.0) + AFFINE_MIN_SCALE
+    return alpha * x, _sum_event(torch.log(alpha), n_event_dims)
+
+
+def scale_inverse(z: Tensor, h: Tensor, n_event_dims: int = 1) -> Tuple[Tensor, Tensor]:
+    alpha = torch.exp(math.log(1 - AFFINE_MIN_SCALE) + h[..., 0] / 2.0) + AFFINE_MIN_SCALE
+    return z / alpha, -_sum_event(torch.log(alpha), n_event_dims)
+
+
 TRANSFORMERS = {
     # kind -> (forward, inverse, params per element)
     'affine': (affine_forward, affine_inverse),
     'inverse_affine': (affine_inverse, affine_forward),   # affine.py:62-70
     'shift': (shift_forward, shift_inverse),
     'rq': (rq_forward, rq_inverse),
+    'lrs': (lrs_forward, lrs_inverse),
+    'scale': (scale_forward, scale_inverse),
 }
 
 
 def transformer_apply(kind: str, direction: str, x: Tensor, h: Tensor, **kw):
     fwd, inv = TRANSFORMERS[kind]
     fn = fwd if direction == 'forward' else inv
-    if kind == 'rq':
+    if kind in ('rq', 'lrs'):
         return fn(x, h, **kw)
     return fn(x, h)
 
 
 def params_per_element(kind: str, n_bins: int = 8) -> int:
-    return {'affine': 2, 'inverse_affine': 2, 'shift': 1, 'rq': 3 * n_bins - 1}[kind]
+    return {'affine': 2, 'inverse_affine': 2, 'shift': 1, 'rq': 3 * n_bins - 1, 'lrs': 4 * n_bins, 'scale': 1}[kind]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -283,6 +392,9 @@ PRESETS = {
     'CouplingRQNSF': ('coupling', 'rq'),
     'MaskedAutoregressiveRQNSF': ('ma', 'rq'),
     'InverseAutoregressiveRQNSF': ('inverse_ma', 'rq'),
+    'CouplingLRS': ('coupling', 'lrs'),                   # architectures.py:166-223
+    'MaskedAutoregressiveLRS': ('ma', 'lrs'),
+    'InverseAutoregressiveLRS': ('inverse_ma', 'lrs'),
 }
 
 
@@ -320,7 +432,7 @@ class OracleFlow:
 
     # -- helpers -------------------------------------------------------------------------------
     def _tkw(self, spec):
-        return dict(n_bins=self.n_bins, boundary=self.boundary) if spec.transformer == 'rq' else {}
+        return dict(n_bins=self.n_bins, boundary=self.boundary) if spec.transformer in ('rq', 'lrs') else {}
 
     def _flat(self, x: Tensor) -> Tensor:
         return x.reshape(*x.shape[: x.dim() - len(self.event_shape)], self.n_dim)

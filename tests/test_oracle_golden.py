@@ -68,3 +68,30 @@ def test_gradients_match_reference_autograd(golden):
             if g.numel() == 0:
                 continue
             assert torch.allclose(sd[k].grad, g, rtol=1e-5, atol=1e-7), k
+
+
+def test_lrs_and_scale_transformers_bit_identical(golden):
+    """Linear rational spline / Scale restatements against the reference's outputs (tests/golden/make_golden_lrs.py)."""
+    torch.set_num_threads(1)
+    for c in golden('lrs.pt')['transformers']:
+        ne = len(c['event_shape'])
+        if c['kind'] == 'lrs':
+            o, l = fo.lrs_forward(c['x'], c['h'], c['n_bins'], c['boundary'], ne)
+            o2, l2 = fo.lrs_inverse(c['z_in'], c['h'], c['n_bins'], c['boundary'], ne)
+        else:
+            o, l = fo.scale_forward(c['x'], c['h'], ne)
+            o2, l2 = fo.scale_inverse(c['z_in'], c['h'], ne)
+        _eq(o, c['forward']['out'], 'forward out')
+        _eq(l, c['forward']['ld'], 'forward log_det')
+        _eq(o2, c['inverse']['out'], 'inverse out')
+        _eq(l2, c['inverse']['ld'], 'inverse log_det')
+
+
+def test_lrs_presets_bit_identical(golden):
+    torch.set_num_threads(1)
+    for c in golden('lrs.pt')['presets']:
+        o = fo.OracleFlow(c['preset'], c['event_shape'], c['state_dict'])
+        _eq(o.log_prob(c['x']), c['log_prob'], c['preset'] + ' log_prob')
+        xs, lps = o.sample_from_noise(c['noise'], return_log_prob=True)
+        _eq(xs, c['xs'], c['preset'] + ' xs')
+        _eq(lps, c['lp_s'], c['preset'] + ' lp_s')

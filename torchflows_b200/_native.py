@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get('B2F_LIB') or os.path.join(_HERE, 'lib', 'libb2f.so') 
 
 # enum b2f_transformer
 T_SHIFT_ADD, T_SHIFT_SUB, T_AFFINE_FWD, T_AFFINE_INV, T_RQ_FWD, T_RQ_INV = range(6)
+# stand-alone transformer kernels only (b2f_transformer_apply / _backward), never part of a flow program
+T_LRS_FWD, T_LRS_INV, T_SCALE_FWD, T_SCALE_INV = range(6, 10)
 # enum b2f_op_kind
 OP_ELEMENTWISE, OP_FLIP, OP_COUPLING, OP_MADE, OP_MADE_SEQ = range(5)
 MAX_OPS = 40
@@ -27,7 +29,8 @@ FLOW_WS_FILLED = 8
 KERNEL_NONE, KERNEL_GENERIC, KERNEL_TC, KERNEL_ROWS, KERNEL_TCQ, KERNEL_TCA, KERNEL_TCM = range(7)
 
 INVERSE_KIND = {T_SHIFT_ADD: T_SHIFT_SUB, T_SHIFT_SUB: T_SHIFT_ADD, T_AFFINE_FWD: T_AFFINE_INV,
-                T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD}
+                T_AFFINE_INV: T_AFFINE_FWD, T_RQ_FWD: T_RQ_INV, T_RQ_INV: T_RQ_FWD, T_LRS_FWD: T_LRS_INV,
+                T_LRS_INV: T_LRS_FWD, T_SCALE_FWD: T_SCALE_INV, T_SCALE_INV: T_SCALE_FWD}
 
 
 class B2FError(RuntimeError):

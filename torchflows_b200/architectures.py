@@ -3,4 +3,4 @@
 from torchflows_b200.bijections.finite.autoregressive.architectures import *  # noqa: F401,F403
 from torchflows_b200.bijections.finite.autoregressive.architectures import (  # noqa: F401
     AutoregressiveArchitecture, NICE, RealNVP, InverseRealNVP, MAF, IAF, CouplingRQNSF, MaskedAutoregressiveRQNSF,
-    InverseAutoregressiveRQNSF)
+    InverseAutoregressiveRQNSF, CouplingLRS, MaskedAutoregressiveLRS, InverseAutoregressiveLRS)

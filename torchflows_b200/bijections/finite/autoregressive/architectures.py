@@ -1,4 +1,4 @@
-"""Architecture presets (API of torchflows/.../autoregressive/architectures.py:31-163, 196-208).
+"""Architecture presets (API of torchflows/.../autoregressive/architectures.py:31-223).
 
 Every preset is ``ElementwiseAffine -> [ReversePermutation -> <base> -> ActNorm] x n_layers -> ElementwiseAffine ->
 ActNorm``.  With the default arguments the whole stack lowers to one libb2f flow program, i.e. ``log_prob`` and
@@ -12,6 +12,8 @@ from torchflows_b200.bijections.finite.autoregressive.layers import (ActNorm, Af
                                                                     AffineForwardMaskedAutoregressive,
                                                                     AffineInverseMaskedAutoregressive,
                                                                     ElementwiseAffine, InverseAffineCoupling,
+                                                                    LRSCoupling, LRSForwardMaskedAutoregressive,
+                                                                    LRSInverseMaskedAutoregressive,
                                                                     RQSCoupling, RQSForwardMaskedAutoregressive,
                                                                     RQSInverseMaskedAutoregressive, ShiftCoupling)
 from torchflows_b200.bijections.finite.autoregressive.layers_base import (CouplingBijection,
@@ -91,3 +93,21 @@ class MaskedAutoregressiveRQNSF(AutoregressiveArchitecture):
 class InverseAutoregressiveRQNSF(AutoregressiveArchitecture):
     def __init__(self, event_shape, **kwargs):
         super().__init__(event_shape, base_bijection=RQSInverseMaskedAutoregressive, **kwargs)
+
+
+class CouplingLRS(AutoregressiveArchitecture):
+    """Dolatabadi et al. 2020: linear rational spline coupling (architectures.py:166-178).  The spline runs as the stand-alone
+    transformer kernel (csrc/b2f_lrs.cuh) behind the conditioner's GEMMs, not inside the whole-flow kernels."""
+
+    def __init__(self, event_shape, **kwargs):
+        super().__init__(event_shape, base_bijection=LRSCoupling, **kwargs)
+
+
+class MaskedAutoregressiveLRS(AutoregressiveArchitecture):
+    def __init__(self, event_shape, **kwargs):
+        super().__init__(event_shape, base_bijection=LRSForwardMaskedAutoregressive, **kwargs)
+
+
+class InverseAutoregressiveLRS(AutoregressiveArchitecture):
+    def __init__(self, event_shape, **kwargs):
+        super().__init__(event_shape, base_bijection=LRSInverseMaskedAutoregressive, **kwargs)

@@ -7,7 +7,8 @@ from torchflows_b200 import _native as N
 from torchflows_b200.bijections.finite.autoregressive.layers_base import (CouplingBijection, ElementwiseBijection,
                                                                            InverseMaskedAutoregressiveBijection,
                                                                            MaskedAutoregressiveBijection)
-from torchflows_b200.bijections.finite.autoregressive.transformers.linear.affine import Affine, InverseAffine, Shift
+from torchflows_b200.bijections.finite.autoregressive.transformers.linear.affine import Affine, InverseAffine, Scale, Shift
+from torchflows_b200.bijections.finite.autoregressive.transformers.spline.linear_rational import LinearRational
 from torchflows_b200.bijections.finite.autoregressive.transformers.spline.rational_quadratic import RationalQuadratic
 
 
@@ -19,6 +20,11 @@ class ElementwiseAffine(ElementwiseBijection):
 class ElementwiseInverseAffine(ElementwiseBijection):
     def __init__(self, event_shape, **kwargs):
         super().__init__(event_shape, InverseAffine, **kwargs)
+
+
+class ElementwiseScale(ElementwiseBijection):
+    def __init__(self, event_shape, **kwargs):
+        super().__init__(event_shape, Scale, **kwargs)
 
 
 class ElementwiseShift(ElementwiseBijection):
@@ -91,6 +97,11 @@ class ShiftCoupling(CouplingBijection):
         super().__init__(event_shape, Shift, **kwargs)
 
 
+class LRSCoupling(CouplingBijection):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, LinearRational, **kwargs)
+
+
 class RQSCoupling(CouplingBijection):
     def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
         super().__init__(event_shape, RationalQuadratic, **kwargs)
@@ -106,6 +117,11 @@ class RQSForwardMaskedAutoregressive(MaskedAutoregressiveBijection):
         super().__init__(event_shape, RationalQuadratic, **kwargs)
 
 
+class LRSForwardMaskedAutoregressive(MaskedAutoregressiveBijection):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, LinearRational, **kwargs)
+
+
 class AffineInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
     def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
         super().__init__(event_shape, InverseAffine, **kwargs)
@@ -114,3 +130,8 @@ class AffineInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
 class RQSInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
     def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
         super().__init__(event_shape, RationalQuadratic, **kwargs)
+
+
+class LRSInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, LinearRational, **kwargs)

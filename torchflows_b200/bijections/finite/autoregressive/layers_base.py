@@ -93,7 +93,8 @@ def _fits_fused_kernel(n_dim: int, n_hidden: int, kind: int = N.OP_ELEMENTWISE, 
 def _transformer_fusable(tr) -> bool:
     if isinstance(tr, RationalQuadratic):
         return tr.n_bins == 8
-    return isinstance(tr, ScalarTransformer) and tr._tkind_forward >= 0
+    # Affine / InverseAffine / Shift; LinearRational and Scale have stand-alone kernels only (kinds above T_RQ_INV)
+    return isinstance(tr, ScalarTransformer) and 0 <= tr._tkind_forward <= N.T_RQ_INV
 
 
 class AutoregressiveBijection(Bijection):
@@ -275,9 +276,11 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
         super().__init__(transformer.event_shape, transformer, conditioner_transform,
                          l2_regularization=l2_regularization, **kwargs)
         ct = conditioner_transform
-        if not (ct.n_layers == 2 and ct.is_plain and _transformer_fusable(transformer)):
+        if not (ct.n_layers == 2 and ct.is_plain and isinstance(transformer, ScalarTransformer)):
             raise NotImplementedError('masked autoregressive layers are implemented for the default MADE depth '
-                                      '(n_layers=2), predicted parameters only, and n_bins=8 splines')
+                                      '(n_layers=2) and predicted parameters only')
+        # transformers without a whole-flow kernel (LinearRational, splines with n_bins != 8) run as a composite: masked
+        # conditioner GEMMs + the stand-alone transformer kernel, the sequential direction as the reference's D-step loop
         # With a context, MADE concatenates it to x and gives the context columns degrees n_dim+1.. (transforms.py:
         # 222-226).  Hidden units that see a context column therefore have a degree > n_dim, and the strict output mask
         # (transforms.py:254) cuts every such unit off from every output: the context provably never reaches h.  The
@@ -291,8 +294,8 @@ class MaskedAutoregressiveBijection(AutoregressiveBijection):
         fin = ct.sequential[0].mask[:, :self.n_dim].sum(dim=1).to(torch.int32)
         self.register_buffer('_fin_steps', fin, persistent=False)
         # event sizes whose backward tile no longer fits shared memory (D >= 768) run as a composite, see _composite_*
-        self._fusable = _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_MADE, transformer._tkind_forward,
-                                           self._spline_args()[0])
+        self._fusable = _transformer_fusable(transformer) and _fits_fused_kernel(
+            self.n_dim, ct.n_hidden, N.OP_MADE, transformer._tkind_forward, self._spline_args()[0])
 
     def _lower(self, one_pass: bool, transformer_direction: str):
         seq = self.conditioner_transform.sequential

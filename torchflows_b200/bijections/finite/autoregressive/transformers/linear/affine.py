@@ -60,3 +60,31 @@ class Shift(ScalarTransformer):
     @property
     def default_parameters(self) -> torch.Tensor:
         return torch.zeros(self.parameter_shape)
+
+
+class Scale(ScalarTransformer):
+    """z = alpha * x with alpha = exp(log(1 - m) + u / 2) + m > 0 (affine.py:160-200): the Affine kernel without a shift."""
+    _tkind_forward = N.T_SCALE_FWD
+    _tkind_inverse = N.T_SCALE_INV
+
+    def __init__(self, event_shape: torch.Size, min_scale: float = 1e-10):
+        super().__init__(event_shape=event_shape)
+        if min_scale != 1e-10:
+            raise NotImplementedError('the kernels implement the default min_scale = 1e-10')
+        self.m = min_scale
+        self.const = 2.0
+        self.u_alpha_1 = math.log(1 - self.m)
+
+    @property
+    def parameter_shape_per_element(self):
+        return (1,)
+
+    @property
+    def default_parameters(self) -> torch.Tensor:
+        return torch.zeros(self.parameter_shape)
+
+    def unconstrain_alpha(self, a):
+        return self.const * (torch.log(a - self.m) - self.u_alpha_1)
+
+    def constrain_alpha(self, u):
+        return torch.exp(self.u_alpha_1 + u / self.const) + self.m

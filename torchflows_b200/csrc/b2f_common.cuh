@@ -42,6 +42,8 @@ inline int params_per_element(int tkind, int n_bins) {
         case B2F_T_SHIFT_ADD: case B2F_T_SHIFT_SUB: return 1;
         case B2F_T_AFFINE_FWD: case B2F_T_AFFINE_INV: return 2;
         case B2F_T_RQ_FWD: case B2F_T_RQ_INV: return 3 * n_bins - 1;
+        case B2F_T_LRS_FWD: case B2F_T_LRS_INV: return 4 * n_bins;
+        case B2F_T_SCALE_FWD: case B2F_T_SCALE_INV: return 1;
         default: return -1;
     }
 }

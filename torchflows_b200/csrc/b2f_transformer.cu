@@ -13,6 +13,7 @@
 
 #include "b2f_common.cuh"
 #include "b2f_math.cuh"
+#include "b2f_lrs.cuh"
 
 namespace b2f {
 
@@ -36,7 +37,8 @@ __global__ void __launch_bounds__(256) transformer_kernel(const float* __restric
     const long long row = wg * rpw + lane / GS;
     const int sub = lane % GS;
     const bool valid = row < n_rows;
-    const int P = (TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV) ? 3 * nb - 1 : ((TK == B2F_T_AFFINE_FWD || TK == B2F_T_AFFINE_INV) ? 2 : 1);
+    const int P = (TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV) ? 3 * nb - 1 : (TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV) ? 4 * nb
+                  : ((TK == B2F_T_AFFINE_FWD || TK == B2F_T_AFFINE_INV) ? 2 : 1);
     float ld = 0.0f;
     if (valid) {
         const float* hr = h + row * h_row_stride;
@@ -49,6 +51,10 @@ __global__ void __launch_bounds__(256) transformer_kernel(const float* __restric
             else if constexpr (TK == B2F_T_SHIFT_SUB) { o = v - __ldg(he); l = 0.0f; }
             else if constexpr (TK == B2F_T_AFFINE_FWD) affine_fwd<MODE>(v, __ldg(he), __ldg(he + 1), o, l);
             else if constexpr (TK == B2F_T_AFFINE_INV) affine_inv<MODE>(v, __ldg(he), __ldg(he + 1), o, l);
+            else if constexpr (TK == B2F_T_SCALE_FWD) scale_fwd<MODE>(v, __ldg(he), o, l);
+            else if constexpr (TK == B2F_T_SCALE_INV) scale_inv<MODE>(v, __ldg(he), o, l);
+            else if constexpr (TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV)
+                lrs_apply<NB, TK == B2F_T_LRS_INV>(v, HGlobal{he}, nb, boundary, o, l);
             else {
                 int k;
                 rq_apply<NB, TK == B2F_T_RQ_INV, MODE>(v, HGlobal{he}, nb, boundary, o, l, k);
@@ -71,7 +77,8 @@ __global__ void __launch_bounds__(256) transformer_backward_kernel(
     if (idx >= n_rows * E) return;
     const long long row = idx / E;
     const int e = (int)(idx - row * E);
-    const int P = (TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV) ? 3 * nb - 1 : ((TK == B2F_T_AFFINE_FWD || TK == B2F_T_AFFINE_INV) ? 2 : 1);
+    const int P = (TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV) ? 3 * nb - 1 : (TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV) ? 4 * nb
+                  : ((TK == B2F_T_AFFINE_FWD || TK == B2F_T_AFFINE_INV) ? 2 : 1);
     const float* he = h + row * h_row_stride + (long long)e * P;
     float* ge = gh + idx * P;
     const float v = __ldg(x + idx);
@@ -82,6 +89,10 @@ __global__ void __launch_bounds__(256) transformer_backward_kernel(
     else if constexpr (TK == B2F_T_SHIFT_SUB) { dv = GZ; ge[0] = -GZ; }
     else if constexpr (TK == B2F_T_AFFINE_FWD) affine_fwd_backward<MODE>(v, __ldg(he), GZ, GL, dv, ge[0], ge[1]);
     else if constexpr (TK == B2F_T_AFFINE_INV) affine_inv_backward<MODE>(v, __ldg(he), __ldg(he + 1), GZ, GL, dv, ge[0], ge[1]);
+    else if constexpr (TK == B2F_T_SCALE_FWD) { float unused; affine_fwd_backward<MODE>(v, __ldg(he), GZ, GL, dv, ge[0], unused); }
+    else if constexpr (TK == B2F_T_SCALE_INV) { float unused; affine_inv_backward<MODE>(v, __ldg(he), 0.0f, GZ, GL, dv, ge[0], unused); }
+    else if constexpr (TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV)
+        lrs_backward<NB, TK == B2F_T_LRS_INV>(v, HGlobal{he}, nb, boundary, GZ, GL, dv, GGlobal{ge});
     else if constexpr (TK == B2F_T_RQ_FWD) rq_backward_fwd<NB, MODE>(v, HGlobal{he}, nb, boundary, GZ, GL, dv, GGlobal{ge});
     else rq_backward_inv<NB, MODE>(v, HGlobal{he}, nb, boundary, GZ, GL, dv, GGlobal{ge});
     gx[idx] = dv;
@@ -160,7 +171,7 @@ static int launch_fwd(const float* x, const float* h, float* out, float* log_det
     const int block = 256;
     const long long blocks = (warps * 32 + block - 1) / block;
     if (blocks > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_apply: too many rows");
-    constexpr bool rq = TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV;
+    constexpr bool rq = TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV || TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV;
     if (rq && nb == 8)
         transformer_kernel<TK, 8, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, out, log_det, k_out, n_rows, E, hs, nb, boundary, GS);
     else
@@ -176,13 +187,14 @@ static int launch_bwd(const float* x, const float* h, const float* gout, const f
     const long long blocks = (n + block - 1) / block;
     if (blocks > 0x7fffffffLL) return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_backward: too many elements");
     constexpr bool rq = TK == B2F_T_RQ_FWD || TK == B2F_T_RQ_INV;
+    constexpr bool lrs = TK == B2F_T_LRS_FWD || TK == B2F_T_LRS_INV;
     if constexpr (rq) {
         if (nb == 8 && hs == (int64_t)E * 23 && !((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(gh)) & 15)) {
             transformer_backward_staged_kernel<TK, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, gout, gld, gx, gh, n, E, boundary);
             return check_launch("b2f_transformer_backward");
         }
     }
-    if (rq && nb == 8)
+    if ((rq || lrs) && nb == 8)
         transformer_backward_kernel<TK, 8, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, gout, gld, gx, gh, n_rows, E, hs, nb, boundary);
     else
         transformer_backward_kernel<TK, 0, MODE><<<(unsigned)blocks, block, 0, st>>>(x, h, gout, gld, gx, gh, n_rows, E, hs, nb, boundary);
@@ -199,7 +211,7 @@ extern "C" int b2f_transformer_apply(int32_t tkind, const float* x, const float*
     if (n_rows == 0 && n_event > 0) return B2F_OK;
     if (!x || !h || !out || n_rows < 0 || n_event <= 0 || h_row_stride < 0)
         return fail(B2F_ERR_INVALID, "b2f_transformer_apply: bad arguments");
-    const bool rq = tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV;
+    const bool rq = tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV || tkind == B2F_T_LRS_FWD || tkind == B2F_T_LRS_INV;
     if (rq && (n_bins < 1 || n_bins > kRqMaxBins || !(boundary > 0.0f)))
         return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_apply: n_bins=%d (1..%d) boundary=%g", n_bins, kRqMaxBins, boundary);
     if (n_rows == 0) return B2F_OK;
@@ -216,6 +228,10 @@ extern "C" int b2f_transformer_apply(int32_t tkind, const float* x, const float*
         B2F_DISPATCH(B2F_T_AFFINE_INV)
         B2F_DISPATCH(B2F_T_RQ_FWD)
         B2F_DISPATCH(B2F_T_RQ_INV)
+        B2F_DISPATCH(B2F_T_LRS_FWD)
+        B2F_DISPATCH(B2F_T_LRS_INV)
+        B2F_DISPATCH(B2F_T_SCALE_FWD)
+        B2F_DISPATCH(B2F_T_SCALE_INV)
     }
 #undef B2F_DISPATCH
     return fail(B2F_ERR_INVALID, "b2f_transformer_apply: unknown transformer kind %d", tkind);
@@ -228,7 +244,7 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
     if (n_rows == 0 && n_event > 0) return B2F_OK;
     if (!x || !h || !gx || !gh || n_rows < 0 || n_event <= 0 || h_row_stride < 0)
         return fail(B2F_ERR_INVALID, "b2f_transformer_backward: bad arguments");
-    if ((tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV) && (n_bins < 1 || n_bins > kRqMaxBins || !(boundary > 0.0f)))
+    if ((tkind == B2F_T_RQ_FWD || tkind == B2F_T_RQ_INV || tkind == B2F_T_LRS_FWD || tkind == B2F_T_LRS_INV) && (n_bins < 1 || n_bins > kRqMaxBins || !(boundary > 0.0f)))
         return fail(B2F_ERR_UNSUPPORTED, "b2f_transformer_backward: n_bins=%d", n_bins);
     if (n_rows == 0) return B2F_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -242,6 +258,10 @@ extern "C" int b2f_transformer_backward(int32_t tkind, const float* x, const flo
         B2F_DISPATCH(B2F_T_AFFINE_INV)
         B2F_DISPATCH(B2F_T_RQ_FWD)
         B2F_DISPATCH(B2F_T_RQ_INV)
+        B2F_DISPATCH(B2F_T_LRS_FWD)
+        B2F_DISPATCH(B2F_T_LRS_INV)
+        B2F_DISPATCH(B2F_T_SCALE_FWD)
+        B2F_DISPATCH(B2F_T_SCALE_INV)
     }
 #undef B2F_DISPATCH
     return fail(B2F_ERR_INVALID, "b2f_transformer_backward: unknown transformer kind %d", tkind);
