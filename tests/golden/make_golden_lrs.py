@@ -5,7 +5,8 @@ Run in the build container only (the reference lives at /root/reference and does
     python tests/golden/make_golden_lrs.py
 
 Stores tests/golden/lrs.pt: transformer-level cases (inputs, parameters, outputs of forward and inverse, autograd gradients of
-a fixed scalar objective) and preset-level cases (CouplingLRS, MaskedAutoregressiveLRS, InverseAutoregressiveLRS: state_dict,
+a fixed scalar objective), single layers outside the presets (residual conditioner, graphical coupling mask, Linear*
+couplings, ElementwiseScale) and preset-level cases (CouplingLRS, MaskedAutoregressiveLRS, InverseAutoregressiveLRS: state_dict,
 inputs, log_prob, samples from given noise).  Pins oracle/flow_oracle.py (tests/test_oracle_golden.py) and is the
 reference-produced half of tests/test_gpu_lrs.py.
 """
@@ -98,9 +99,43 @@ def preset_cases():
     return cases
 
 
+def layer_cases():
+    """Single layers outside the presets: residual conditioner, graphical coupling mask, Linear* couplings, ElementwiseScale."""
+    from torchflows.bijections.finite.autoregressive import layers as L
+    from torchflows.bijections.finite.autoregressive.conditioning.transforms import ResidualFeedForward
+    specs = [
+        ('RQSCoupling', (10,), dict(conditioner_transform_class=ResidualFeedForward)),
+        ('LRSCoupling', (9,), dict(conditioner_transform_class=ResidualFeedForward, conditioner_kwargs=dict(n_layers=4))),
+        ('AffineCoupling', (8,), dict(coupling_kwargs=dict(edge_list=[(0, 4), (1, 5), (2, 6), (0, 7)]))),
+        ('RQSCoupling', (8,), dict(coupling_kwargs=dict(edge_list=[(0, 1), (2, 3), (5, 3), (5, 7)]))),
+        ('LinearAffineCoupling', (6,), {}),
+        ('LinearLRSCoupling', (6,), {}),
+        ('ElementwiseScale', (6,), {}),
+    ]
+    cases = []
+    for n, (name, event_shape, kwargs) in enumerate(specs):
+        torch.manual_seed(700 + n)
+        layer = getattr(L, name)(event_shape, **kwargs)
+        layer.eval()
+        with torch.no_grad():
+            for p in layer.parameters():
+                p.add_(0.2 * torch.randn_like(p))
+        x = torch.randn(40, *event_shape)
+        noise = torch.randn(40, *event_shape)
+        with torch.no_grad():
+            z, ld_f = layer.forward(x)
+            xs, ld_i = layer.inverse(noise)
+        kw = {k: v for k, v in kwargs.items() if k != 'conditioner_transform_class'}
+        cases.append(dict(layer=name, event_shape=event_shape, kwargs=kw,
+                          conditioner='ResidualFeedForward' if 'conditioner_transform_class' in kwargs else None,
+                          state_dict={k: v.clone() for k, v in layer.state_dict().items()}, x=x, noise=noise, z=z, ld_f=ld_f,
+                          xs=xs, ld_i=ld_i))
+    return cases
+
+
 def main():
     torch.manual_seed(0)
-    torch.save(dict(transformers=transformer_cases(), presets=preset_cases()), os.path.join(OUT, 'lrs.pt'))
+    torch.save(dict(transformers=transformer_cases(), presets=preset_cases(), layers=layer_cases()), os.path.join(OUT, 'lrs.pt'))
     print('wrote', os.path.join(OUT, 'lrs.pt'))
 
 

@@ -104,3 +104,28 @@ def test_presets_match_reference(golden, idx):
     for name, p in flow.named_parameters():
         if name in c['grads']:
             assert rel_l2(p.grad, c['grads'][name]) < 2e-3, name
+
+
+@pytest.mark.parametrize('idx', range(7))
+def test_layers_outside_the_presets_match_reference(golden, idx):
+    """ResidualFeedForward conditioners (transforms.py:315-362), GraphicalCoupling masks (coupling_masks.py:63-75), the Linear*
+    couplings and ElementwiseScale: same state_dict layout as the reference, same outputs both ways."""
+    from torchflows_b200.bijections.finite.autoregressive import layers as L
+    from torchflows_b200.bijections.finite.autoregressive.conditioning.transforms import ResidualFeedForward
+    dev = torch.device('cuda:0')
+    c = golden('lrs.pt')['layers'][idx]
+    kwargs = dict(c['kwargs'])
+    if c['conditioner'] == 'ResidualFeedForward':
+        kwargs['conditioner_transform_class'] = ResidualFeedForward
+    layer = getattr(L, c['layer'])(c['event_shape'], **kwargs)
+    layer.load_state_dict(c['state_dict'])
+    layer = layer.to(dev).eval()
+    with torch.no_grad():
+        z, ld = layer.forward(c['x'].to(dev))
+        xs, ldi = layer.inverse(c['noise'].to(dev))
+        xr, ldr = layer.inverse(z)
+    close(z, c['z'], 'z', 2e-5, 2e-5)
+    close(ld, c['ld_f'], 'log_det', 1e-4, 1e-4)
+    close(xs, c['xs'], 'inverse', 2e-5, 2e-5)
+    close(ldi, c['ld_i'], 'inverse log_det', 1e-4, 1e-4)
+    close(xr, c['x'], 'round trip', 1e-4, 1e-4)

@@ -201,3 +201,44 @@ class FeedForward(TensorConditionerTransform):
 class Linear(FeedForward):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs, n_layers=1)
+
+
+class ResidualFeedForward(TensorConditionerTransform):
+    """Linear -> act -> (n_layers - 2) residual blocks ``x + MLP(x)`` of ``block_size`` Linear layers -> Linear
+    (API and state_dict layout of transforms.py:315-362).  Couplings that use it run as a composite: this network on the
+    library's GEMMs, the transformer as its stand-alone kernel (the whole-flow kernels implement the two-layer FeedForward)."""
+
+    class ResidualBlock(nn.Module):
+        def __init__(self, event_size: int, hidden_size: int, block_size: int, nonlinearity: Type[nn.Module]):
+            super().__init__()
+            if block_size < 2:
+                raise ValueError(f'block_size must be at least 2 but found {block_size}. '
+                                 f'For block_size = 1, use the FeedForward class instead.')
+            widths = [event_size] + [hidden_size] * (block_size - 1) + [event_size]
+            modules = []
+            for i in range(block_size):
+                modules.append(nn.Linear(widths[i], widths[i + 1]))
+                if i + 1 < block_size:
+                    modules.append(nonlinearity())
+            self.sequential = nn.Sequential(*modules)
+
+        def forward(self, x):
+            return x + self.sequential(x)
+
+    def __init__(self, input_event_shape, parameter_shape, context_shape=None, n_hidden: int = None, n_layers: int = 3,
+                 block_size: int = 2, nonlinearity: Type[nn.Module] = nn.ReLU, **kwargs):
+        super().__init__(input_event_shape=input_event_shape, context_shape=context_shape,
+                         parameter_shape=parameter_shape, **kwargs)
+        n_in, n_out = self.n_input_event_dims, self.n_predicted_parameters
+        if n_hidden is None:
+            n_hidden = max(int(5 * math.log10(max(n_in, n_out))), 4)
+        if n_layers <= 2:
+            raise ValueError(f'Number of layers in ResidualFeedForward must be at least 3, but found {n_layers}')
+        self.n_hidden, self.n_layers, self.nonlinearity = n_hidden, n_layers, nonlinearity
+        modules = [nn.Linear(n_in, n_hidden), nonlinearity()]
+        modules += [self.ResidualBlock(n_hidden, n_hidden, block_size, nonlinearity) for _ in range(n_layers - 2)]
+        modules += [nn.Linear(n_hidden, n_out), nn.Unflatten(dim=-1, unflattened_size=(n_out,))]
+        self.sequential = nn.Sequential(*modules)
+
+    def predict_theta_flat(self, x: torch.Tensor, context: torch.Tensor = None):
+        return self.sequential(self.context_combiner(x, context))

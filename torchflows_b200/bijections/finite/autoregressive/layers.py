@@ -135,3 +135,25 @@ class RQSInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
 class LRSInverseMaskedAutoregressive(InverseMaskedAutoregressiveBijection):
     def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
         super().__init__(event_shape, LinearRational, **kwargs)
+
+
+# Couplings whose name promises a one-layer conditioner.  As in the reference (layers.py:298-335) the ``n_layers=1`` keyword is
+# passed to the layer, not to the conditioner, where it is swallowed: the conditioner stays the default two-layer FeedForward.
+class LinearAffineCoupling(AffineCoupling):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, **kwargs, n_layers=1)
+
+
+class LinearRQSCoupling(RQSCoupling):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, **kwargs, n_layers=1)
+
+
+class LinearLRSCoupling(LRSCoupling):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, **kwargs, n_layers=1)
+
+
+class LinearShiftCoupling(ShiftCoupling):
+    def __init__(self, event_shape: Union[Tuple[int, ...], torch.Size], **kwargs):
+        super().__init__(event_shape, **kwargs, n_layers=1)
