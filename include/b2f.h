@@ -121,6 +121,13 @@ enum b2f_op_kind {
                                        p[5] (first MADE op) = program blob: int32 {magic, final pass, 0, layers}, then as for
                                          B2F_FLAG_TCQ_OPERANDS */
 
+#define B2F_FLAG_ROW_BIAS 64        /* op flag (COUPLING): the conditioner is context-conditioned (conditioning/context.py:46-60,
+                                       Concatenation: the hidden layer sees [x_A, context]).  p[0] holds the x_A columns of W1
+                                       only, and p[1] is a PER-ROW hidden bias (B, H) = b1 + context . W1[:, n_src:]^T computed by
+                                       the caller; b2f_flow_backward writes dL/d(pre-activation) per row into g[1] (B, H), from
+                                       which the caller derives the gradients of b1, the context columns of W1 and the context.
+                                       Such programs run on the generic and backward kernels (b2f_flow.cu, b2f_flow_bwd.cu). */
+
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
     int32_t tkind;    /* enum b2f_transformer */

@@ -64,6 +64,23 @@ def kernel_params(op: LoweredOp) -> List[Optional[torch.Tensor]]:
     if op.kind == N.OP_ELEMENTWISE:
         return [op.leafs[0].detach().reshape(-1, 2).contiguous()]
     W1, b1, W2, b2 = op.leafs
+    if op.flags & N.FLAG_ROW_BIAS:
+        # context-conditioned coupling: W1 is the x_A block of the first layer and b1 the per-row hidden bias, both made for
+        # this call (never cached: a recycled allocation would alias a stale entry); only the output layer's layout is cached
+        P = params_per_element(op.tkind, op.n_bins)
+        n_elem = W2.shape[0] // P
+        cache = getattr(op.owner, '_b2f_cache', None)
+        if cache is None:
+            cache = {}
+            if op.owner is not None:
+                object.__setattr__(op.owner, '_b2f_cache', cache)
+        key, ver = ('rowbias', op.kind, op.tkind), ((W2.data_ptr(), W2._version), (b2.data_ptr(), b2._version))
+        hit = cache.get(key)
+        if hit is None or hit[0] != ver:
+            with torch.no_grad():
+                hit = (ver, [to_tile_layout(W2.detach(), n_elem, P), b2.detach().contiguous()])
+            cache[key] = hit
+        return [W1.detach().contiguous(), b1.detach().contiguous(), hit[1][0], hit[1][1]]
     key = (op.kind, op.tkind)
     ver = tuple((t.data_ptr(), t._version) for t in op.leafs)
     cache = getattr(op.owner, '_b2f_cache', None)
@@ -112,6 +129,8 @@ _TC_GEOM = {  # transformer kind -> (parameter columns per element CPE, elements
 def tc_eligible(op: LoweredOp, D: int) -> bool:
     """Mirror of try_launch_flow_tc's per-op conditions (csrc/b2f_flow_tc.cu)."""
     if op.kind not in (N.OP_COUPLING, N.OP_MADE) or op.tkind not in _TC_GEOM or D % 16 != 0 or D < 32:
+        return False
+    if op.flags & N.FLAG_ROW_BIAS:           # context-conditioned layer (per-row hidden bias): generic kernel
         return False
     x3 = _TC_GEOM[op.tkind][2]
     if x3:
@@ -257,7 +276,8 @@ class FlowFunction(torch.autograd.Function):
                     g = [torch.zeros_like(t) for t in kp[:4]] + [None] * (len(kp) - 4)
             grads.append(g)
         B, D = x2.shape
-        arr = N.make_ops(op_dicts(ops, grads))
+        od = op_dicts(ops, grads)          # holds the per-call operand tensors (row-bias ops) alive until the launch below
+        arr = N.make_ops(od)
         flags = cfg.flags
         if ctx.ws is not None:
             ws, flags = ctx.ws, flags | N.FLOW_WS_FILLED       # x2 is the forward output here
@@ -287,6 +307,7 @@ class FlowFunction(torch.autograd.Function):
                 if op.kind in (N.OP_MADE, N.OP_MADE_SEQ):
                     gW1, gW2 = gW1 * op.consts[0], gW2 * op.consts[1]
                 leaf_grads.extend([gW1, gb1, gW2, gb2])
+        del od
         return (gx if need_gx else None, None, *leaf_grads)
 
 

@@ -34,6 +34,8 @@ def eligible(ops: Sequence, D: int) -> bool:
             if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
                 return False
         elif op.kind == N.OP_COUPLING:
+            if op.flags & N.FLAG_ROW_BIAS:              # context-conditioned layer: generic kernel
+                return False
             if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV, N.T_SHIFT_ADD, N.T_SHIFT_SUB) or not (1 <= op.n_hidden <= 31):
                 return False
             written.add(0 if flip else 1)

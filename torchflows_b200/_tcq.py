@@ -53,6 +53,8 @@ def eligible(ops: Sequence, D: int) -> bool:
             if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
                 return False
         elif op.kind == N.OP_COUPLING:
+            if op.flags & N.FLAG_ROW_BIAS:              # context-conditioned layer: generic kernel
+                return False
             if op.tkind not in (N.T_RQ_FWD, N.T_RQ_INV) or op.n_bins != 8 or not (1 <= op.n_hidden <= 30):
                 return False
             written.add(0 if flip else 1)

@@ -111,14 +111,18 @@ class BijectiveComposition(Bijection):
             layer.requires_grad_(True)
 
     # -- fused execution --------------------------------------------------------------------------------
-    def _segments(self, direction: str):
+    def _segments(self, direction: str, context: torch.Tensor = None):
         """Split the layer sequence (in application order) into maximal runs of lowerable layers.
         A layer that needs a data-dependent initialisation first (ActNorm in training mode) starts a new run
-        so that it can look at its own input."""
+        so that it can look at its own input.  ``context``: layers that can fold a context tensor into their lowered form
+        (context-conditioned couplings: a per-row hidden bias) get it; the others ignore it or stay composite."""
         order = list(self.layers) if direction == 'forward' else list(self.layers)[::-1]
         segments, current = [], []
         for layer in order:
-            ops = layer.lower(direction)
+            if context is not None and getattr(layer, 'lowers_with_context', False):
+                ops = layer.lower(direction, context=context)
+            else:
+                ops = layer.lower(direction)
             needs_data = direction == 'forward' and getattr(layer, 'needs_data_init', lambda: False)()
             # per-column layers the whole-flow kernels do not take (very wide events) still fuse with their neighbours
             # into one pass over the batch (csrc/b2f_colrun.cu)
@@ -168,7 +172,7 @@ class BijectiveComposition(Bijection):
             nonlocal log_det
             log_det = ld if log_det is None else log_det + ld
 
-        for kind, item in self._segments(direction):
+        for kind, item in self._segments(direction, context):
             if kind == 'ops':
                 x2, ld, _ = prog.run_program(item, x2)
                 add(ld)

@@ -14,6 +14,7 @@ import torch.nn as nn
 from torchflows_b200 import _native as N
 from torchflows_b200 import _program as prog
 from torchflows_b200.bijections.base import Bijection
+from torchflows_b200.bijections.finite.autoregressive.conditioning.context import Concatenation
 from torchflows_b200.bijections.finite.autoregressive.conditioning.coupling_masks import (HalfSplit, PartialCoupling,
                                                                                            make_coupling)
 from torchflows_b200.bijections.finite.autoregressive.conditioning.transforms import (MADE, ConditionerTransform,
@@ -147,6 +148,14 @@ class CouplingBijection(AutoregressiveBijection):
                          and _transformer_fusable(transformer)
                          and _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_COUPLING, transformer._tkind_forward,
                                                 self._spline_args()[0]))
+        # Context-conditioned (conditioning/context.py:46-60: the hidden layer sees [x_A, context]): W1 [x_A, c]^T + b1 =
+        # W1[:, :n_A] x_A + (b1 + W1[:, n_A:] c), i.e. the same coupling op with a PER-ROW hidden bias (B2F_FLAG_ROW_BIAS);
+        # the bias (B, H) is one small product per call, h = conditioner output still never exists in memory.
+        self._fusable_ctx = (context_shape is not None and isinstance(coupling, HalfSplit) and type(ct) is FeedForward
+                             and ct.n_layers == 2 and ct.nonlinearity is nn.Tanh and ct.is_plain
+                             and type(ct.context_combiner) is Concatenation and _transformer_fusable(transformer)
+                             and _fits_fused_kernel(self.n_dim, ct.n_hidden, N.OP_COUPLING, transformer._tkind_forward,
+                                                    self._spline_args()[0]))
         # too wide for the whole-flow kernels (e.g. n_dim = 1024, n_hidden = 1024): the layer runs on the tcgen05 GEMM
         # pipeline of csrc/b2f_wide.cu (spline as the output-layer GEMM's epilogue, h never in memory)
         wide_ok = (context_shape is None and isinstance(coupling, HalfSplit)
@@ -187,7 +196,12 @@ class CouplingBijection(AutoregressiveBijection):
         return h.view(*batch_shape, *self.transformer.parameter_shape)
 
     # -- fused path ------------------------------------------------------------------------------------------
-    def lower(self, direction: str) -> Optional[List[prog.LoweredOp]]:
+    #: BijectiveComposition hands the context to lower() (see _segments)
+    lowers_with_context: bool = True
+
+    def lower(self, direction: str, context: torch.Tensor = None) -> Optional[List[prog.LoweredOp]]:
+        if context is not None:
+            return self._lower_with_context(direction, context)
         if not self._fusable or self._trains_wide():
             return None
         seq = self.conditioner_transform.sequential
@@ -195,6 +209,21 @@ class CouplingBijection(AutoregressiveBijection):
         return [prog.LoweredOp(kind=N.OP_COUPLING, tkind=self._tkind(direction),
                                leafs=[seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias],
                                n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, owner=self)]
+
+    def _lower_with_context(self, direction: str, context: torch.Tensor) -> Optional[List[prog.LoweredOp]]:
+        ct = self.conditioner_transform
+        if not self._fusable_ctx or not context.is_cuda or context.dtype != torch.float32:
+            return None
+        seq = ct.sequential
+        n_a = ct.context_combiner.n_input_dims
+        c2 = flatten_event(context, ct.context_shape).reshape(-1, ct.context_combiner.n_context_dims)
+        w1 = seq[0].weight
+        row_bias = torch.addmm(seq[0].bias, c2, w1[:, n_a:].t())          # (B, H): b1 + W1[:, n_A:] c
+        n_bins, boundary = self._spline_args()
+        return [prog.LoweredOp(kind=N.OP_COUPLING, tkind=self._tkind(direction),
+                               leafs=[w1[:, :n_a], row_bias, seq[2].weight, seq[2].bias],
+                               n_hidden=seq[0].out_features, n_bins=n_bins, boundary=boundary, flags=N.FLAG_ROW_BIAS,
+                               owner=self)]
 
     #: composite path only: run the conditioner's library GEMMs on the tensor cores in TF32 for spline layers (the same
     #: precision the fused tcgen05 kernel uses; affine / shift layers always stay in fp32)
@@ -248,13 +277,22 @@ class CouplingBijection(AutoregressiveBijection):
             out[..., tgt] = yb
         return unflatten_event(out, self.event_shape), log_det
 
-    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _run_direction(self, x: torch.Tensor, context, direction: str):
+        if context is not None:
+            ops = self._lower_with_context(direction, context) if x.is_cuda else None
+            if ops is None:
+                return self._composite(x, context, direction)
+            batch_shape = get_batch_shape(x, self.event_shape)
+            y2, ld, _ = prog.run_program(ops, x.reshape(-1, self.n_dim))
+            return y2.reshape(x.shape), ld.reshape(batch_shape)
         fused = self._fusable and not self._trains_wide()
-        return self._run_fused(x, 'forward') if fused else self._composite(x, context, 'forward')
+        return self._run_fused(x, direction) if fused else self._composite(x, context, direction)
+
+    def forward(self, x: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self._run_direction(x, context, 'forward')
 
     def inverse(self, z: torch.Tensor, context: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        fused = self._fusable and not self._trains_wide()
-        return self._run_fused(z, 'inverse') if fused else self._composite(z, context, 'inverse')
+        return self._run_direction(z, context, 'inverse')
 
 
 class MaskedAutoregressiveBijection(AutoregressiveBijection):

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) flow_kernel(const __grid_constant__ FlowA
         const int n_src = coupling ? D / 2 : D;            // HalfSplit: first D//2 flat dims are the source
         const int t0 = coupling ? D / 2 : 0, n_tgt = D - t0;
         if (!seq) {
-            hidden_layer<true>(t, op, n_src);
+            hidden_layer<true>(t, op, n_src, (op.flags & B2F_FLAG_ROW_BIAS) ? op.p1 + row0 * op.H : nullptr, rows);
             __syncthreads();
         }
         run_transform<MODE>(t, op, t0, n_tgt, seq);

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         }
         const bool coupling = op.f.kind == B2F_OP_COUPLING;
         const int n_src = coupling ? D / 2 : D, t0 = coupling ? D / 2 : 0;
-        hidden_layer<true>(t, op.f, n_src);
+        hidden_layer<true>(t, op.f, n_src, (op.f.flags & B2F_FLAG_ROW_BIAS) ? op.f.p1 + row0 * op.f.H : nullptr, rows);
         __syncthreads();
         run_transform_forward<MODE>(t, op.f, t0, D - t0);
         __syncthreads();
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
         long long c_a = 0, c_b = 0, c_c = 0;
         if (dbg) c_a = clock64();
 #endif
-        hidden_layer<true>(t, op.f, n_src);
+        hidden_layer<true>(t, op.f, n_src, (op.f.flags & B2F_FLAG_ROW_BIAS) ? op.f.p1 + row0 * op.f.H : nullptr, rows);
         __syncthreads();
 #ifdef B2F_BWD_CLOCK_HOOK
         if (dbg) c_b = clock64();
@@ -690,10 +690,18 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
                 for (int m = 0; m < TM; ++m) s = fmaf(b.dhid[m * HS + j], t.xt[m * XS + c], s);
                 atomicAdd(op.g0 + idx, s);
             }
-            for (int j = tid; j < H; j += NT) {
-                float s = 0.0f;
-                for (int m = 0; m < TM; ++m) s += b.dhid[m * HS + j];
-                atomicAdd(op.g1 + j, s);
+            if (op.f.flags & B2F_FLAG_ROW_BIAS) {
+                // context-conditioned layer: dL/d(pre-activation) per row; the caller owns the chain to b1 / context
+                for (int idx = tid; idx < rows * H; idx += NT) {
+                    const int m = idx / H, j = idx - m * H;
+                    op.g1[(row0 + m) * H + j] = b.dhid[m * HS + j];
+                }
+            } else {
+                for (int j = tid; j < H; j += NT) {
+                    float s = 0.0f;
+                    for (int m = 0; m < TM; ++m) s += b.dhid[m * HS + j];
+                    atomicAdd(op.g1 + j, s);
+                }
             }
         }
         // dL/dx_src[m][k] += sum_j dpre[m][j] * W1[j][k]

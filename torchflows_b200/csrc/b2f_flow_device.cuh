@@ -85,14 +85,17 @@ struct Tile {
 };
 
 // hidden layer: hid[m][j] = act(b1[j] + sum_k W1[j][k] * x[m][src k])     (transforms.py:295-296 / :259-262)
+// row_bias: per-row hidden bias of this tile's rows ([TM][H], B2F_FLAG_ROW_BIAS: context-conditioned layer), else nullptr;
+// rows: valid rows of the tile (rows beyond it get a zero bias, their results are never stored).
 template <bool TANH>
-__device__ __forceinline__ void hidden_layer(const Tile& t, const DevOp& op, int n_src) {
+__device__ __forceinline__ void hidden_layer(const Tile& t, const DevOp& op, int n_src, const float* row_bias = nullptr,
+                                             int rows = 0) {
     const int H = op.H;
     for (int idx = threadIdx.x; idx < (H << t.logTM); idx += blockDim.x) {
         const int m = idx & (t.TM - 1), j = idx >> t.logTM;   // j is warp-uniform: W1 reads are broadcasts
         const float* w = op.p0 + (size_t)j * n_src;
         const float* xr = t.xt + m * t.XS;
-        float a0 = __ldg(op.p1 + j), a1 = 0.0f;
+        float a0 = row_bias ? (m < rows ? __ldg(row_bias + (size_t)m * H + j) : 0.0f) : __ldg(op.p1 + j), a1 = 0.0f;
         int k = 0;
         if (!t.flip) {
             for (; k + 1 < n_src; k += 2) {

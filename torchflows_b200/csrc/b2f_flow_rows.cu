@@ -52,6 +52,7 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
                 break;
             case B2F_OP_COUPLING: case B2F_OP_MADE: case B2F_OP_MADE_SEQ: {
                 if (!o.p[0] || !o.p[1] || !o.p[2] || !o.p[3] || o.n_hidden <= 0 || o.n_hidden > 32) return 0;
+                if (o.flags & B2F_FLAG_ROW_BIAS) return 0;      // context-conditioned layers: generic kernel
                 if (o.kind == B2F_OP_MADE_SEQ && !o.p[4]) return 0;
                 if (o.tkind == B2F_T_RQ_FWD || o.tkind == B2F_T_RQ_INV) {
                     // splines: only the D-step sequential direction (the one-pass direction has a real GEMM as its output

@@ -513,6 +513,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
         if (o.kind != B2F_OP_COUPLING && o.kind != B2F_OP_MADE) return 0;
+        if (o.flags & B2F_FLAG_ROW_BIAS) return 0;          // context-conditioned layers: generic kernel
         t.made = o.kind == B2F_OP_MADE;
         t.ws_off = ws_next;                 // same order and stride as b2f_flow_backward_workspace
         ws_next += B * (long long)D;

@@ -509,6 +509,7 @@ int try_launch_flow_tca(const b2f_op_t* ops, int32_t n_ops, const float* x, floa
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (o.kind == B2F_OP_ELEMENTWISE) continue;                 // folded into the blobs by the caller
         if (o.kind != B2F_OP_COUPLING || !(o.flags & B2F_FLAG_TCA_OPERANDS)) return 0;
+        if (o.flags & B2F_FLAG_ROW_BIAS) return 0;
         const bool affine = o.tkind == B2F_T_AFFINE_FWD || o.tkind == B2F_T_AFFINE_INV;
         const bool shift = o.tkind == B2F_T_SHIFT_ADD || o.tkind == B2F_T_SHIFT_SUB;
         if ((!affine && !shift) || o.n_hidden < 1 || o.n_hidden > 31 || !o.p[4] || A.n_layers >= kAMaxLayers) return 0;

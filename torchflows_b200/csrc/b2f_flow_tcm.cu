@@ -515,6 +515,7 @@ int try_launch_flow_tcm(const b2f_op_t* ops, int32_t n_ops, const float* x, floa
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
         if (o.kind == B2F_OP_ELEMENTWISE) continue;                 // folded into the blobs by the caller
         if (o.kind != B2F_OP_MADE || !(o.flags & B2F_FLAG_TCM_OPERANDS)) return 0;
+        if (o.flags & B2F_FLAG_ROW_BIAS) return 0;
         if ((o.tkind != B2F_T_RQ_FWD && o.tkind != B2F_T_RQ_INV) || o.n_bins != 8) return 0;
         if (o.n_hidden < 1 || o.n_hidden > 30 || !o.p[4] || A.n_layers >= kMaxLayers) return 0;
         if (reinterpret_cast<uintptr_t>(o.p[4]) & 15) return fail(B2F_ERR_INVALID, "op %d: tcm operand blob must be 16-byte aligned", i);
