@@ -336,8 +336,10 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
     };
     __syncwarp();
     stage(0, buf[0]);
+    const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(xin)) & 15) == 0;
+    float4 vin = make_float4(0.f, 0.f, 0.f, 0.f), vout = vin;
     // one element per iteration, NOT unrolled: the body holds two inlined spline evaluations (the second one for the
-    // reference's log-det quirk) and must stay inside the instruction cache; x is read and written as scalars
+    // reference's log-det quirk) and must stay inside the instruction cache
 #pragma unroll 1
     for (int i = 0; i < D; ++i) {
         const int c = rev ? D - 1 - i : i, cur = i & 1;       // physical column of logical step i (rev: flipped tile)
@@ -345,7 +347,16 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
         __syncwarp();                                 // element i's weights have landed; the other buffer is free
         if (i + 1 < D) stage(i + 1, buf[cur ^ 1]);
         const float* w2e = buf[cur];
-        float v = live ? xin[c] : 0.0f;
+        float v;
+        if (vec) {
+            // four columns per memory access: a thread walks its own row, so a scalar access costs the warp 32 wavefronts per
+            // ELEMENT (LSU wavefronts were 72 % busy, profiles/r2_rows_seq_ncu_summary.txt); the group is consumed by rotation
+            if ((i & 3) == 0) vin = live ? *reinterpret_cast<const float4*>(xin + (rev ? c - 3 : c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rev) { v = vin.w; vin = make_float4(0.0f, vin.x, vin.y, vin.z); }
+            else { v = vin.x; vin = make_float4(vin.y, vin.z, vin.w, 0.0f); }
+        } else {
+            v = live ? xin[c] : 0.0f;
+        }
         if (er) v = fmaf(er[c], v, er[D + c]);
 #pragma unroll
         for (int j = 0; j < HP; ++j)
@@ -374,7 +385,13 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
         } else {
             transform_element<TK, MODE, PP>(v, acc, op.boundary, out, l);
         }
-        if (live) x0[c] = out;
+        if (vec) {
+            if (rev) vout = make_float4(out, vout.x, vout.y, vout.z);
+            else vout = make_float4(vout.y, vout.z, vout.w, out);
+            if ((i & 3) == 3 && live) *reinterpret_cast<float4*>(x0 + (rev ? c : c - 3)) = vout;
+        } else if (live) {
+            x0[c] = out;
+        }
         ld += l;
 #pragma unroll
         for (int j4 = 0; j4 < HP / 4; ++j4) {
