@@ -128,6 +128,11 @@ enum b2f_op_kind {
                                        which the caller derives the gradients of b1, the context columns of W1 and the context.
                                        Such programs run on the generic and backward kernels (b2f_flow.cu, b2f_flow_bwd.cu). */
 
+#define B2F_FLAG_SEQ_FOLDED 128     /* op flag (MADE_SEQ, RQ, n_bins 8; inference): p[2] = folded output layer [element][hidden][24]
+                                       (the 24 columns of csrc/b2f_rqfast.cuh, masks multiplied in, elements in LOGICAL order),
+                                       p[3] = folded bias [element][24]; the sequential direction then evaluates the spline in the
+                                       folded formulation of the tensor-core kernels (tolerance-checked like them) */
+
 typedef struct b2f_op {
     int32_t kind;     /* enum b2f_op_kind */
     int32_t tkind;    /* enum b2f_transformer */

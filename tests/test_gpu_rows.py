@@ -221,3 +221,36 @@ def test_rows_kernel_in_place_spline_sampling_is_bit_identical():
             finally:
                 os.environ.pop('B2F_ROWS_NO_INPLACE', None)
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), B
+
+
+def test_sequential_spline_folded_operands_agree_with_the_plain_ones():
+    """MA-RQNSF sampling on the rows kernel with the folded output layer (B2F_FLAG_SEQ_FOLDED, csrc/b2f_rqfast.cuh
+    sequential_step) against the same kernel fed the plain 23-parameter operands (B2F_NO_SEQ_FOLD=1), incl. the reference's
+    last-iteration log-det and its exact variant."""
+    from torchflows_b200 import Flow, _native as N
+    import torchflows_b200.architectures as arch
+    dev = torch.device('cuda:0')
+    torch.manual_seed(5)
+    flow = Flow(arch.MaskedAutoregressiveRQNSF(64)).to(dev).eval()
+    with torch.no_grad():
+        for name, p in flow.named_parameters():
+            if name.endswith('.value'):
+                p.add_(0.3 * torch.randn_like(p))
+    z = 1.5 * torch.randn(3000, 64, device=dev)
+    for quirk in (True, False):
+        for layer in flow.bijection.layers:
+            if hasattr(layer, 'sequential_log_det_reference_quirk'):
+                layer.sequential_log_det_reference_quirk = quirk
+        with torch.no_grad():
+            xs, lps = flow._sample_from_base(z, no_grad=True, return_log_prob=True)
+            assert N.last_flow_kernel() == N.KERNEL_ROWS
+            os.environ['B2F_NO_SEQ_FOLD'] = '1'
+            try:
+                xs0, lps0 = flow._sample_from_base(z, no_grad=True, return_log_prob=True)
+                assert N.last_flow_kernel() == N.KERNEL_ROWS
+            finally:
+                os.environ.pop('B2F_NO_SEQ_FOLD', None)
+        assert not torch.equal(xs, xs0)          # two different formulations really ran
+        err = ((xs.double() - xs0.double()).abs() / (1 + xs0.double().abs())).max().item()
+        err_lp = ((lps.double() - lps0.double()).abs() / (1 + lps0.double().abs())).max().item()
+        assert err < 2e-3 and err_lp < 1e-4, (quirk, err, err_lp)

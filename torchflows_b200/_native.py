@@ -23,6 +23,7 @@ FLAG_TCQ_OPERANDS = 8
 FLAG_TCA_OPERANDS = 16
 FLAG_TCM_OPERANDS = 32
 FLAG_ROW_BIAS = 64
+FLAG_SEQ_FOLDED = 128
 FLOW_LOGP_OF_INPUT = 1
 FLOW_MODE_PRECISE = 2
 FLOW_MODE_FAST_KNOTS = 4

@@ -191,8 +191,42 @@ def tc_operands(op: LoweredOp, flipped: bool, D: int):
     return out
 
 
+def seq_fold_eligible(ops: Sequence[LoweredOp], D: int, flags: int) -> bool:
+    """Can the sequential spline layers of this program run in the folded formulation (rows kernel, B2F_FLAG_SEQ_FOLDED)?
+    Cheap mirror of the rows kernel's main conditions; the library rejects the rest and the caller retries unfolded."""
+    if (flags & N.FLOW_MODE_PRECISE) or os.environ.get('B2F_DISABLE_ROWS') or os.environ.get('B2F_NO_SEQ_FOLD') \
+            or D % 8 != 0 or D > 1024:
+        return False
+    seq = [op for op in ops if op.kind == N.OP_MADE_SEQ and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV)]
+    return bool(seq) and all(op.n_bins == 8 and op.n_hidden <= 15 and not getattr(op.owner, '_b2f_no_seq_fold', False)
+                             for op in seq)
+
+
+def seq_folded_operands(op: LoweredOp):
+    """[element][hidden][24] folded output layer and [element][24] folded bias of a sequential spline MADE layer (include/b2f.h,
+    B2F_FLAG_SEQ_FOLDED; columns of csrc/b2f_rqfast.cuh), masks multiplied in, cached per parameter version."""
+    W1, b1, W2, b2 = op.leafs
+    ver = tuple((t.data_ptr(), t._version) for t in (W2, b2))
+    cache = getattr(op.owner, '_b2f_cache', None)
+    if cache is None:
+        cache = {}
+        if op.owner is not None:
+            object.__setattr__(op.owner, '_b2f_cache', cache)
+    key = ('seqfold', op.kind, op.tkind)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        n_elem = W2.shape[0] // 23
+        Wf, bf = _tcq.fold_output_layer(W2.detach().float() * op.consts[1].to(W2.device), b2.detach().float(), n_elem)
+        out = (Wf.permute(0, 2, 1).contiguous(), bf.contiguous())
+    cache[key] = (ver, out)
+    return out
+
+
 def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.Tensor]]]] = None,
-             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None, tca_plan=None, tcm_plan=None):
+             D: Optional[int] = None, tcq_plan: Optional['_tcq.Plan'] = None, tca_plan=None, tcm_plan=None,
+             fold_seq: bool = False):
     """b2f_op descriptors of a program.  ``tcq_plan``: the program is laid out for the second-generation spline kernel
     (csrc/b2f_flow_tcq.cu): every coupling op carries its blob in p[4], the first one the program blob in p[5]."""
     out = []
@@ -214,6 +248,10 @@ def op_dicts(ops: Sequence[LoweredOp], grads: Optional[List[List[Optional[torch.
             p = p[:4] + [tca_plan.layer_blobs[n_coupling], tca_plan.program_blob if n_coupling == 0 else None]
             flags |= N.FLAG_TCA_OPERANDS
             n_coupling += 1
+        elif fold_seq and grads is None and op.kind == N.OP_MADE_SEQ and op.tkind in (N.T_RQ_FWD, N.T_RQ_INV):
+            wf, bf = seq_folded_operands(op)
+            p = p[:2] + [wf, bf] + p[4:]
+            flags |= N.FLAG_SEQ_FOLDED
         elif D is not None and grads is None and tc_eligible(op, D):
             w1c, w2c = tc_operands(op, flipped, D)
             p = p[:4] + [w1c, w2c]
@@ -374,10 +412,23 @@ def run_program(ops: Sequence[LoweredOp], x2: torch.Tensor, want_log_prob=False,
     if (not (flags & N.FLOW_MODE_PRECISE) and not os.environ.get('B2F_DISABLE_TCQ') and not os.environ.get('B2F_DISABLE_TC')
             and _tcq.eligible(ops, D)):
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
-    y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=_tca_plan(ops, D, base_loc, base_log_scale, flags),
-                                      tcm_plan=_tcm_plan(ops, D, base_loc, base_log_scale, flags)),
-                             x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
+    fold = seq_fold_eligible(ops, D, flags)
+    try:
+        y, ld, lp = N.flow_apply(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=_tca_plan(ops, D, base_loc, base_log_scale, flags),
+                                          tcm_plan=_tcm_plan(ops, D, base_loc, base_log_scale, flags), fold_seq=fold),
+                                 x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
+    except N.B2FError as e:
+        if not fold or 'B2F_FLAG_SEQ_FOLDED' not in str(e):
+            raise
+        _no_seq_fold(ops)              # the rows kernel does not take this program: plain operands from now on
+        y, ld, lp = N.flow_apply(op_dicts(ops, D=D), x2.detach(), want_y, True, want_log_prob, base_loc, base_log_scale, flags)
     return y, ld, lp
+
+
+def _no_seq_fold(ops):
+    for op in ops:
+        if op.kind == N.OP_MADE_SEQ and op.owner is not None:
+            object.__setattr__(op.owner, '_b2f_no_seq_fold', True)
 
 
 def _tcm_plan(ops, D, base_loc, base_log_scale, flags):
@@ -418,8 +469,16 @@ def run_sample_program(ops: Sequence[LoweredOp], B: int, D: int, device, want_lo
         plan = _tcq.cached_plan(ops, D, base_loc, base_log_scale)
     tca = _tca_plan(ops, D, base_loc, base_log_scale, flags) if plan is None else None
     tcm = _tcm_plan(ops, D, base_loc, base_log_scale, flags) if plan is None and tca is None else None
-    return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=tca, tcm_plan=tcm), B, D, device, want_log_prob, base_loc,
-                         base_log_scale, flags, seed, offset, in_kernel=plan is not None or tca is not None or tcm is not None)
+    fold = seq_fold_eligible(ops, D, flags)
+    try:
+        return N.flow_sample(op_dicts(ops, D=D, tcq_plan=plan, tca_plan=tca, tcm_plan=tcm, fold_seq=fold), B, D, device,
+                             want_log_prob, base_loc, base_log_scale, flags, seed, offset,
+                             in_kernel=plan is not None or tca is not None or tcm is not None)
+    except N.B2FError as e:
+        if not fold or 'B2F_FLAG_SEQ_FOLDED' not in str(e):
+            raise
+        _no_seq_fold(ops)
+        return N.flow_sample(op_dicts(ops, D=D), B, D, device, want_log_prob, base_loc, base_log_scale, flags, seed, offset)
 
 
 # ---- runs of per-column layers outside whole-flow programs (csrc/b2f_colrun.cu) ---------------------------------------------

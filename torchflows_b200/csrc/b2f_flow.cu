@@ -250,6 +250,10 @@ static int flow_apply_impl(const b2f_op_t* ops, int32_t n_ops, const float* x, f
             if (rc != 0) return rc == 1 ? B2F_OK : rc;
         }
     }
+    for (int i = 0; i < n_ops; ++i)
+        if (ops[i].flags & B2F_FLAG_SEQ_FOLDED)
+            return fail(B2F_ERR_UNSUPPORTED, "b2f_flow_apply: op %d carries folded sequential-spline operands (B2F_FLAG_SEQ_FOLDED), "
+                        "which only the row-per-thread kernel takes, and that kernel declined this program", i);
     FlowArgs A;
     memset(&A, 0, sizeof(A));
     int Hmax = 1, has_seq = 0, has_rq = 0;

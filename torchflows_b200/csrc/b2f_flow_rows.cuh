@@ -35,6 +35,7 @@
 // HBM traffic is the algorithmic minimum (x read once, z / log-density written once, weights from L1/L2).
 #pragma once
 #include "b2f_flow_device.cuh"
+#include "b2f_rqfast.cuh"
 
 namespace b2f {
 
@@ -320,6 +321,9 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
         fin[j] = (j < H) ? __ldg(op.p4 + j) : -1;
     }
     const bool quirk = !(op.flags & B2F_FLAG_SEQ_LOGDET_EXACT);
+    // B2F_FLAG_SEQ_FOLDED: p[2] / p[3] hold the FOLDED output layer (24 columns per element, csrc/b2f_rqfast.cuh) and the
+    // spline runs in the folded formulation of the tensor-core kernels: ~1/3 of the instructions of the stand-alone one
+    const bool folded = MODE != 0 && (op.flags & B2F_FLAG_SEQ_FOLDED);
     const float4* w1c = reinterpret_cast<const float4*>(W.w1);
     float* buf[2] = {wst, wst + wst_stride};
     auto stage = [&](int i, float* dst) {            // logical element i
@@ -328,9 +332,9 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
             const unsigned d = (unsigned)__cvta_generic_to_shared(dst + 4 * q);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + q) : "memory");
         }
-        if (lane < P) {
+        if (lane < (folded ? PP : P)) {
             const unsigned d = (unsigned)__cvta_generic_to_shared(dst + H * PP + lane);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(op.p3 + (size_t)i * P + lane) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(op.p3 + (size_t)i * (folded ? PP : P) + lane) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -363,7 +367,7 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
             if (fin[j] == i) act[j] = rows_tanh<MODE>(pre[j]);
         float acc[PP];
 #pragma unroll
-        for (int p = 0; p < PP; ++p) acc[p] = (p < P) ? w2e[H * PP + p] : 0.0f;
+        for (int p = 0; p < PP; ++p) acc[p] = (p < P || folded) ? w2e[H * PP + p] : 0.0f;
 #pragma unroll
         for (int j = 0; j < HP; ++j)
             if (j < H) {
@@ -377,7 +381,12 @@ __device__ __forceinline__ void rows_sequential_rq(float* x0, const float* xin, 
                 }
             }
         float out, l;
-        if (quirk && i < D - 1) {
+        if (MODE != 0 && folded) {
+            constexpr bool INV = TK == B2F_T_RQ_INV;
+            if (quirk && i < D - 1) rqf::sequential_step<INV, true, true, (MODE >= 2)>(v, acc, op.boundary, out, l);
+            else rqf::sequential_step<INV, true, false, (MODE >= 2)>(v, acc, op.boundary, out, l);
+            l *= rqf::kLn2;
+        } else if (quirk && i < D - 1) {
             // the reference returns the log-det of its LAST full pass, in which dimension i < D-1 is fed the already
             // inverted value (layers_base.py:218-223): reproduce that term
             auto h = [&](int q) { return acc[q]; };

@@ -195,6 +195,113 @@ B2F_HD void inverse(float v, const float (&g)[24], float b, float& out, float& l
 }
 
 
+B2F_HD float f_rcpn(float x) {            // reciprocal + one Newton step (~1 ulp)
+    const float y = f_rcp(x);
+    return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
+
+// ---- sequential direction of a masked autoregressive spline layer (b2f_flow_rows.cuh, rows_sequential_rq) --------------------
+// One element per step with the SAME parameters used twice: the map itself, and -- for every dimension but the last -- the
+// log-determinant the reference reports, which is the one of its last full pass, where the dimension is fed its already
+// transformed value (layers_base.py:218-223).  The softmax bin sizes are computed once (sizes), the bin
+// search and the evaluation run per evaluation point (search / eval).  Same arithmetic as select / forward / inverse above
+// (knot exponentials: see FASTEXP).
+// FASTEXP: SFU exponentials (2 ulp: knots then differ from the one-pass direction's by ~1e-5 at boundary 50, which shows in the
+// forward-then-inverse round trip); otherwise the ~1 ulp polynomial of b2f_math.cuh (the default: round trips stay at the
+// reference's own level)
+template <bool SAFE, bool FASTEXP>
+B2F_HD void sizes(const float (&g)[24], float two_b, f2 (&sz)[8]) {
+    f2 e[8];
+    float m = 0.0f, my = 0.0f;
+    if (SAFE) {
+        m = g[0]; my = g[0] + g[8];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) { m = fmaxf(m, g[j]); my = fmaxf(my, g[j] + g[8 + j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float ax = SAFE ? g[j] - m : g[j], ay = SAFE ? (g[j] + g[8 + j]) - my : g[j] + g[8 + j];
+        if (FASTEXP) { e[j].x = f_ex2(ax); e[j].y = f_ex2(ay); }
+        else e[j] = exp_det2(mk2(ax * kLn2, ay * kLn2));
+    }
+    const f2 sum = pk_add(pk_add(pk_add(e[0], e[1]), pk_add(e[2], e[3])), pk_add(pk_add(e[4], e[5]), pk_add(e[6], e[7])));
+    const float r = (kSizeScale * two_b) * f_rcpn(sum.x * sum.y);     // Newton-refined: errors feed the next dimensions
+    const f2 rr = mk2(r * sum.y, r * sum.x);
+    const float minb = kRqMinBin * two_b;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sz[j] = pk_fma(e[j], rr, mk2(minb, minb));
+}
+
+template <bool INV>
+B2F_HD void search(const f2 (&sz)[8], const float (&g)[24], float t, float two_b, Sel& s) {
+    f2 lo = mk2(0.0f, 0.0f), up = sz[0];
+    s.dl0 = kEdgeLogit; s.dl1 = kEdgeLogit + g[16];
+    float c = 0.0f, m7 = 0.0f;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        c += INV ? sz[j - 1].y : sz[j - 1].x;
+        m7 = select_step(c, t, lo, up, s.dl0, s.dl1, sz[j - 1], sz[j], g[16 + j - 1], g[16 + j]);
+    }
+    if (m7 != 0.0f) up = mk2(two_b, two_b);
+    s.xl = lo.x; s.yl = lo.y; s.xu = up.x; s.yu = up.y;
+}
+
+// value and log2 |d out / d v| of the map at t = v + b inside the selected bin (no bounds handling)
+template <bool INV>
+B2F_HD void eval(float t, const Sel& s, float b, float& o, float& ld2) {
+    const float w = s.xu - s.xl, hgt = s.yu - s.yl;
+    const float d0 = delta(s.dl0), d1 = delta(s.dl1);
+    const float h2 = hgt + hgt, hw = hgt * w;
+    const float T = fmaf(w, d0 + d1, -h2);
+    if (!INV) {
+        const float a = fminf(fmaxf(t - s.xl, 0.0f), w);
+        const float wa = w - a, aw = a * wa;
+        const float den = fmaf(T, aw, hw * w);
+        const float num = fmaf(hgt * a, a, (w * d0) * aw);
+        const float hR = hgt * f_rcpn(den);
+        o = fmaf(hR, num, s.yl - b);
+        const float M3 = fmaf(w, fmaf(d0 * wa, wa, (d1 * a) * a), h2 * aw);
+        ld2 = f_lg2((hR * hR) * (M3 * w));
+    } else {
+        const float t0 = fminf(fmaxf(t - s.yl, 0.0f), hgt);
+        const float B2 = fmaf(-t0, T, hw * d0);
+        const float A2 = fmaf(hgt, hgt, -B2);
+        const float disc = fmaf(B2, B2, (4.0f * (A2 * hgt)) * t0);
+        const float sq = sqrtf(fmaxf(disc, 0.0f));
+        const float xi = fminf(fmaxf((h2 * t0) * f_rcpn(B2 + sq), 0.0f), 1.0f);
+        const float a = xi * w;
+        o = (s.xl - b) + a;
+        const float wa = w - a, aw = a * wa;
+        const float den = fmaf(T, aw, hw * w);
+        const float M3 = fmaf(w, fmaf(d0 * wa, wa, (d1 * a) * a), h2 * aw);
+        ld2 = f_lg2(den * den) - f_lg2((hgt * hgt) * (M3 * w));
+    }
+}
+
+// out = map(v); ld2 = log2-determinant of the map evaluated AT out (QUIRK, see above) or at v (the exact one)
+template <bool INV, bool SAFE, bool QUIRK, bool FASTEXP>
+B2F_HD void sequential_step(float v, const float (&g)[24], float b, float& out, float& ld2) {
+    const float two_b = b + b;
+    const bool inb = fabsf(v) < b;
+    f2 sz[8];
+    sizes<SAFE, FASTEXP>(g, two_b, sz);
+    Sel s;
+    search<INV>(sz, g, v + b, two_b, s);
+    float o, l;
+    eval<INV>(v + b, s, b, o, l);
+    out = inb ? o : v;
+    if (QUIRK) {
+        const bool inb2 = inb && fabsf(out) < b;
+        search<INV>(sz, g, out + b, two_b, s);
+        float o2, l2;
+        eval<INV>(out + b, s, b, o2, l2);
+        ld2 = inb2 ? l2 : 0.0f;
+    } else {
+        ld2 = inb ? l : 0.0f;
+    }
+}
+
+
 // ---- backward of the forward-direction spline on the RAW 23 parameters (p[0..8) widths logits, p[8..16) heights
 // offsets, p[16..23) interior derivative logits; p[23] unused) for the wide-conditioner kernel (b2f_wide.cu), whose
 // backward is the epilogue of a GEMM and must be short.  Same partial derivatives as rq_backward_fwd (b2f_math.cuh,
@@ -202,10 +309,6 @@ B2F_HD void inverse(float v, const float (&g)[24], float b, float& out, float& l
 // backward -- rq_backward_fwd evaluates 32 polynomial exponentials), reciprocals instead of divisions, the sigmoid of the
 // two selected derivative logits only.  ~450 issue slots instead of ~1700.  Tolerance-checked against rq_backward_fwd
 // (tests/test_c_oracle_and_hostmath.py) like everything downstream of a TF32 GEMM.
-B2F_HD float f_rcpn(float x) {            // reciprocal + one Newton step (~1 ulp)
-    const float y = f_rcp(x);
-    return fmaf(y, fmaf(-x, y, 1.0f), y);
-}
 
 B2F_HD void backward_fwd(float v, const float (&p)[24], float b, float GZ_in, float GL_in, float& dv, float (&dp)[24]) {
     // Out of bounds (identity tail): dL/dv = GZ and zero parameter gradients.  The arithmetic below runs on v clamped into
