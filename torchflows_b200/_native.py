@@ -2,7 +2,7 @@
 tensors are not CUDA fp32 the call fails loudly."""
 import ctypes
 import os
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 

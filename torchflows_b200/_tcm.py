@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _native as N
-from ._tcq import CPE, EPC, HDR, _elementwise_affine, canonical, fold_output_layer, round_tf32
+from ._tcq import CPE, EPC, _elementwise_affine, canonical, fold_output_layer, round_tf32
 
 MAGIC = 0x4D435442                              # 'BTCM'
 

@@ -6,7 +6,7 @@ reference's module tree so that ``state_dict`` keys are identical (``sequential.
 the weights directly and never materialise the output ``h``.  Calling a conditioner on its own
 (``forward(x) -> h``) is the stand-alone API and is two library GEMMs (``F.linear``) on the module's device."""
 import math
-from typing import Optional, Tuple, Type, Union
+from typing import Optional, Type
 
 import torch
 import torch.nn as nn

@@ -12,7 +12,6 @@ import torch
 
 from torchflows_b200 import _native as N
 from torchflows_b200.bijections.finite.autoregressive.transformers.spline.base import MonotonicSpline
-from torchflows_b200.utils import get_batch_shape
 
 
 class RationalQuadratic(MonotonicSpline):

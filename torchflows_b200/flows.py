@@ -7,7 +7,7 @@ minibatch and gradients are all-reduced over NCCL (NVLink/NVSwitch) in one flat 
 import math
 import time
 import warnings
-from typing import Optional, Tuple, Union
+from typing import Tuple, Union
 
 import torch
 import torch.nn as nn
