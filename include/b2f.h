@@ -126,6 +126,9 @@ enum b2f_op_kind {
                                        only, and p[1] is a PER-ROW hidden bias (B, H) = b1 + context . W1[:, n_src:]^T computed by
                                        the caller; b2f_flow_backward writes dL/d(pre-activation) per row into g[1] (B, H), from
                                        which the caller derives the gradients of b1, the context columns of W1 and the context.
+                                       On an ELEMENTWISE op (context-conditioned ElementwiseAffine, layers_base.py:281-296): p[0]
+                                       holds PER-ROW parameters (B, D, 2) predicted by the caller's conditioner, and the backward
+                                       writes their gradient per row into g[0] (B, D, 2).
                                        Such programs run on the generic and backward kernels (b2f_flow.cu, b2f_flow_bwd.cu). */
 
 #define B2F_FLAG_SEQ_FOLDED 128     /* op flag (MADE_SEQ, RQ, n_bins 8; inference): p[2] = folded output layer [element][hidden][24]

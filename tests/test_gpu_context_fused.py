@@ -1,6 +1,6 @@
 """Context-conditioned coupling layers on the fused path: the context enters as a per-row hidden bias
-(B2F_FLAG_ROW_BIAS; conditioning/context.py:46-60, transforms.py:293-307), so the coupling layers of a context-conditioned preset run inside
-one flow program again (h is never materialised).  Checked against the composite path (conditioner on library GEMMs + stand-alone transformer kernel)
+(B2F_FLAG_ROW_BIAS; conditioning/context.py:46-60, transforms.py:293-307), and context-conditioned ElementwiseAffine layers carry their predicted
+parameters per row, so a whole context-conditioned coupling preset is one flow program again.  Checked against the composite path (conditioner on library GEMMs + stand-alone transformer kernel)
 and, in tests/test_gpu_parity.py::test_context_presets_vs_golden, against the reference's own outputs and gradients."""
 import pytest
 import torch
@@ -35,17 +35,20 @@ def test_context_couplings_run_fused_and_match_the_composite_path(preset, D, ctx
                 p.add_(0.3 * torch.randn_like(p))
     x = torch.randn(B, D, device=dev)
     c = torch.randn(B, *ctx_shape, device=dev)
-    # the two context-conditioned ElementwiseAffine layers of a preset (architectures.py:46,52) predict their own per-row
-    # parameters from the context and run the stand-alone transformer kernel on them; everything between them -- both coupling
-    # layers with their permutations and ActNorms -- is ONE program
+    # the whole context-conditioned preset is ONE program: the couplings carry the context as a per-row hidden bias, the two
+    # context-conditioned ElementwiseAffine layers (architectures.py:46,52) as per-row parameters
     segs = flow.bijection._segments('forward', c)
-    assert [k for k, _ in segs] == ['layer', 'ops', 'layer', 'ops'], [k for k, _ in segs]
-    assert sum(bool(op.flags & N.FLAG_ROW_BIAS) for op in segs[1][1]) == 2
+    assert [k for k, _ in segs] == ['ops'], [k for k, _ in segs]
+    assert sum(bool(op.flags & N.FLAG_ROW_BIAS) for op in segs[0][1] if op.kind == N.OP_COUPLING) == 2
+    assert sum(bool(op.flags & N.FLAG_ROW_BIAS) for op in segs[0][1] if op.kind == N.OP_ELEMENTWISE) == 2
 
     def run(fused):
         couplings = [l for l in flow.bijection.layers if hasattr(l, '_fusable_ctx')]
         for l in couplings:
             l._fusable_ctx = fused
+        for l in flow.bijection.layers:
+            if hasattr(l, 'fuse_context'):
+                l.fuse_context = fused
         xg, cg = x.clone().requires_grad_(True), c.clone().requires_grad_(True)
         flow.zero_grad()
         z, ld = flow.bijection.forward(xg, context=cg)
@@ -56,6 +59,9 @@ def test_context_couplings_run_fused_and_match_the_composite_path(preset, D, ctx
         grads = {k: p.grad.clone() for k, p in flow.named_parameters() if p.grad is not None}
         for l in couplings:
             l._fusable_ctx = True
+        for l in flow.bijection.layers:
+            if hasattr(l, 'fuse_context'):
+                l.fuse_context = True
         return z, ld, lp, xr, ldi, xg.grad, cg.grad, grads, kernel
 
     f = run(True)

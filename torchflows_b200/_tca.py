@@ -31,7 +31,7 @@ def eligible(ops: Sequence, D: int) -> bool:
         if op.kind == N.OP_FLIP:
             flip = not flip
         elif op.kind == N.OP_ELEMENTWISE:
-            if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
+            if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV) or (op.flags & N.FLAG_ROW_BIAS):
                 return False
         elif op.kind == N.OP_COUPLING:
             if op.flags & N.FLAG_ROW_BIAS:              # context-conditioned layer: generic kernel

@@ -28,7 +28,7 @@ def eligible(ops: Sequence, D: int) -> bool:
         if op.kind == N.OP_FLIP:
             flip = not flip
         elif op.kind == N.OP_ELEMENTWISE:
-            if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV):
+            if op.tkind not in (N.T_AFFINE_FWD, N.T_AFFINE_INV) or (op.flags & N.FLAG_ROW_BIAS):
                 return False
         elif op.kind == N.OP_MADE:
             if op.tkind not in (N.T_RQ_FWD, N.T_RQ_INV) or op.n_bins != 8 or not (1 <= op.n_hidden <= 30):

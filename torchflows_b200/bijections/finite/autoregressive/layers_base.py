@@ -440,12 +440,23 @@ class ElementwiseBijection(AutoregressiveBijection):
             raise RuntimeError('Context must be provided')
         return self.conditioner_transform(x=None, context=context)
 
-    def lower(self, direction: str):
+    #: BijectiveComposition hands the context to lower() (see _segments)
+    lowers_with_context: bool = True
+    #: context-conditioned layers join the flow program with per-row parameters (False: stand-alone transformer kernel)
+    fuse_context: bool = True
+
+    def lower(self, direction: str, context: torch.Tensor = None):
         tk = self._tkind(direction)
-        if (self.use_global_parameters and tk in (N.T_AFFINE_FWD, N.T_AFFINE_INV)
-                and _fits_fused_kernel(self.n_dim, 1)):
+        if tk not in (N.T_AFFINE_FWD, N.T_AFFINE_INV) or not _fits_fused_kernel(self.n_dim, 1):
+            return None
+        if self.use_global_parameters:
             return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[self.value], owner=self)]
-        return None
+        if context is None or not self.fuse_context or not context.is_cuda or context.dtype != torch.float32:
+            return None
+        # context-conditioned (layers_base.py:281-296): the layer's own conditioner predicts (B, D, 2) parameters from the
+        # context; the op carries them per row (B2F_FLAG_ROW_BIAS on an elementwise op) and the layer stays inside the program
+        h = self.conditioner_transform(x=None, context=context).reshape(-1, self.n_dim, 2)
+        return [prog.LoweredOp(kind=N.OP_ELEMENTWISE, tkind=tk, leafs=[h], flags=N.FLAG_ROW_BIAS, owner=self)]
 
     def column_op(self, direction: str):
         """(kind, value) of this layer as one op of a per-column run (csrc/b2f_colrun.cu), for event sizes the whole-flow

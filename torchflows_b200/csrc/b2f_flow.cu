@@ -123,8 +123,32 @@ __global__ void __launch_bounds__(512) flow_kernel(const __grid_constant__ FlowA
     for (int oi = 0; oi < A.n_ops; ++oi) {
         const DevOp& op = A.ops[oi];
         if (op.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
+        if (op.kind == B2F_OP_ELEMENTWISE && (op.flags & B2F_FLAG_ROW_BIAS)) {
+            // context-conditioned elementwise layer (layers_base.py:281-296): its parameters were predicted per row, (B, D, 2)
+            const float* pr = op.p0 + (size_t)row0 * D * 2;
+            const bool fwd = op.tkind == B2F_T_AFFINE_FWD;
+            for (int m = warp; m < TM; m += NW) {
+                float* xr = t.xt + m * XS;
+                float sld = 0.0f;
+                if (m < rows) {
+                    for (int j = lane; j < D; j += 32) {
+                        const float2 u = __ldg(reinterpret_cast<const float2*>(pr + ((size_t)m * D + j) * 2));
+                        float a, la;
+                        affine_scale<0>(u.x, a, la);
+                        const int c = t.col(j);
+                        xr[c] = fwd ? fmaf(a, xr[c], u.y) : (xr[c] - u.y) / a;
+                        sld += fwd ? la : -la;
+                    }
+                }
+                sld = warp_sum(sld);
+                if (lane == 0) ldacc[m] += sld;
+            }
+            __syncthreads();
+            continue;
+        }
         if (op.kind == B2F_OP_ELEMENTWISE) {
-            auto get = [&](int i) { return EwOp{A.ops[i].kind, A.ops[i].tkind, A.ops[i].p0}; };
+            // (a per-row layer ends a run of global ones: it reports kind -1 to the run composer)
+            auto get = [&](int i) { return EwOp{(A.ops[i].flags & B2F_FLAG_ROW_BIAS) ? -1 : A.ops[i].kind, A.ops[i].tkind, A.ops[i].p0}; };
             const int n_run = elementwise_stage_run(ea, get, oi, A.n_ops, D, tid, NT);
             __syncthreads();
             for (int m = warp; m < TM; m += NW) {

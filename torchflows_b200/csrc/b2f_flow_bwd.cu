@@ -542,6 +542,20 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
     for (int oi = 0; oi < A.n_ops; ++oi) {
         const BwdOp& op = A.ops[oi];
         if (op.f.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
+        if (op.f.kind == B2F_OP_ELEMENTWISE && (op.f.flags & B2F_FLAG_ROW_BIAS)) {
+            // context-conditioned elementwise layer: per-row parameters (B, D, 2)
+            const float* pr = op.f.p0 + (size_t)row0 * D * 2;
+            const bool fwd = op.f.tkind == B2F_T_AFFINE_FWD;
+            for (int idx = tid; idx < rows * D; idx += NT) {
+                const int m = idx / D, j = idx - m * D, c = t.col(j);
+                const float2 u = __ldg(reinterpret_cast<const float2*>(pr + (size_t)idx * 2));
+                float a, la;
+                affine_scale<0>(u.x, a, la);
+                t.xt[m * XS + c] = fwd ? fmaf(a, t.xt[m * XS + c], u.y) : (t.xt[m * XS + c] - u.y) / a;
+            }
+            __syncthreads();
+            continue;
+        }
         if (op.f.kind == B2F_OP_ELEMENTWISE) {
             elementwise_stage(ea, op.f, D);
             __syncthreads();
@@ -594,6 +608,38 @@ __global__ void __launch_bounds__(384) flow_backward_kernel(const __grid_constan
     for (int oi = A.n_ops - 1; oi >= 0; --oi) {
         const BwdOp& op = A.ops[oi];
         if (op.f.kind == B2F_OP_FLIP) { t.flip ^= 1; continue; }
+        if (op.f.kind == B2F_OP_ELEMENTWISE && (op.f.flags & B2F_FLAG_ROW_BIAS)) {
+            // per-row parameters: un-do the layer in place, propagate the gradient, WRITE the parameter gradient per row
+            const float* pr = op.f.p0 + (size_t)row0 * D * 2;
+            const bool fwd = op.f.tkind == B2F_T_AFFINE_FWD;
+            for (int idx = tid; idx < rows * D; idx += NT) {
+                const int m = idx / D, j = idx - m * D, c = t.col(j);
+                const float2 u = __ldg(reinterpret_cast<const float2*>(pr + (size_t)idx * 2));
+                float a, la;
+                affine_scale<0>(u.x, a, la);
+                const float ia = 1.0f / a, zo = t.xt[m * XS + c], gz = b.gt[m * XS + c], GLm = b.GL[m];
+                float du0, du1;
+                if (fwd) {                     // z = a*x + b, ld += log a
+                    const float xi = (zo - u.y) * ia;
+                    du0 = gz * xi + GLm * ia;
+                    du1 = gz;
+                    t.xt[m * XS + c] = xi;
+                    b.gt[m * XS + c] = gz * a;
+                } else {                       // z = (x - b)/a, ld -= log a
+                    du0 = -gz * zo * ia - GLm * ia;
+                    du1 = -gz * ia;
+                    t.xt[m * XS + c] = fmaf(a, zo, u.y);
+                    b.gt[m * XS + c] = gz * ia;
+                }
+                if (op.g0) {
+                    float* gp = op.g0 + ((size_t)row0 * D + idx) * 2;
+                    gp[0] = du0 * (a - kAffineM) * 0.5f;
+                    gp[1] = du1;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         if (op.f.kind == B2F_OP_ELEMENTWISE) {
             elementwise_stage(ea, op.f, D);
             __syncthreads();

@@ -48,7 +48,7 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
         switch (o.kind) {
             case B2F_OP_FLIP: break;
             case B2F_OP_ELEMENTWISE:
-                if (!o.p[0] || (o.tkind != B2F_T_AFFINE_FWD && o.tkind != B2F_T_AFFINE_INV)) return 0;
+                if (!o.p[0] || (o.tkind != B2F_T_AFFINE_FWD && o.tkind != B2F_T_AFFINE_INV) || (o.flags & B2F_FLAG_ROW_BIAS)) return 0;
                 break;
             case B2F_OP_COUPLING: case B2F_OP_MADE: case B2F_OP_MADE_SEQ: {
                 if (!o.p[0] || !o.p[1] || !o.p[2] || !o.p[3] || o.n_hidden <= 0 || o.n_hidden > 32) return 0;

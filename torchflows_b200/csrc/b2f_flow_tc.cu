@@ -511,6 +511,7 @@ int try_launch_flow_tc(const b2f_op_t* ops, int32_t n_ops, const float* x, float
         TcOp& t = A.ops[i];
         t.kind = o.kind; t.tkind = o.tkind; t.H = o.n_hidden; t.boundary = o.boundary; t.flip_before = flip;
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
+        if (o.kind == B2F_OP_ELEMENTWISE && (o.flags & B2F_FLAG_ROW_BIAS)) return 0;     // per-row parameters: generic kernel
         if (o.kind == B2F_OP_ELEMENTWISE) { t.value = (const float*)o.p[0]; continue; }
         if (o.kind != B2F_OP_COUPLING && o.kind != B2F_OP_MADE) return 0;
         if (o.flags & B2F_FLAG_ROW_BIAS) return 0;          // context-conditioned layers: generic kernel

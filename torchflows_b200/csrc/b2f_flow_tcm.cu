@@ -513,6 +513,7 @@ int try_launch_flow_tcm(const b2f_op_t* ops, int32_t n_ops, const float* x, floa
     for (int i = 0; i < n_ops; ++i) {
         const b2f_op_t& o = ops[i];
         if (o.kind == B2F_OP_FLIP) { flip ^= 1; continue; }
+        if (o.kind == B2F_OP_ELEMENTWISE && (o.flags & B2F_FLAG_ROW_BIAS)) return 0;      // per-row parameters: generic kernel
         if (o.kind == B2F_OP_ELEMENTWISE) continue;                 // folded into the blobs by the caller
         if (o.kind != B2F_OP_MADE || !(o.flags & B2F_FLAG_TCM_OPERANDS)) return 0;
         if (o.flags & B2F_FLAG_ROW_BIAS) return 0;
