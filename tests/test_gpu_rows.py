@@ -254,3 +254,27 @@ def test_sequential_spline_folded_operands_agree_with_the_plain_ones():
         err = ((xs.double() - xs0.double()).abs() / (1 + xs0.double().abs())).max().item()
         err_lp = ((lps.double() - lps0.double()).abs() / (1 + lps0.double().abs())).max().item()
         assert err < 2e-3 and err_lp < 1e-4, (quirk, err, err_lp)
+
+
+def test_folded_sequential_operands_fall_back_when_the_rows_kernel_declines():
+    """A 4-byte-aligned input makes the rows kernel decline the program; the library then rejects the folded operands
+    (only the rows kernel takes them) and the host retries with the plain ones on the generic kernel: same samples."""
+    from torchflows_b200 import Flow, _native as N
+    import torchflows_b200.architectures as arch
+    dev = torch.device('cuda:0')
+    torch.manual_seed(9)
+    D, B = 16, 200
+    flow = Flow(arch.MaskedAutoregressiveRQNSF(D)).to(dev).eval()
+    storage = torch.randn(B * D + 1, device=dev)
+    z_misaligned = storage[1:].view(B, D)
+    assert z_misaligned.data_ptr() % 16 != 0
+    z = z_misaligned.clone()
+    with torch.no_grad():
+        xs = flow._sample_from_base(z, no_grad=True)
+        assert N.last_flow_kernel() == N.KERNEL_ROWS
+        xs_m = flow._sample_from_base(z_misaligned, no_grad=True)
+        assert N.last_flow_kernel() == N.KERNEL_GENERIC
+    err = ((xs.double() - xs_m.double()).abs() / (1 + xs.double().abs())).max().item()
+    assert err < 2e-3, err
+    # the layers remember: no second failed launch
+    assert all(getattr(l, '_b2f_no_seq_fold', False) for l in flow.bijection.layers if hasattr(l, 'sequential_log_det_reference_quirk'))
