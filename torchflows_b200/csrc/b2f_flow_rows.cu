@@ -11,17 +11,17 @@ namespace b2f {
 // b2f_flow_rows_rq.cu: the instantiations with sequential spline layers (mode 0 / 1 / 2, hidden width <= 15)
 cudaError_t launch_rows_spline(int mode, int hp4, const RowsArgs& A, unsigned grid, size_t smem, cudaStream_t st);
 
-template <int MODE>
+template <int MODE, int NT>
 static cudaError_t launch_rows_h(const RowsArgs& A, int hp4, unsigned grid, size_t smem, cudaStream_t st) {
     switch (hp4) {
-        case 1: return launch_rows_kernel<MODE, 1, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 2: return launch_rows_kernel<MODE, 2, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 3: return launch_rows_kernel<MODE, 3, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 4: return launch_rows_kernel<MODE, 4, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 5: return launch_rows_kernel<MODE, 5, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 6: return launch_rows_kernel<MODE, 6, false, kRowsThreadsAffine>(A, grid, smem, st);
-        case 7: return launch_rows_kernel<MODE, 7, false, kRowsThreadsAffine>(A, grid, smem, st);
-        default: return launch_rows_kernel<MODE, 8, false, kRowsThreadsAffine>(A, grid, smem, st);
+        case 1: return launch_rows_kernel<MODE, 1, false, NT>(A, grid, smem, st);
+        case 2: return launch_rows_kernel<MODE, 2, false, NT>(A, grid, smem, st);
+        case 3: return launch_rows_kernel<MODE, 3, false, NT>(A, grid, smem, st);
+        case 4: return launch_rows_kernel<MODE, 4, false, NT>(A, grid, smem, st);
+        case 5: return launch_rows_kernel<MODE, 5, false, NT>(A, grid, smem, st);
+        case 6: return launch_rows_kernel<MODE, 6, false, NT>(A, grid, smem, st);
+        case 7: return launch_rows_kernel<MODE, 7, false, NT>(A, grid, smem, st);
+        default: return launch_rows_kernel<MODE, 8, false, NT>(A, grid, smem, st);
     }
 }
 
@@ -78,7 +78,7 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
     if (((XS >> 2) & 1) == 0) XS += 4;     // XS/4 odd: conflict-free 16-byte row accesses across a warp
     const bool spline = Hrq > 0;
     if (spline && (hp4 > 4 || (flags & B2F_FLOW_MODE_PRECISE))) return 0;      // precise splines: generic kernel
-    const int NT = spline ? kRowsThreadsSpline : kRowsThreadsAffine;
+    int NT = spline ? kRowsThreadsSpline : kRowsThreadsAffine;
     // staged weights of every conditioner layer: w1 [n_src][HP] + b1 [HP] + w2 [n_tgt*P][HP] (no w2 for spline layers)
     size_t wtotal = 0;
     for (int i = 0; i < n_ops; ++i) {
@@ -115,9 +115,18 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
     }
     if (inplace) XS = 0;                                           // no tile
     const int rq_stride = spline ? ((Hrq * 24 + 24 + 3) & ~3) : 0;
-    const size_t smem = sizeof(float) * ((size_t)(NT / 32) * 32 * R * XS + (size_t)n_runs * 2 * D + 2 * D + 8 + wtotal +
-                                         (size_t)(NT / 32) * 2 * rq_stride);
-    if (smem > 110 * 1024) return 0;
+    auto smem_for = [&](int nt) {
+        return sizeof(float) * ((size_t)(nt / 32) * 32 * R * XS + (size_t)n_runs * 2 * D + 2 * D + std::max(8, 2 * (nt / 32)) +
+                                wtotal + (size_t)(nt / 32) * 2 * rq_stride);        // (+ [2][warps] partials, >= 8 floats)
+    };
+    if (!spline && !inplace && !getenv("B2F_ROWS_NO_BIG_CTA")) {
+        // tile-limited programs: one big CTA per SM holds more warps than several small ones that each stage the weights
+        const size_t small = smem_for(NT), big = smem_for(kRowsThreadsAffineBig);
+        const size_t warps_small = small <= 110 * 1024 ? std::min<size_t>((227 * 1024) / small, 16) * (NT / 32) : 0;
+        if (big <= 227 * 1024 && (size_t)(kRowsThreadsAffineBig / 32) > warps_small) NT = kRowsThreadsAffineBig;
+    }
+    const size_t smem = smem_for(NT);
+    if (smem > (NT == kRowsThreadsAffineBig ? 227 : 110) * 1024) return 0;
     A.n_ops = n_ops; A.D = D; A.XS = XS; A.B = B; A.flags = flags; A.n_runs = n_runs;
     A.wtotal = (int)wtotal; A.rq_stride = rq_stride; A.inplace = inplace ? 1 : 0;
     A.x = x; A.y = y; A.log_det = log_det; A.log_prob = log_prob; A.base_loc = base_loc; A.base_log_scale = base_log_scale;
@@ -136,8 +145,11 @@ int try_launch_flow_rows(const b2f_op_t* ops, int32_t n_ops, const float* x, flo
     cudaStream_t st = (cudaStream_t)stream;
     const int mode = (flags & B2F_FLOW_MODE_PRECISE) ? 0 : ((flags & B2F_FLOW_MODE_FAST_KNOTS) ? 2 : 1);
     const cudaError_t ce = spline ? launch_rows_spline(mode, hp4, A, (unsigned)grid, smem, st)
-                         : mode == 0 ? launch_rows_h<0>(A, hp4, (unsigned)grid, smem, st)
-                                     : launch_rows_h<1>(A, hp4, (unsigned)grid, smem, st);
+                         : NT == kRowsThreadsAffineBig
+                             ? (mode == 0 ? launch_rows_h<0, kRowsThreadsAffineBig>(A, hp4, (unsigned)grid, smem, st)
+                                          : launch_rows_h<1, kRowsThreadsAffineBig>(A, hp4, (unsigned)grid, smem, st))
+                             : (mode == 0 ? launch_rows_h<0, kRowsThreadsAffine>(A, hp4, (unsigned)grid, smem, st)
+                                          : launch_rows_h<1, kRowsThreadsAffine>(A, hp4, (unsigned)grid, smem, st));
     if (ce != cudaSuccess) return fail(B2F_ERR_CUDA, "flow_rows_kernel: %s", cudaGetErrorString(ce));
     const int rc = check_launch("b2f_flow_apply (rows kernel)");
     return rc == B2F_OK ? 1 : rc;

@@ -663,5 +663,8 @@ static cudaError_t launch_rows_kernel(const RowsArgs& A, unsigned grid, size_t s
 }
 
 constexpr int kRowsThreadsAffine = 128, kRowsThreadsSpline = 64;
+// one-pass affine / shift programs whose row tile, not the register file, limits the resident warps (MAF-128: 17 KB of tile per
+// warp + 25 KB of weights = two 4-warp CTAs per SM): ONE 12-warp CTA shares the weights and fills the shared memory
+constexpr int kRowsThreadsAffineBig = 384;
 
 }  // namespace b2f
