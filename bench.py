@@ -502,9 +502,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def quick_probe(torch, dev, rank, workload, hbm_peak, reps=10):
+def quick_probe(torch, dev, rank, workload, hbm_peak, reps=20):
     """Flow.log_prob / Flow.sample launch times of one of the other BASELINE configurations on this rank's GPU (device
-    events around every call, 3 warm-up calls, median of `reps` timed calls): the numbers their own bench lines report at length."""
+    events, 3 warm-up calls, `reps` timed calls each): the numbers their own bench lines report at length."""
     from torchflows_b200 import _native as N_
     preset, D, B, _, _ = WORKLOADS[workload]
     g = torch.Generator(device=dev).manual_seed(11 + rank)
@@ -518,15 +518,15 @@ def quick_probe(torch, dev, rank, workload, hbm_peak, reps=10):
                 fn()
             kernel = N_.last_flow_kernel()
             torch.cuda.synchronize()
-            # one event pair per call, median: these launches are as short as the host-side cost of issuing them (0.2 ms),
-            # so a single pair around `reps` calls would time the Python loop, not the kernels
-            pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-            for e0, e1 in pairs:
-                e0.record()
+            # one event pair around `reps` back-to-back calls: the queue stays ahead of the GPU as long as a launch takes
+            # longer than issuing it (~0.1 ms of Python per call), which holds for every workload here
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
                 fn()
-                e1.record()
+            e1.record()
             torch.cuda.synchronize()
-            ms = sorted(e0.elapsed_time(e1) for e0, e1 in pairs)[reps // 2]
+            ms = e0.elapsed_time(e1) / reps
             nbytes = by_lp if name == 'log_prob' else by_s
             out[name] = {'launch_ms': ms, 'samples_per_s': B / (ms * 1e-3), 'kernel': KERNEL_IDS.get(kernel, str(kernel)),
                          'hbm_frac': nbytes * B / (ms * 1e-3) / 1e9 / hbm_peak}
