@@ -144,7 +144,7 @@ def test_actnorm_data_init_state_T(golden, dev, idx):
     sd = flow.state_dict()
     for k, v in c['actnorm_T'].items():
         close(sd[k], v, k, 2e-4, 2e-4)
-    close(lp, c['log_prob_T'], 'log_prob_T', 5e-4, 5e-4)
+    close(lp, c['log_prob_T'], 'log_prob_T', LP_TOL, LP_TOL)        # measured: <= 3.4e-6 relative on all 16 cases (scripts/state_t_probe.py)
 
 
 def test_oracle_agrees_on_fresh_inputs(golden, dev):
