@@ -676,6 +676,17 @@ class Flow(BaseFlow):
                 return lp.reshape(batch_shape)
         return self.forward_with_log_prob(x, context)[1]
 
+    def _base_draw_parameters(self):
+        """(loc, log_scale) for the library's base draws, or (None, None) for a standard normal base (both all zero): the
+        kernels then skip the per-draw scale and shift.  One device read per parameter version, cached."""
+        loc, log_scale = self.base.loc, self.base.log_scale
+        key = (loc.data_ptr(), loc._version, log_scale.data_ptr(), log_scale._version)
+        hit = getattr(self, '_b2f_std_base', None)
+        if hit is None or hit[0] != key:
+            hit = (key, not bool(loc.detach().any()) and not bool(log_scale.detach().any()))
+            object.__setattr__(self, '_b2f_std_base', hit)
+        return (None, None) if hit[1] else (loc, log_scale)
+
     def sample(self, sample_shape: Union[int, torch.Size, Tuple[int, ...]], context: torch.Tensor = None,
                no_grad: bool = False, return_log_prob: bool = False):
         """x = bijection.inverse(z), z ~ base.  With ``return_log_prob`` the second output is
@@ -694,9 +705,10 @@ class Flow(BaseFlow):
                     n = 1
                     for d in sample_shape:
                         n *= int(d)
+                    loc, log_scale = self._base_draw_parameters()
                     with torch.no_grad():
                         x2, lp = prog.run_sample_program(ops, n, self.event_size, dev, want_log_prob=return_log_prob,
-                                                         base_loc=self.base.loc, base_log_scale=self.base.log_scale)
+                                                         base_loc=loc, base_log_scale=log_scale)
                     x = x2.reshape(*sample_shape, *self.event_shape)
                     return (x, lp.reshape(sample_shape)) if return_log_prob else x
             z = self.base_sample(sample_shape=sample_shape)
