@@ -1,7 +1,7 @@
 """Randomised parity sweep on the GPU (not part of the test suite): random presets / event sizes / batch sizes / depths /
 weight states against the CPU oracle, and context-conditioned presets fused against composite.  Prints every violation.
 
-    python scripts/fuzz_parity.py [seconds] [seed] [grad]
+    python scripts/fuzz_parity.py [seconds] [seed] [grad|big]
 
 With `grad`: the training loss (flows.py:199-224) and all its gradients against torch autograd through the fp64 oracle
 (context-conditioned presets: fused against composite), relative L2 per tensor.
@@ -82,6 +82,7 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     g = torch.Generator().manual_seed(seed)
     ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    big = len(sys.argv) > 3 and sys.argv[3] == 'big'
     t0, n, bad = time.time(), 0, 0
     while time.time() - t0 < budget:
         preset = PRESETS[ri(0, len(PRESETS) - 1)]
@@ -91,6 +92,8 @@ def main():
         if 'LRS' in preset and seq:
             D = min(D, 16)              # composite D-step loop in Python
         B = [1, 7, 100, 129, 1000, 3000, 20000][ri(0, 6 if D <= 64 and not seq else 4)]
+        if big and D % 32 == 0 and ri(0, 2) == 0:
+            B = [19077, 40000 + ri(0, 127)][ri(0, 1)]          # more 128-row tiles than SMs, ragged tail (persistent kernels)
         n_layers = ri(1, 3)
         state = 'ET'[ri(0, 1)]
         ctx = ri(0, 3) == 0 and 'LRS' not in preset
